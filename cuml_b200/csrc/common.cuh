@@ -1,0 +1,156 @@
+// cuml_b200 internal: error handling, handle, device buffers, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/cuml_b200/kmeans_c.h"
+
+namespace cb2 {
+
+struct Error : public std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define CB2_STR2(x) #x
+#define CB2_STR(x) CB2_STR2(x)
+#define CB2_CUDA(call)                                                                        \
+  do {                                                                                        \
+    cudaError_t e__ = (call);                                                                 \
+    if (e__ != cudaSuccess) {                                                                 \
+      throw ::cb2::Error(CUML_B200_CUDA_ERROR, std::string("CUDA error: ") +                  \
+                                                 cudaGetErrorString(e__) + " at " __FILE__   \
+                                                 ":" CB2_STR(__LINE__) " (" #call ")");       \
+    }                                                                                         \
+  } while (0)
+#define CB2_EXPECTS(cond, msg)                                                                \
+  do {                                                                                        \
+    if (!(cond)) throw ::cb2::Error(CUML_B200_INVALID_ARGUMENT, std::string(msg));            \
+  } while (0)
+#define CB2_CHECK_LAUNCH()                                                                    \
+  do {                                                                                        \
+    ::cb2::count_launch();                                                                    \
+    CB2_CUDA(cudaGetLastError());                                                             \
+  } while (0)
+
+void count_launch();
+int64_t launches();
+void reset_launches();
+
+struct EventPair {
+  cudaEvent_t a, b;
+};
+
+// the sliver of raft::handle_t the k-means path uses
+struct Handle {
+  cudaStream_t stream = nullptr;
+  bool own_stream      = false;
+  void* comm           = nullptr;  // ncclComm_t
+  bool own_comm        = false;
+  int rank             = 0;
+  int n_ranks          = 1;
+  int device           = 0;
+  int sm_count         = 148;
+  size_t smem_optin    = 0;
+  int cc_major = 0, cc_minor = 0;
+  // kernel timing (bench roofline): CUDA events on `stream` around the dominant kernels
+  bool timing = false;
+  std::vector<EventPair> fused_events, update_events;
+  std::vector<EventPair> event_pool;
+  // pinned scalar mailbox for per-iteration convergence read-back
+  double* pinned = nullptr;
+  // solver cached by the lloyd_step measurement hook (freed with the handle)
+  std::shared_ptr<void> step_cache;
+
+  EventPair begin_event();
+  void end_event(EventPair ev, bool fused);
+};
+
+// run a section rank-locally (no collectives) on a handle that carries a communicator
+struct SoloGuard {
+  Handle& h;
+  int n_ranks, rank;
+  void* comm;
+  explicit SoloGuard(Handle& h_) : h(h_), n_ranks(h_.n_ranks), rank(h_.rank), comm(h_.comm)
+  {
+    h.n_ranks = 1;
+    h.rank    = 0;
+    h.comm    = nullptr;
+  }
+  ~SoloGuard()
+  {
+    h.n_ranks = n_ranks;
+    h.rank    = rank;
+    h.comm    = comm;
+  }
+};
+
+template <typename T>
+struct DevBuf {
+  T* p           = nullptr;
+  size_t n       = 0;
+  cudaStream_t s = nullptr;
+  DevBuf() = default;
+  DevBuf(size_t n_, cudaStream_t s_) { alloc(n_, s_); }
+  void alloc(size_t n_, cudaStream_t s_)
+  {
+    release();
+    n = n_;
+    s = s_;
+    if (n) { CB2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), n * sizeof(T), s)); }
+  }
+  void release()
+  {
+    if (p) cudaFreeAsync(p, s);
+    p = nullptr;
+    n = 0;
+  }
+  ~DevBuf() { release(); }
+  DevBuf(const DevBuf&)            = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
+  DevBuf& operator=(DevBuf&& o) noexcept
+  {
+    if (this != &o) {
+      release();
+      p = o.p; n = o.n; s = o.s;
+      o.p = nullptr; o.n = 0;
+    }
+    return *this;
+  }
+  T* get() const { return p; }
+};
+
+inline bool is_device_pointer(const void* ptr)
+{
+  // reference: ML::is_device_or_managed_type, cpp/src/ml_cuda_utils.h:21-33
+  cudaPointerAttributes att{};
+  cudaError_t e = cudaPointerGetAttributes(&att, ptr);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return att.type == cudaMemoryTypeDevice || att.type == cudaMemoryTypeManaged;
+}
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- NCCL (loaded lazily with dlopen; only the MG path needs it) -------------------------
+namespace nccl {
+void allreduce_sum_f64(Handle& h, double* buf, size_t count);
+void allreduce_max_f64(Handle& h, double* buf, size_t count);
+void broadcast_bytes(Handle& h, void* buf, size_t bytes, int root);
+void allgather_bytes(Handle& h, const void* send, void* recv, size_t bytes_per_rank);
+void unique_id(void* out128);
+void init_rank(Handle& h, const void* id128, int rank, int n_ranks);
+void destroy(Handle& h);
+}  // namespace nccl
+
+}  // namespace cb2

@@ -1,0 +1,430 @@
+// Fused pairwise-L2 + argmin for sm_100a (the fusedL2NN role of the reference's cuVS backend,
+// reached from cpp/src/kmeans/kmeans_fit.cu:58-59,153-154 and kmeans_predict.cu:41-42).
+//
+//   label_i = argmin_j ( 1/2 ||c_j||^2 - x_i . c_j )        (first minimum on ties)
+//
+// The x.c contraction runs on the 5th-gen tensor cores (tcgen05.mma kind::tf32, fp32
+// accumulators in TMEM) as 3xTF32:  x.c ~= x_lo.c_hi + x_hi.c_lo + x_hi.c_hi  with
+// hi = fp32 with the 13 low mantissa bits cleared (exactly representable in tf32) and
+// lo = x - hi (exact in fp32).  The result has ~22 mantissa bits: fp32-grade labels.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      A producer : TMA loads of the raw X tile (128 rows x d, 128B-swizzled K-blocks)
+//   warp 2      B producer : TMA loads of centroid hi/lo K-blocks (L2-resident operand buffers)
+//   warps 4-7   converter  : split the raw X tile into hi (in place) and lo tiles in shared memory
+//   warp 1      MMA issuer : one elected thread issues tcgen05.mma, 3 per K=8 step
+//   warps 8-11  epilogue   : tcgen05.ld the 128 x BN accumulator, add 1/2||c||^2, running
+//                            (min, argmin) per row in registers, coalesced label store
+// Pipelines are mbarrier rings: A raw->ready->empty, B full/empty, and two TMEM accumulators
+// (full/empty) so the argmin of N-tile t overlaps the MMAs of N-tile t+1.
+#include <cuda.h>
+
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace cb2 {
+
+namespace {
+
+constexpr int TILE_M       = 128;
+constexpr int KBLOCK       = 32;              // fp32 elements per 128-byte swizzle row
+constexpr int KBLOCK_BYTES = TILE_M * 128;    // one K-block of an A tile: 16 KB
+constexpr int NUM_THREADS  = 384;
+constexpr int MAX_STAGES   = 4;
+constexpr int MAX_A_SLOTS  = 8;
+constexpr int A_SLOT_BYTES = 2 * KBLOCK_BYTES;  // hi then lo
+
+struct FusedParams {
+  int64_t n;
+  int64_t m_tiles;
+  int k_tiles;    // k_pad / bn
+  int kb;         // d_pad / 32
+  int bn;         // centroids per accumulator tile (multiple of 32, <= 256)
+  int a_slots;    // ring of X K-block slots (hi 16 KB + lo 16 KB each); >= kb when k_tiles > 1
+  int b_stages;   // 2..4
+  uint32_t tmem_cols;
+  const float* cnh;  // [k_pad] 1/2 ||c||^2, +inf for padding
+  int32_t* labels;
+  float* dbg_dots;   // optional [n, k_pad] dump of the x.c accumulators (tests only)
+};
+
+struct Barriers {
+  uint64_t a_raw_full[MAX_A_SLOTS], a_ready[MAX_A_SLOTS], a_empty[MAX_A_SLOTS];
+  uint64_t b_full[MAX_STAGES], b_empty[MAX_STAGES];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
+                       const __grid_constant__ CUtensorMap tm_lo, const FusedParams p)
+{
+  extern __shared__ uint8_t smem_dyn[];
+  // 128B-swizzled operand tiles need 1024-byte alignment
+  const uint32_t raw_base = ptx::smem_u32(smem_dyn);
+  const uint32_t base     = (raw_base + 1023u) & ~1023u;
+  uint8_t* gbase          = smem_dyn + (base - raw_base);
+
+  const uint32_t b_half_bytes  = static_cast<uint32_t>(p.bn) * 128u;
+  const uint32_t b_stage_bytes = 2u * b_half_bytes;                                // hi then lo
+  const uint32_t a_base  = base;
+  const uint32_t b_base  = a_base + p.a_slots * A_SLOT_BYTES;
+  const uint32_t cn_off  = p.a_slots * A_SLOT_BYTES + p.b_stages * b_stage_bytes;
+  float* cn_s            = reinterpret_cast<float*>(gbase + cn_off);               // [2][bn]
+  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float));
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_A_SLOTS; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->a_raw_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->a_ready[s]), 128);
+      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 128);
+    }
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->b_empty[s]), 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_x);
+    ptx::prefetch_tmap(&tm_hi);
+    ptx::prefetch_tmap(&tm_lo);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== A producer: raw X K-blocks into the slot ring =====================
+    if (lane == 0) {
+      uint32_t a_cnt = 0;
+      for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
+          const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
+          ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[sa]), pa ^ 1u);
+          const uint32_t full = ptx::smem_u32(&bars->a_raw_full[sa]);
+          ptx::mbar_arrive_expect_tx(full, KBLOCK_BYTES);
+          ptx::tma_load_2d_hint(a_base + sa * A_SLOT_BYTES, &tm_x, kbi * KBLOCK, static_cast<int32_t>(tile * TILE_M),
+                                full, ptx::kEvictFirst);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== B producer: centroid hi/lo K-blocks =====================
+    if (lane == 0) {
+      uint32_t b_cnt = 0;
+      for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        for (int nt = 0; nt < p.k_tiles; ++nt) {
+          for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
+            const uint32_t sb = b_cnt % p.b_stages, pb = (b_cnt / p.b_stages) & 1u;
+            ptx::mbar_wait(ptx::smem_u32(&bars->b_empty[sb]), pb ^ 1u);
+            const uint32_t full = ptx::smem_u32(&bars->b_full[sb]);
+            ptx::mbar_arrive_expect_tx(full, b_stage_bytes);
+            const uint32_t dst = b_base + sb * b_stage_bytes;
+            ptx::tma_load_2d_hint(dst, &tm_hi, kbi * KBLOCK, nt * p.bn, full, ptx::kEvictLast);
+            ptx::tma_load_2d_hint(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, nt * p.bn, full, ptx::kEvictLast);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== converter: raw -> (hi in place, lo) =====================
+    const int ct = threadIdx.x - 128;  // 0..127
+    uint32_t a_cnt = 0;
+    for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
+        const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
+        ptx::mbar_wait(ptx::smem_u32(&bars->a_raw_full[sa]), pa);
+        uint4* hi = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES);
+        uint4* lo = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES);
+#pragma unroll
+        for (int i = 0; i < KBLOCK_BYTES / 16 / 128; ++i) {
+          const int e = ct + i * 128;
+          uint4 v = hi[e];
+          uint4 h, l;
+          h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          hi[e] = h;
+          lo[e] = l;
+        }
+        ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+        ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready[sa]));
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_tf32(TILE_M, p.bn);
+      uint32_t a_cnt0 = 0, b_cnt = 0, acc_cnt = 0;
+      for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, a_cnt0 += p.kb) {
+        for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
+          const uint32_t acc = acc_cnt & 1u, pacc = (acc_cnt >> 1) & 1u;
+          ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * p.bn;
+          for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
+            const uint32_t a_cnt = a_cnt0 + kbi;
+            const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
+            if (nt == 0) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[sa]), pa);  // first use of this X K-block
+            const uint32_t sb = b_cnt % p.b_stages, pb = (b_cnt / p.b_stages) & 1u;
+            ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), pb);
+            ptx::tc_fence_after();
+            const uint64_t da_hi = ptx::umma_desc_sw128(a_base + sa * A_SLOT_BYTES);
+            const uint64_t da_lo = ptx::umma_desc_sw128(a_base + sa * A_SLOT_BYTES + KBLOCK_BYTES);
+            const uint64_t db_hi = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes);
+            const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t adv = static_cast<uint64_t>(ks * 2);  // 8 tf32 = 32 bytes = 2 x 16B units
+              // small terms first, then the dominant hi.hi term
+              ptx::mma_tf32_ss(d_tmem, da_lo + adv, db_hi + adv, idesc, (kbi | ks) != 0 ? 1u : 0u);
+              ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+              ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+            }
+            ptx::mma_commit(ptx::smem_u32(&bars->b_empty[sb]));  // frees the B stage when these MMAs retire
+            // last centroid tile: this X K-block is not needed again -> release its slot early so
+            // the next row tile's load + hi/lo split overlaps the remaining K-blocks
+            if (nt == p.k_tiles - 1) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[sa]));
+          }
+          ptx::mma_commit(ptx::smem_u32(&bars->acc_full[acc]));  // accumulator ready for the epilogue
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue: argmin over the accumulator =====================
+    const int et      = threadIdx.x - 256;   // 0..127 == row within the tile == TMEM lane
+    const int quarter = warp & 3;            // warps 8..11 -> TMEM lanes [32q, 32q+32)
+    uint32_t acc_cnt  = 0;
+    const float inf   = __int_as_float(0x7f800000);
+    for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      float best = inf;
+      int bidx   = 0;
+      for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
+        const uint32_t acc = acc_cnt & 1u, pacc = (acc_cnt >> 1) & 1u;
+        float* cn = cn_s + acc * p.bn;
+        for (int i = et; i < p.bn; i += 128) cn[i] = __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + i);
+        ptx::named_bar_sync(1, 128);
+        ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[acc]), pacc);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.bn;
+        const int jbase      = nt * p.bn;
+        uint32_t r[32];
+        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+          ptx::tmem_ld_32x32(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          if (p.dbg_dots) {
+            const int64_t row = tile * TILE_M + et;
+            if (row < p.n) {
+              float* o = p.dbg_dots + row * (static_cast<int64_t>(p.k_tiles) * p.bn) + jbase + c0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+            }
+          }
+          const float4* cn4 = reinterpret_cast<const float4*>(cn + c0);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 c4 = cn4[q4];
+            float v;
+            v = c4.x - __uint_as_float(r[q4 * 4 + 0]);
+            if (v < best) { best = v; bidx = jbase + c0 + q4 * 4 + 0; }
+            v = c4.y - __uint_as_float(r[q4 * 4 + 1]);
+            if (v < best) { best = v; bidx = jbase + c0 + q4 * 4 + 1; }
+            v = c4.z - __uint_as_float(r[q4 * 4 + 2]);
+            if (v < best) { best = v; bidx = jbase + c0 + q4 * 4 + 2; }
+            v = c4.w - __uint_as_float(r[q4 * 4 + 3]);
+            if (v < best) { best = v; bidx = jbase + c0 + q4 * 4 + 3; }
+          }
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[acc]));
+      }
+      const int64_t row = tile * TILE_M + et;
+      if (row < p.n) p.labels[row] = bidx;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// hi/lo split + half norms of the centroids into padded operand buffers
+__global__ void prepare_centroids_kernel(const float* __restrict__ C, int k, int d, int k_pad, int d_pad,
+                                         float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ cnh)
+{
+  const int j    = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (j >= k_pad) return;
+  double s = 0.0;
+  for (int c = lane; c < d_pad; c += 32) {
+    float v = (j < k && c < d) ? C[static_cast<int64_t>(j) * d + c] : 0.0f;
+    float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    hi[static_cast<int64_t>(j) * d_pad + c] = h;
+    lo[static_cast<int64_t>(j) * d_pad + c] = v - h;
+    s += static_cast<double>(v) * static_cast<double>(v);
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) cnh[j] = (j < k) ? static_cast<float>(0.5 * s) : __int_as_float(0x7f800000);
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CB2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess)
+      throw Error(CUML_B200_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+CUtensorMap make_map_2d(const float* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_cols,
+                        uint32_t box_rows, CUtensorMapL2promotion promo)
+{
+  CUtensorMap m;
+  cuuint64_t dims[2]    = {cols, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2]     = {box_cols, box_rows};
+  cuuint32_t estr[2]    = {1, 1};
+  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    throw Error(CUML_B200_CUDA_ERROR, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+  return m;
+}
+
+struct TilePlan {
+  int kb, bn, a_slots, b_stages;
+  size_t smem;
+};
+
+TilePlan plan_tiles(int d, int k, size_t smem_limit)
+{
+  TilePlan t{};
+  t.kb = static_cast<int>(ceil_div(d, KBLOCK));
+  // widest N tile (<= 256, multiple of 32) covering k with the least padding
+  int bn0 = 256;
+  if (k <= 32) bn0 = 32;
+  else if (k <= 64) bn0 = 64;
+  else if (k <= 128) bn0 = 128;
+  auto bytes = [&](int bn_, int as_, int bs_) {
+    return static_cast<size_t>(as_) * A_SLOT_BYTES + static_cast<size_t>(bs_) * 2 * bn_ * 128 +
+           2 * bn_ * sizeof(float) + sizeof(Barriers) + 1024;
+  };
+  t.bn = 0;
+  for (int bn = bn0; bn >= 32 && t.bn == 0; bn /= 2) {
+    const int k_tiles = static_cast<int>(ceil_div(k, bn));
+    const int a_min   = (k_tiles > 1) ? t.kb : std::min(t.kb, 2);  // all K-blocks stay resident across N tiles
+    // at least 3 B stages when a stage is short (N <= 128), 2 otherwise
+    const int b_min = (bn <= 128) ? 3 : 2;
+    if (bytes(bn, std::max(a_min, 2), b_min) > smem_limit) continue;
+    t.bn       = bn;
+    t.a_slots  = std::max(a_min, 2);
+    t.b_stages = b_min;
+    // spend what is left: first one extra X slot per K-block (full double buffering), then B depth
+    while (t.a_slots < std::min(2 * t.kb, MAX_A_SLOTS) && bytes(bn, t.a_slots + 1, t.b_stages) <= smem_limit) ++t.a_slots;
+    while (t.b_stages < MAX_STAGES && bytes(bn, t.a_slots, t.b_stages + 1) <= smem_limit) ++t.b_stages;
+    t.smem = bytes(bn, t.a_slots, t.b_stages);
+  }
+  return t;
+}
+
+}  // namespace
+
+bool tc_supported(int64_t d, int k)
+{
+  return d >= 4 && d % 4 == 0 && d <= 128 && k >= 1 && k <= (1 << 20);
+}
+
+void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out)
+{
+  TilePlan t = plan_tiles(d, k, h.smem_optin);
+  CB2_EXPECTS(t.bn > 0, "tcgen05 k-means tile plan does not fit shared memory");
+  const int d_pad = t.kb * KBLOCK;
+  const int k_pad = static_cast<int>(ceil_div(k, t.bn)) * t.bn;
+  if (out.k_pad != k_pad || out.d_pad != d_pad || !out.hi.get()) {
+    out.hi.alloc(static_cast<size_t>(k_pad) * d_pad, h.stream);
+    out.lo.alloc(static_cast<size_t>(k_pad) * d_pad, h.stream);
+    out.cnh.alloc(k_pad, h.stream);
+    out.k_pad = k_pad;
+    out.d_pad = d_pad;
+  }
+  out.block_n = t.bn;
+  prepare_centroids_kernel<<<static_cast<unsigned>(ceil_div(k_pad, 8)), 256, 0, h.stream>>>(
+    C, k, d, k_pad, d_pad, out.hi.get(), out.lo.get(), out.cnh.get());
+  CB2_CHECK_LAUNCH();
+}
+
+void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen, int32_t* labels,
+               float* dbg_dots)
+{
+  if (n == 0) return;
+  CB2_EXPECTS(h.cc_major == 10, "the tcgen05 k-means engine needs an sm_100-class GPU (B200)");
+  CB2_EXPECTS(reinterpret_cast<uintptr_t>(X) % 16 == 0, "X must be 16-byte aligned for TMA");
+  TilePlan t = plan_tiles(d, k, h.smem_optin);
+  CB2_EXPECTS(t.bn == cen.block_n, "centroid operand buffers were prepared for a different tile plan");
+
+  FusedParams p{};
+  p.n         = n;
+  p.m_tiles   = ceil_div(n, TILE_M);
+  p.k_tiles   = cen.k_pad / t.bn;
+  p.kb        = t.kb;
+  p.bn        = t.bn;
+  p.a_slots   = t.a_slots;
+  p.b_stages  = t.b_stages;
+  uint32_t cols = 32;
+  while (cols < static_cast<uint32_t>(2 * t.bn)) cols <<= 1;
+  p.tmem_cols = cols;
+  p.cnh       = cen.cnh.get();
+  p.labels    = labels;
+  p.dbg_dots  = dbg_dots;
+
+  CUtensorMap tm_x  = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
+                                  static_cast<uint64_t>(d) * sizeof(float), KBLOCK, TILE_M,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  CUtensorMap tm_hi = make_map_2d(cen.hi.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * sizeof(float),
+                                  KBLOCK, t.bn, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+  CUtensorMap tm_lo = make_map_2d(cen.lo.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * sizeof(float),
+                                  KBLOCK, t.bn, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(h.smem_optin)));
+    attr_set = true;
+  }
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
+  EventPair ev{};
+  if (h.timing) ev = h.begin_event();
+  fused_l2_argmin_kernel<<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+  CB2_CHECK_LAUNCH();
+  if (h.timing) h.end_event(ev, true);
+}
+
+}  // namespace cb2

@@ -1,0 +1,63 @@
+// cuml_b200 internal: launch wrappers implemented in the .cu files.
+#pragma once
+#include "common.cuh"
+
+namespace cb2 {
+
+// ---- generic SIMT distance kernels (fallback shapes, fp64, seeding, transform) -----------
+// labels/mind may be null.  mind = max(0, ||x||^2 + min_j(||c_j||^2 - 2 x.c_j)).
+template <typename T>
+void simt_assign(Handle& h, const T* X, int64_t n, int d, const T* C, int k, const T* cnorm,
+                 int32_t* labels, T* mind);
+// min-update form used by seeding: mind[i] = min(mind[i], dist to nearest of C)
+template <typename T>
+void simt_min_update(Handle& h, const T* X, int64_t n, int d, const T* C, int k, const T* cnorm, T* mind);
+template <typename T>
+void simt_transform(Handle& h, const T* X, int64_t n, int d, const T* C, int k, const T* cnorm,
+                    T* out, bool take_sqrt);
+template <typename T>
+void row_norms(Handle& h, const T* A, int64_t rows, int d, T* out);  // ||a_i||^2
+
+// ---- tcgen05 fused distance + argmin (fp32 via 3xTF32) -------------------------------------
+bool tc_supported(int64_t d, int k);
+struct TcCentroids {           // per-iteration operand buffers (hi/lo split + half norms)
+  DevBuf<float> hi, lo, cnh;
+  int k_pad = 0, d_pad = 0, block_n = 0;
+};
+void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out);
+void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen,
+               int32_t* labels, float* dbg_dots = nullptr);
+
+// ---- M-step: centroid sums / weights / exact inertia ----------------------------------------
+template <typename T>
+struct UpdateWorkspace {
+  DevBuf<T> partial_S;        // [row_blocks][k][d]
+  DevBuf<T> partial_W;        // [row_blocks][k]
+  DevBuf<double> partial_I;   // [row_blocks * slices]
+  int row_blocks = 0, slices = 0, ds = 0, warps = 0;
+  size_t smem = 0;
+  int k = 0, d = 0;
+  bool atomic_path = false;
+};
+template <typename T>
+void update_plan(Handle& h, int64_t n_max, int d, int k, UpdateWorkspace<T>& ws);
+// accumulate one partition into packed (double [k*d + k + 1], S | W | inertia); `accumulate_into`
+// false => packed is overwritten, true => added to (multi-partition).
+template <typename T>
+void update_accumulate(Handle& h, UpdateWorkspace<T>& ws, const T* X, int64_t n, int d, const int32_t* labels,
+                       const T* w, const T* C_old, int k, double* packed, bool accumulate_into,
+                       bool sums /* false: inertia only */);
+// C_new = S/W (W>0) else C_old; shift2 = sum (C_new-C_old)^2 (deterministic, one block)
+template <typename T>
+void finalize_centroids(Handle& h, const double* packed, T* C, int k, int d, double* shift2_out);
+
+// ---- small utilities -----------------------------------------------------------------------
+template <typename T>
+void gather_rows(Handle& h, const T* X, int d, const int64_t* idx_dev, int m, T* out);
+template <typename T>
+double sum_weights(Handle& h, const T* w, int64_t n);  // host result (syncs)
+void labels_to_i64(Handle& h, const int32_t* in, int64_t n, int64_t* out);
+template <typename T>
+void weighted_histogram(Handle& h, const int32_t* labels, const T* w, int64_t n, int k, double* out /*dev, zeroed*/);
+
+}  // namespace cb2

@@ -1,0 +1,503 @@
+// fit / predict / transform drivers and the extern "C" boundary (include/cuml_b200/kmeans_c.h).
+//
+// Mirrors the reference's forwarding layer: pointer residency detection and host->device staging
+// (cpp/src/kmeans/kmeans_fit.cu:101-231, cpp/src/ml_cuda_utils.h:21-33), the partition-list
+// overload (kmeans_fit.cu:23-99,237-318), predict (kmeans_predict.cu:19-135) and transform
+// (kmeans_transform.cu:18-78).  Everything below those shims -- which in the reference is the
+// un-vendored cuVS -- is this library's own CUDA code.
+#include <limits>
+
+#include "lloyd.cuh"
+
+namespace cb2 {
+
+Handle* make_handle(void* stream, void* comm, int rank, int n_ranks);
+void free_handle(Handle* h);
+
+namespace {
+
+thread_local std::string t_last_error;
+
+template <typename F>
+int guarded(F&& f)
+{
+  try {
+    f();
+    return CUML_B200_SUCCESS;
+  } catch (const Error& e) {
+    t_last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    t_last_error = e.what();
+    return CUML_B200_INTERNAL_ERROR;
+  } catch (...) {
+    t_last_error = "unknown error";
+    return CUML_B200_INTERNAL_ERROR;
+  }
+}
+
+void check_params(const cuml_b200_kmeans_params_t& p)
+{
+  CB2_EXPECTS(p.n_clusters > 0, "n_clusters=" + std::to_string(p.n_clusters) + " should be a positive integer.");
+  CB2_EXPECTS(p.max_iter >= 0, "max_iter must be >= 0");
+  CB2_EXPECTS(p.metric == CUML_B200_L2Expanded || p.metric == CUML_B200_L2SqrtExpanded,
+              "only L2Expanded / L2SqrtExpanded metrics are supported by k-means");
+  CB2_EXPECTS(p.init >= 0 && p.init <= 2, "invalid init method");
+  CB2_EXPECTS(p.n_init >= 1, "n_init must be >= 1");
+  CB2_EXPECTS(p.oversampling_factor >= 0.0, "oversampling_factor must be >= 0");
+  CB2_EXPECTS(p.device_buffer_samples >= 0, "device_buffer_samples must be >= 0");
+}
+
+// device-resident view of caller partitions; host partitions are staged into owned buffers
+template <typename T>
+struct Staged {
+  std::vector<Part<T>> parts;
+  std::vector<DevBuf<T>> owned;
+};
+
+template <typename T>
+void stage_parts(Handle& h, const T* const* X_parts, const int64_t* n_parts_rows, int64_t n_parts, int64_t d,
+                 const T* const* w_parts, Staged<T>& out)
+{
+  // residency is decided by the first non-empty partition (reference kmeans_fit.cu:237-246)
+  bool on_device = true;
+  for (int64_t i = 0; i < n_parts; ++i) {
+    if (n_parts_rows[i] > 0) {
+      on_device = is_device_pointer(X_parts[i]);
+      break;
+    }
+  }
+  for (int64_t i = 0; i < n_parts; ++i) {
+    const int64_t n = n_parts_rows[i];
+    CB2_EXPECTS(n >= 0, "negative partition size");
+    if (n == 0) continue;
+    CB2_EXPECTS(X_parts[i] != nullptr, "null partition pointer");
+    const T* wp = w_parts ? w_parts[i] : nullptr;
+    if (on_device) {
+      out.parts.push_back(Part<T>{X_parts[i], n, wp});
+    } else {
+      // host-resident: staged whole.  (The reference streams device_buffer_samples-sized batches;
+      // out-of-core streaming is a "next" row of the scope table.)
+      out.owned.emplace_back(static_cast<size_t>(n) * d, h.stream);
+      T* dx = out.owned.back().get();
+      CB2_CUDA(cudaMemcpyAsync(dx, X_parts[i], sizeof(T) * n * d, cudaMemcpyHostToDevice, h.stream));
+      T* dw = nullptr;
+      if (wp) {
+        out.owned.emplace_back(static_cast<size_t>(n), h.stream);
+        dw = out.owned.back().get();
+        CB2_CUDA(cudaMemcpyAsync(dw, wp, sizeof(T) * n, cudaMemcpyHostToDevice, h.stream));
+      }
+      out.parts.push_back(Part<T>{dx, n, dw});
+    }
+  }
+}
+
+int64_t allreduce_i64_host(Handle& h, int64_t v)
+{
+  if (h.n_ranks <= 1) return v;
+  DevBuf<double> cell(1, h.stream);
+  double dv = static_cast<double>(v);
+  CB2_CUDA(cudaMemcpyAsync(cell.get(), &dv, sizeof(double), cudaMemcpyHostToDevice, h.stream));
+  nccl::allreduce_sum_f64(h, cell.get(), 1);
+  CB2_CUDA(cudaMemcpyAsync(&dv, cell.get(), sizeof(double), cudaMemcpyDeviceToHost, h.stream));
+  CB2_CUDA(cudaStreamSynchronize(h.stream));
+  return static_cast<int64_t>(dv + 0.5);
+}
+
+// exclusive prefix of n_local over ranks
+int64_t rank_row_offset(Handle& h, int64_t n_local)
+{
+  if (h.n_ranks <= 1) return 0;
+  DevBuf<int64_t> sb(1, h.stream), rb(h.n_ranks, h.stream);
+  CB2_CUDA(cudaMemcpyAsync(sb.get(), &n_local, sizeof(int64_t), cudaMemcpyHostToDevice, h.stream));
+  nccl::allgather_bytes(h, sb.get(), rb.get(), sizeof(int64_t));
+  std::vector<int64_t> cnt(h.n_ranks);
+  CB2_CUDA(cudaMemcpyAsync(cnt.data(), rb.get(), sizeof(int64_t) * h.n_ranks, cudaMemcpyDeviceToHost, h.stream));
+  CB2_CUDA(cudaStreamSynchronize(h.stream));
+  int64_t off = 0;
+  for (int i = 0; i < h.rank; ++i) off += cnt[i];
+  return off;
+}
+
+template <typename T>
+void fit_parts_impl(Handle& h, const cuml_b200_kmeans_params_t& params, const T* const* X_parts,
+                    const int64_t* n_parts_rows, int64_t n_parts, int64_t d, const T* const* w_parts, T* centroids,
+                    T& inertia_out, int64_t& n_iter_out)
+{
+  check_params(params);
+  CB2_EXPECTS(d >= 1 && d <= std::numeric_limits<int>::max(), "n_features out of range");
+  CB2_EXPECTS(centroids != nullptr && is_device_pointer(centroids), "centroids must be device accessible");
+  CB2_CUDA(cudaSetDevice(h.device));
+  const int k  = params.n_clusters;
+  const int di = static_cast<int>(d);
+
+  Staged<T> st;
+  stage_parts<T>(h, X_parts, n_parts_rows, n_parts, d, w_parts, st);
+  int64_t n_local = 0;
+  for (auto& p : st.parts) n_local += p.n;
+  const int64_t n_global = allreduce_i64_host(h, n_local);
+  CB2_EXPECTS(n_global >= k, "n_samples=" + std::to_string(n_global) + " should be >= n_clusters=" + std::to_string(k) + ".");
+
+  // weights are normalised so that sum(w) == n_samples (cuVS checkWeight role).  Centroids are
+  // invariant to the scale, so only the inertia is rescaled.
+  bool weighted = false;
+  for (auto& p : st.parts) weighted = weighted || (p.w != nullptr);
+  double wscale = 1.0;
+  if (weighted) {
+    double ws = 0.0;
+    for (auto& p : st.parts) ws += p.w ? sum_weights<T>(h, p.w, p.n) : static_cast<double>(p.n);
+    if (h.n_ranks > 1) {
+      DevBuf<double> cell(1, h.stream);
+      CB2_CUDA(cudaMemcpyAsync(cell.get(), &ws, sizeof(double), cudaMemcpyHostToDevice, h.stream));
+      nccl::allreduce_sum_f64(h, cell.get(), 1);
+      CB2_CUDA(cudaMemcpyAsync(&ws, cell.get(), sizeof(double), cudaMemcpyDeviceToHost, h.stream));
+      CB2_CUDA(cudaStreamSynchronize(h.stream));
+    }
+    CB2_EXPECTS(ws > 0.0, "sample weights must have a positive sum");
+    wscale = static_cast<double>(n_global) / ws;
+  }
+
+  LloydSolver<T> solver(h, st.parts, di, k, ENGINE_AUTO);
+  SeedContext<T> sctx{h, st.parts, di, n_local, n_global, rank_row_offset(h, n_local), params.rng_seed, ENGINE_AUTO};
+
+  const int n_init = (params.init == CUML_B200_INIT_Array) ? 1 : params.n_init;
+  DevBuf<T> trial(static_cast<size_t>(k) * di, h.stream);
+  double best_inertia = std::numeric_limits<double>::infinity();
+  int64_t best_iter   = 0;
+  for (int run = 0; run < n_init; ++run) {
+    T* C = (n_init == 1) ? centroids : trial.get();
+    sctx.seed = params.rng_seed + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(run);
+    if (params.init == CUML_B200_INIT_Array) {
+      // centroids already hold the caller's initial centres
+    } else if (params.init == CUML_B200_INIT_Random) {
+      init_random<T>(sctx, k, C);
+    } else if (params.oversampling_factor == 0.0) {
+      init_kmeans_plus_plus<T>(sctx, k, C);
+    } else {
+      init_scalable<T>(sctx, params, C);
+    }
+    const int64_t iters = solver.run(C, params.max_iter, params.tol);
+    // final E-step + cost with the final centroids
+    solver.assign(C);
+    const double inertia = solver.inertia(C) * wscale;
+    if (inertia < best_inertia || run == 0) {
+      best_inertia = inertia;
+      best_iter    = iters;
+      if (C != centroids)
+        CB2_CUDA(cudaMemcpyAsync(centroids, C, sizeof(T) * k * di, cudaMemcpyDeviceToDevice, h.stream));
+    }
+  }
+  CB2_CUDA(cudaStreamSynchronize(h.stream));
+  inertia_out = static_cast<T>(best_inertia);
+  n_iter_out  = best_iter;
+}
+
+template <typename T, typename LabelT>
+void predict_impl(Handle& h, const cuml_b200_kmeans_params_t& params, const T* centroids, const T* X, int64_t n,
+                  int64_t d, const T* w, bool normalize_weights, LabelT* labels, T& inertia_out)
+{
+  check_params(params);
+  CB2_EXPECTS(n >= 0 && d >= 1, "invalid shape");
+  CB2_EXPECTS(n == 0 || (X && is_device_pointer(X)), "X must be device accessible for predict");
+  CB2_EXPECTS(centroids && is_device_pointer(centroids), "centroids must be device accessible");
+  CB2_EXPECTS(n == 0 || labels != nullptr, "labels must not be null");
+  CB2_CUDA(cudaSetDevice(h.device));
+  const int k = params.n_clusters, di = static_cast<int>(d);
+  if (n == 0) {
+    inertia_out = T(0);
+    return;
+  }
+  SoloGuard solo(h);  // predict is rank-local (no collectives), reference dask/cluster/kmeans.py:237-243
+  std::vector<Part<T>> parts{Part<T>{X, n, w}};
+  LloydSolver<T> solver(h, parts, di, k, ENGINE_AUTO);
+  solver.assign(centroids);
+  double inertia = solver.inertia(centroids);
+  if (w && normalize_weights) {
+    const double ws = sum_weights<T>(h, w, n);
+    CB2_EXPECTS(ws > 0.0, "sample weights must have a positive sum");
+    inertia *= static_cast<double>(n) / ws;
+  }
+  if (std::is_same<LabelT, int32_t>::value) {
+    CB2_CUDA(cudaMemcpyAsync(labels, solver.labels(), sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, h.stream));
+  } else {
+    labels_to_i64(h, solver.labels(), n, reinterpret_cast<int64_t*>(labels));
+  }
+  CB2_CUDA(cudaStreamSynchronize(h.stream));
+  inertia_out = static_cast<T>(inertia);
+}
+
+template <typename T>
+void transform_impl(Handle& h, const cuml_b200_kmeans_params_t& params, const T* centroids, const T* X, int64_t n,
+                    int64_t d, T* X_new)
+{
+  check_params(params);
+  CB2_EXPECTS(n >= 0 && d >= 1, "invalid shape");
+  if (n == 0) return;
+  CB2_EXPECTS(X && is_device_pointer(X), "X must be device accessible for transform");
+  CB2_EXPECTS(centroids && is_device_pointer(centroids), "centroids must be device accessible");
+  CB2_EXPECTS(X_new && is_device_pointer(X_new), "X_new must be device accessible");
+  CB2_CUDA(cudaSetDevice(h.device));
+  const int k = params.n_clusters, di = static_cast<int>(d);
+  DevBuf<T> cn(k, h.stream);
+  row_norms<T>(h, centroids, k, di, cn.get());
+  simt_transform<T>(h, X, n, di, centroids, k, cn.get(), X_new, params.metric == CUML_B200_L2SqrtExpanded);
+  CB2_CUDA(cudaStreamSynchronize(h.stream));
+}
+
+}  // namespace
+}  // namespace cb2
+
+using namespace cb2;
+
+extern "C" {
+
+void cuml_b200_kmeans_params_default(cuml_b200_kmeans_params_t* p)
+{
+  if (!p) return;
+  p->metric                = CUML_B200_L2Expanded;
+  p->n_clusters            = 8;
+  p->init                  = CUML_B200_INIT_KMeansPlusPlus;
+  p->max_iter              = 300;
+  p->tol                   = 1e-4;
+  p->verbosity             = 3;
+  p->rng_seed              = 0;
+  p->rng_base_subsequence  = 0;
+  p->rng_type              = 0;
+  p->n_init                = 1;
+  p->oversampling_factor   = 2.0;
+  p->batch_samples         = 1 << 15;
+  p->batch_centroids       = 0;
+  p->init_size             = 0;
+  p->device_buffer_samples = 0;
+}
+
+int cuml_b200_handle_create(cuml_b200_handle_t** out, void* stream, void* nccl_comm, int rank, int n_ranks)
+{
+  return guarded([&] {
+    CB2_EXPECTS(out != nullptr, "null output handle pointer");
+    *out = reinterpret_cast<cuml_b200_handle_t*>(make_handle(stream, nccl_comm, rank, n_ranks));
+  });
+}
+int cuml_b200_handle_destroy(cuml_b200_handle_t* h)
+{
+  return guarded([&] { free_handle(reinterpret_cast<Handle*>(h)); });
+}
+int cuml_b200_handle_sync(cuml_b200_handle_t* h)
+{
+  return guarded([&] {
+    CB2_EXPECTS(h != nullptr, "null handle");
+    CB2_CUDA(cudaStreamSynchronize(reinterpret_cast<Handle*>(h)->stream));
+  });
+}
+void* cuml_b200_handle_stream(cuml_b200_handle_t* h) { return h ? reinterpret_cast<Handle*>(h)->stream : nullptr; }
+const char* cuml_b200_last_error(void) { return t_last_error.c_str(); }
+const char* cuml_b200_version(void) { return "cuml_b200 0.1.0 (sm_100a)"; }
+
+int cuml_b200_nccl_unique_id(void* id_out)
+{
+  return guarded([&] {
+    CB2_EXPECTS(id_out != nullptr, "null id buffer");
+    nccl::unique_id(id_out);
+  });
+}
+int cuml_b200_handle_init_comm(cuml_b200_handle_t* h, const void* id, int rank, int n_ranks)
+{
+  return guarded([&] {
+    CB2_EXPECTS(h && id, "null handle or id");
+    CB2_EXPECTS(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "invalid rank / n_ranks");
+    nccl::init_rank(*reinterpret_cast<Handle*>(h), id, rank, n_ranks);
+  });
+}
+
+#define HANDLE(h) (*reinterpret_cast<Handle*>(h))
+#define REQUIRE_HANDLE(h) CB2_EXPECTS((h) != nullptr, "null handle")
+
+#define DEFINE_FIT(SUFFIX, T, IDX)                                                                              \
+  int cuml_b200_kmeans_fit_##SUFFIX(cuml_b200_handle_t* h, const cuml_b200_kmeans_params_t* params, const T* X, \
+                                    IDX n_samples, IDX n_features, const T* sample_weight, T* centroids,        \
+                                    T* inertia, IDX* n_iter)                                                    \
+  {                                                                                                             \
+    return guarded([&] {                                                                                        \
+      REQUIRE_HANDLE(h);                                                                                        \
+      CB2_EXPECTS(params && inertia && n_iter, "null argument");                                                \
+      CB2_EXPECTS(n_samples >= 0 && (n_samples == 0 || X != nullptr), "invalid X");                             \
+      const T* xp[1]     = {X};                                                                                 \
+      const T* wp[1]     = {sample_weight};                                                                     \
+      int64_t np[1]      = {static_cast<int64_t>(n_samples)};                                                   \
+      int64_t it         = 0;                                                                                   \
+      fit_parts_impl<T>(HANDLE(h), *params, xp, np, 1, static_cast<int64_t>(n_features),                        \
+                        sample_weight ? wp : nullptr, centroids, *inertia, it);                                 \
+      *n_iter = static_cast<IDX>(it);                                                                           \
+    });                                                                                                         \
+  }
+DEFINE_FIT(f32_i32, float, int32_t)
+DEFINE_FIT(f64_i32, double, int32_t)
+DEFINE_FIT(f32_i64, float, int64_t)
+DEFINE_FIT(f64_i64, double, int64_t)
+
+#define DEFINE_FIT_PARTS(SUFFIX, T)                                                                                \
+  int cuml_b200_kmeans_fit_parts_##SUFFIX(cuml_b200_handle_t* h, const cuml_b200_kmeans_params_t* params,          \
+                                          const T* const* X_parts, const int64_t* n_samples_parts, int64_t n_parts, \
+                                          int64_t n_features, const T* const* sample_weight_parts, T* centroids,   \
+                                          T* inertia, int64_t* n_iter)                                             \
+  {                                                                                                                \
+    return guarded([&] {                                                                                           \
+      REQUIRE_HANDLE(h);                                                                                           \
+      CB2_EXPECTS(params && inertia && n_iter, "null argument");                                                   \
+      CB2_EXPECTS(n_parts >= 0 && (n_parts == 0 || (X_parts && n_samples_parts)), "invalid partition list");       \
+      fit_parts_impl<T>(HANDLE(h), *params, X_parts, n_samples_parts, n_parts, n_features, sample_weight_parts,    \
+                        centroids, *inertia, *n_iter);                                                             \
+    });                                                                                                            \
+  }
+DEFINE_FIT_PARTS(f32, float)
+DEFINE_FIT_PARTS(f64, double)
+
+#define DEFINE_PREDICT(SUFFIX, T, IDX)                                                                             \
+  int cuml_b200_kmeans_predict_##SUFFIX(cuml_b200_handle_t* h, const cuml_b200_kmeans_params_t* params,            \
+                                        const T* centroids, const T* X, IDX n_samples, IDX n_features,             \
+                                        const T* sample_weight, int normalize_weights, IDX* labels, T* inertia)    \
+  {                                                                                                                \
+    return guarded([&] {                                                                                           \
+      REQUIRE_HANDLE(h);                                                                                           \
+      CB2_EXPECTS(params && inertia, "null argument");                                                             \
+      predict_impl<T, IDX>(HANDLE(h), *params, centroids, X, static_cast<int64_t>(n_samples),                      \
+                           static_cast<int64_t>(n_features), sample_weight, normalize_weights != 0, labels,        \
+                           *inertia);                                                                              \
+    });                                                                                                            \
+  }
+DEFINE_PREDICT(f32_i32, float, int32_t)
+DEFINE_PREDICT(f64_i32, double, int32_t)
+DEFINE_PREDICT(f32_i64, float, int64_t)
+DEFINE_PREDICT(f64_i64, double, int64_t)
+
+#define DEFINE_TRANSFORM(SUFFIX, T, IDX)                                                                       \
+  int cuml_b200_kmeans_transform_##SUFFIX(cuml_b200_handle_t* h, const cuml_b200_kmeans_params_t* params,      \
+                                          const T* centroids, const T* X, IDX n_samples, IDX n_features,       \
+                                          T* X_new)                                                            \
+  {                                                                                                            \
+    return guarded([&] {                                                                                       \
+      REQUIRE_HANDLE(h);                                                                                       \
+      CB2_EXPECTS(params != nullptr, "null argument");                                                         \
+      transform_impl<T>(HANDLE(h), *params, centroids, X, static_cast<int64_t>(n_samples),                     \
+                        static_cast<int64_t>(n_features), X_new);                                              \
+    });                                                                                                        \
+  }
+DEFINE_TRANSFORM(f32_i32, float, int32_t)
+DEFINE_TRANSFORM(f64_i32, double, int32_t)
+DEFINE_TRANSFORM(f32_i64, float, int64_t)
+DEFINE_TRANSFORM(f64_i64, double, int64_t)
+
+// ---- measurement / test hooks ----------------------------------------------------------------
+int cuml_b200_kmeans_lloyd_step_f32(cuml_b200_handle_t* h, const float* X, int64_t n, int64_t d, const float* w,
+                                    int32_t k, float* centroids, int32_t* labels, double* sums_out,
+                                    double* shift2_out, int engine)
+{
+  return guarded([&] {
+    REQUIRE_HANDLE(h);
+    CB2_EXPECTS(X && centroids && n > 0 && d > 0 && k > 0, "invalid argument");
+    Handle& hh = HANDLE(h);
+    // the solver (operand buffers, partial tables) is cached on the handle between steps
+    struct Cache {
+      const float* X = nullptr;
+      int64_t n = 0, d = 0;
+      int k = 0, engine = -1;
+      const float* w = nullptr;
+      std::unique_ptr<LloydSolver<float>> solver;
+    };
+    auto cp = std::static_pointer_cast<Cache>(hh.step_cache);
+    if (!cp) {
+      cp            = std::make_shared<Cache>();
+      hh.step_cache = cp;
+    }
+    Cache& cache = *cp;
+    if (!cache.solver || cache.X != X || cache.n != n || cache.d != d || cache.k != k || cache.engine != engine ||
+        cache.w != w) {
+      cache.solver.reset();
+      std::vector<Part<float>> parts{Part<float>{X, n, w}};
+      cache.solver = std::make_unique<LloydSolver<float>>(hh, parts, static_cast<int>(d), k, engine);
+      cache.X = X; cache.n = n; cache.d = d; cache.k = k; cache.engine = engine; cache.w = w;
+    }
+    LloydSolver<float>& s = *cache.solver;
+    s.step(centroids);
+    const size_t cnt = s.packed_count();
+    if (sums_out) CB2_CUDA(cudaMemcpyAsync(sums_out, s.packed(), sizeof(double) * cnt, cudaMemcpyDeviceToDevice, hh.stream));
+    if (shift2_out) CB2_CUDA(cudaMemcpyAsync(shift2_out, s.packed() + cnt, sizeof(double), cudaMemcpyDeviceToDevice, hh.stream));
+    if (labels) CB2_CUDA(cudaMemcpyAsync(labels, s.labels(), sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, hh.stream));
+  });
+}
+
+int cuml_b200_kmeans_assign_f32(cuml_b200_handle_t* h, const float* X, int64_t n, int64_t d, int32_t k,
+                                const float* centroids, int32_t* labels, int engine)
+{
+  return guarded([&] {
+    REQUIRE_HANDLE(h);
+    CB2_EXPECTS(X && centroids && labels && n > 0 && d > 0 && k > 0, "invalid argument");
+    Handle& hh = HANDLE(h);
+    std::vector<Part<float>> parts;  // no owned partitions: labels are written straight to the caller
+    LloydSolver<float> s(hh, parts, static_cast<int>(d), k, engine);
+    if (engine == ENGINE_TC || (engine == ENGINE_AUTO && reinterpret_cast<uintptr_t>(X) % 16 != 0)) {
+      CB2_EXPECTS(reinterpret_cast<uintptr_t>(X) % 16 == 0 || engine != ENGINE_TC, "X must be 16-byte aligned");
+    }
+    s.prepare(centroids);
+    s.assign_one(centroids, X, n, labels);
+  });
+}
+
+int cuml_b200_kmeans_debug_dots_f32(cuml_b200_handle_t* h, const float* X, int64_t n, int64_t d, int32_t k,
+                                    const float* centroids, int32_t* labels, float* dots, int64_t* k_pad_out)
+{
+  return guarded([&] {
+    REQUIRE_HANDLE(h);
+    CB2_EXPECTS(X && centroids && labels && n > 0 && d > 0 && k > 0, "invalid argument");
+    Handle& hh = HANDLE(h);
+    TcCentroids cen;
+    tc_prepare(hh, centroids, k, static_cast<int>(d), cen);
+    if (k_pad_out) *k_pad_out = cen.k_pad;
+    if (dots || labels) tc_assign(hh, X, n, static_cast<int>(d), k, cen, labels, dots);
+    CB2_CUDA(cudaStreamSynchronize(hh.stream));
+  });
+}
+
+void cuml_b200_launch_count_reset(void) { reset_launches(); }
+int64_t cuml_b200_launch_count(void) { return launches(); }
+
+int cuml_b200_kernel_timing_enable(cuml_b200_handle_t* h, int enable)
+{
+  return guarded([&] {
+    REQUIRE_HANDLE(h);
+    Handle& hh = HANDLE(h);
+    hh.timing  = enable != 0;
+    for (auto* v : {&hh.fused_events, &hh.update_events}) {
+      for (auto& e : *v) hh.event_pool.push_back(e);
+      v->clear();
+    }
+  });
+}
+
+int cuml_b200_kernel_timing_read(cuml_b200_handle_t* h, double* fused_ms, int64_t* fused_n, double* update_ms,
+                                 int64_t* update_n)
+{
+  return guarded([&] {
+    REQUIRE_HANDLE(h);
+    Handle& hh = HANDLE(h);
+    CB2_CUDA(cudaStreamSynchronize(hh.stream));
+    auto total = [&](std::vector<EventPair>& v, double* ms, int64_t* cnt) {
+      double s = 0.0;
+      for (auto& e : v) {
+        float t = 0.f;
+        CB2_CUDA(cudaEventElapsedTime(&t, e.a, e.b));
+        s += t;
+      }
+      if (ms) *ms = s;
+      if (cnt) *cnt = static_cast<int64_t>(v.size());
+      for (auto& e : v) hh.event_pool.push_back(e);
+      v.clear();
+    };
+    total(hh.fused_events, fused_ms, fused_n);
+    total(hh.update_events, update_ms, update_n);
+  });
+}
+
+int cuml_b200_kmeans_tc_supported(int64_t d, int32_t k) { return tc_supported(d, k) ? 1 : 0; }
+
+}  // extern "C"

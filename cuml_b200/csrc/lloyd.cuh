@@ -1,0 +1,183 @@
+// cuml_b200 internal: the Lloyd solver over a list of device-resident row partitions.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+
+#include "kernels.cuh"
+
+namespace cb2 {
+
+template <typename T>
+struct Part {
+  const T* X;  // [n, d] device
+  int64_t n;
+  const T* w;  // [n] device or null
+};
+
+enum Engine { ENGINE_AUTO = 0, ENGINE_SIMT = 1, ENGINE_TC = 2 };
+
+inline int engine_from_env(int engine)
+{
+  if (engine != ENGINE_AUTO) return engine;
+  const char* e = std::getenv("CUML_B200_ENGINE");
+  if (!e) return ENGINE_AUTO;
+  if (!std::strcmp(e, "simt")) return ENGINE_SIMT;
+  if (!std::strcmp(e, "tc")) return ENGINE_TC;
+  return ENGINE_AUTO;
+}
+
+// One object per (dataset, k): owns labels, operand buffers and the M-step workspace.
+template <typename T>
+class LloydSolver {
+ public:
+  LloydSolver(Handle& h, std::vector<Part<T>> parts, int d, int k, int engine = ENGINE_AUTO)
+    : h_(h), parts_(std::move(parts)), d_(d), k_(k)
+  {
+    engine      = engine_from_env(engine);
+    n_local_    = 0;
+    int64_t nmx = 0;
+    bool aligned = true;
+    for (auto& p : parts_) {
+      n_local_ += p.n;
+      nmx = std::max(nmx, p.n);
+      if (p.n > 0 && reinterpret_cast<uintptr_t>(p.X) % 16 != 0) aligned = false;
+    }
+    bool tc_ok = std::is_same<T, float>::value && tc_supported(d, k) && h.cc_major == 10 && aligned;
+    if (engine == ENGINE_TC) {
+      CB2_EXPECTS(tc_ok, "tcgen05 engine requested but unsupported for this problem (needs fp32, sm_100, "
+                         "n_features % 4 == 0, n_features <= 128, 16-byte aligned X)");
+    }
+    use_tc_ = (engine == ENGINE_SIMT) ? false : tc_ok;
+    labels_.alloc(static_cast<size_t>(std::max<int64_t>(n_local_, 1)), h.stream);
+    cnorm_.alloc(k, h.stream);
+    packed_.alloc(static_cast<size_t>(k) * d + k + 2, h.stream);
+    update_plan<T>(h, std::max<int64_t>(nmx, 1), d, k, ws_);
+  }
+
+  bool uses_tensor_cores() const { return use_tc_; }
+  int64_t n_local() const { return n_local_; }
+  int32_t* labels() { return labels_.get(); }
+  double* packed() { return packed_.get(); }  // S | W | inertia | shift2
+  size_t packed_count() const { return static_cast<size_t>(k_) * d_ + k_ + 1; }
+
+  // E-step for every partition -> labels_ (concatenated in partition order)
+  void assign(const T* C)
+  {
+    prepare(C);
+    int64_t off = 0;
+    for (auto& p : parts_) {
+      assign_one(C, p.X, p.n, labels_.get() + off);
+      off += p.n;
+    }
+  }
+
+  // E-step on arbitrary rows with the operand buffers of the last prepare()/assign()
+  void prepare(const T* C)
+  {
+    if (use_tc_) {
+      if constexpr (std::is_same<T, float>::value) tc_prepare(h_, C, k_, d_, tc_);
+    } else {
+      row_norms<T>(h_, C, k_, d_, cnorm_.get());
+    }
+  }
+  void assign_one(const T* C, const T* X, int64_t n, int32_t* labels)
+  {
+    if (use_tc_) {
+      if constexpr (std::is_same<T, float>::value) tc_assign(h_, X, n, d_, k_, tc_, labels);
+    } else {
+      simt_assign<T>(h_, X, n, d_, C, k_, cnorm_.get(), labels, nullptr);
+    }
+  }
+
+  // M-step accumulation over all partitions using labels_: packed = S | W | inertia(C)
+  void accumulate(const T* C, bool sums)
+  {
+    int64_t off = 0;
+    bool first  = true;
+    EventPair ev{};
+    if (h_.timing) ev = h_.begin_event();
+    for (auto& p : parts_) {
+      update_accumulate<T>(h_, ws_, p.X, p.n, d_, labels_.get() + off, p.w, C, k_, packed_.get(), !first, sums);
+      first = false;
+      off += p.n;
+    }
+    if (parts_.empty()) CB2_CUDA(cudaMemsetAsync(packed_.get(), 0, packed_count() * sizeof(double), h_.stream));
+    if (h_.timing) h_.end_event(ev, false);
+  }
+
+  // One full Lloyd iteration, centroids updated in place; squared shift left at packed[count]
+  void step(T* C)
+  {
+    assign(C);
+    accumulate(C, true);
+    nccl::allreduce_sum_f64(h_, packed_.get(), packed_count());
+    finalize_centroids<T>(h_, packed_.get(), C, k_, d_, packed_.get() + packed_count());
+  }
+
+  // inertia of the current labelling wrt C (exact difference form), all ranks; host result
+  double inertia(const T* C)
+  {
+    accumulate(C, false);
+    double* cell = packed_.get() + packed_count() - 1;
+    nccl::allreduce_sum_f64(h_, cell, 1);
+    CB2_CUDA(cudaMemcpyAsync(h_.pinned, cell, sizeof(double), cudaMemcpyDeviceToHost, h_.stream));
+    CB2_CUDA(cudaStreamSynchronize(h_.stream));
+    return h_.pinned[0];
+  }
+
+  // Lloyd iterations from the centroids in C (in place).  Returns executed iterations.
+  // Stopping rule of the reference's GPU path: stop after the iteration whose raw squared
+  // centroid shift is < tol (tol <= 0 never stops early and needs no host read-back at all).
+  int64_t run(T* C, int max_iter, double tol)
+  {
+    int64_t it = 0;
+    for (; it < max_iter;) {
+      step(C);
+      ++it;
+      if (tol > 0.0) {
+        CB2_CUDA(cudaMemcpyAsync(h_.pinned, packed_.get() + packed_count(), sizeof(double), cudaMemcpyDeviceToHost,
+                                 h_.stream));
+        CB2_CUDA(cudaStreamSynchronize(h_.stream));
+        if (h_.pinned[0] < tol) break;
+      }
+    }
+    return it;
+  }
+
+ private:
+  Handle& h_;
+  std::vector<Part<T>> parts_;
+  int d_, k_;
+  int64_t n_local_ = 0;
+  bool use_tc_     = false;
+  DevBuf<int32_t> labels_;
+  DevBuf<T> cnorm_;
+  DevBuf<double> packed_;
+  TcCentroids tc_;
+  UpdateWorkspace<T> ws_;
+};
+
+// ---- seeding (seeding.cu) -------------------------------------------------------------------
+template <typename T>
+struct SeedContext {
+  Handle& h;
+  std::vector<Part<T>> parts;
+  int d;
+  int64_t n_local;
+  int64_t n_global;
+  int64_t row_offset;  // global index of this rank's first row
+  uint64_t seed;
+  int engine;
+};
+
+template <typename T>
+void init_random(SeedContext<T>& ctx, int k, T* C);
+template <typename T>
+void init_kmeans_plus_plus(SeedContext<T>& ctx, int k, T* C);  // sequential D^2 sampling (single rank)
+template <typename T>
+void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params, T* C);  // k-means||
+
+}  // namespace cb2
