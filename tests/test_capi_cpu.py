@@ -1,0 +1,114 @@
+"""CPU-only checks of the boundary: the C-ABI library builds for sm_100a, loads, exports every
+symbol include/cuml_b200/kmeans_c.h declares, and fails loudly (no CPU fallback) without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cuml_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return _lib.load()
+
+
+def test_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "cuml_b200", "kmeans_c.h")).read()
+    declared = set(re.findall(r"\b(cuml_b200_[a-z0-9_]+)\s*\(", header))
+    declared -= {"cuml_b200_kmeans_params", "cuml_b200_handle"}
+    assert declared, "no declarations parsed"
+    for sym in sorted(declared):
+        assert hasattr(lib, sym), sym
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+
+
+def test_params_default_match_reference(lib):
+    # reference cpp/include/cuml/cluster/kmeans_params.hpp:17-32
+    p = _lib.default_params()
+    assert (p.metric, p.n_clusters, p.init, p.max_iter) == (0, 8, 0, 300)
+    assert p.tol == 1e-4 and p.n_init == 1 and p.oversampling_factor == 2.0
+    assert p.batch_samples == 1 << 15 and p.batch_centroids == 0
+    assert p.init_size == 0 and p.device_buffer_samples == 0 and p.rng_seed == 0
+
+
+def test_params_struct_layout_matches_header():
+    # field order / C layout (natural alignment): 4x int32, double, int32 (+pad), 2x uint64, ...
+    assert _lib.KMeansParams.metric.offset == 0
+    assert _lib.KMeansParams.tol.offset == 16
+    assert _lib.KMeansParams.rng_seed.offset == 32
+    assert _lib.KMeansParams.oversampling_factor.offset == 56
+    assert _lib.KMeansParams.init_size.offset == 72
+    assert C.sizeof(_lib.KMeansParams) == 88
+
+
+def test_tc_support_predicate(lib):
+    assert lib.cuml_b200_kmeans_tc_supported(64, 256) == 1
+    assert lib.cuml_b200_kmeans_tc_supported(128, 1024) == 1
+    assert lib.cuml_b200_kmeans_tc_supported(30, 8) == 0   # n_features % 4 != 0 -> CUDA-core kernel
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    st = lib.cuml_b200_handle_create(C.byref(h), None, None, 0, 1)
+    assert st == 2  # CUML_B200_CUDA_ERROR
+    assert b"CUDA" in lib.cuml_b200_last_error()
+    from cuml_b200.cluster import KMeans
+    with pytest.raises(Exception):
+        KMeans(n_clusters=2).fit(np.zeros((4, 2), np.float32))
+
+
+def test_product_does_not_import_oracle():
+    # the product path must never route through oracle/ (test infrastructure only)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "cuml_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+                assert "sklearn.cluster" not in src.replace('_cpu_class_path = "sklearn.cluster.KMeans"', "").replace(
+                    "from sklearn.cluster import KMeans as SkKMeans", ""), f
+
+
+def test_estimator_param_mapping():
+    from cuml_b200.cluster import KMeans, KMeansMG
+    p = KMeans(n_clusters=5, init="k-means++", random_state=7)._c_params()
+    assert p.oversampling_factor == 0.0 and p.init == _lib.INIT_KMEANS_PLUS_PLUS and p.n_init == 1
+    p = KMeans(init="random", random_state=7)._c_params()
+    assert p.init == _lib.INIT_RANDOM and p.n_init == 10
+    p = KMeans(init=np.zeros((8, 2)), random_state=7)._c_params()
+    assert p.init == _lib.INIT_ARRAY and p.n_init == 10
+    p = KMeans(init="k-means||", random_state=7, n_init=3)._c_params()
+    assert p.init == _lib.INIT_KMEANS_PLUS_PLUS and p.oversampling_factor == 2.0 and p.n_init == 3
+    with pytest.raises(ValueError, match="random_state"):
+        KMeansMG(handle=None)._c_params()
+    with pytest.raises(ValueError, match="k-means\\+\\+"):
+        KMeansMG(handle=None, init="k-means++", random_state=1)._validate_fit_params()
+    with pytest.raises(ValueError, match="oversampling_factor=0"):
+        KMeansMG(handle=None, oversampling_factor=0, random_state=1)._validate_fit_params()
+    with pytest.raises(ValueError, match="positive integer"):
+        KMeans(n_clusters=0)._validate_fit_params()
+    km = KMeans(n_clusters=3)
+    assert km.get_params()["n_clusters"] == 3
+    km.set_params(n_clusters=4, tol=0.0)
+    assert km.n_clusters == 4 and km.tol == 0.0
+
+
+def test_mg_random_init_split_rule():
+    # reference python/cuml/cuml/cluster/kmeans_mg.py:63-81
+    from cuml_b200.cluster.kmeans_mg import random_init_rows_required, shard_bounds, KMeansMG
+    assert [random_init_rows_required(10, r, 4) for r in range(4)] == [4, 2, 2, 2]
+    assert [random_init_rows_required(3, r, 8) for r in range(8)] == [1, 1, 1, 0, 0, 0, 0, 0]
+    assert sum(random_init_rows_required(256, r, 8) for r in range(8)) == 256
+    est = KMeansMG(handle=None, init="random", n_clusters=10, random_state=0)
+    with pytest.raises(ValueError, match="init='random' requires rank 0"):
+        est.validate(np.zeros((3, 2)), 0, 4)
+    est.validate(np.zeros((4, 2)), 0, 4)
+    b = [shard_bounds(10, r, 4) for r in range(4)]
+    assert b == [(0, 3), (3, 6), (6, 8), (8, 10)]

@@ -1,0 +1,329 @@
+"""GPU parity tests: the CUDA path (through the C-ABI / the estimator) against the CPU oracle,
+the golden fixtures made with the reference's CPU execution path, and size-independent
+properties.  Bars (BASELINE.json): relative inertia <= 1e-5, centroids max|dC|/max|C| <= 1e-4,
+>= 99.99 % label agreement with disagreements only where the exact top-2 gap is below the fp32
+tolerance 2^-20 * (||x||^2 + ||c||^2)."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+FP32_GAP_TOL = 2.0 ** -20
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    from cuml_b200 import _lib
+    lib = _lib.load()
+    h = _lib.Handle()
+    return dict(torch=torch, _lib=_lib, lib=lib, h=h)
+
+
+def _step(env, X, C0, k, engine, w=None):
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    n, d = X.shape
+    Xd = torch.from_numpy(X).cuda()
+    Cd = torch.from_numpy(np.ascontiguousarray(C0)).cuda()
+    wd = torch.from_numpy(w).cuda() if w is not None else None
+    labels = torch.zeros(n, dtype=torch.int32, device="cuda")
+    packed = torch.zeros(k * d + k + 1, dtype=torch.float64, device="cuda")
+    shift = torch.zeros(1, dtype=torch.float64, device="cuda")
+    _lib.check(lib.cuml_b200_kmeans_lloyd_step_f32(h.ptr, Xd.data_ptr(), n, d, wd.data_ptr() if w is not None else None,
+                                                   k, Cd.data_ptr(), labels.data_ptr(), packed.data_ptr(),
+                                                   shift.data_ptr(), engine))
+    h.sync()
+    return labels.cpu().numpy(), packed.cpu().numpy(), Cd.cpu().numpy(), float(shift.item())
+
+
+SHAPES = [(2000, 8, 5), (5000, 32, 16), (3001, 20, 3), (4000, 64, 40), (1500, 7, 9), (20000, 128, 300),
+          (129, 4, 2), (128, 32, 1), (10000, 16, 64), (7000, 96, 130), (9000, 100, 257)]
+
+
+@pytest.mark.parametrize("n,d,k", SHAPES)
+@pytest.mark.parametrize("engine", [1, 2])
+def test_single_lloyd_step_matches_oracle(env, n, d, k, engine):
+    from oracle import blobs, lloyd
+    if engine == 2 and not env["lib"].cuml_b200_kmeans_tc_supported(d, k):
+        pytest.skip("shape not taken by the tensor-core engine")
+    X, centres, _ = blobs.make_blobs(n, d, k)
+    init = blobs.parity_init(centres)
+    lab, packed, C_new, shift2 = _step(env, X, init, k, engine)
+    lab_o, S, W, C_o, inertia, shift_o = lloyd.lloyd_step(X, init)
+    agree, bad = lloyd.label_disagreements_ok(X, init, lab, FP32_GAP_TOL)
+    assert agree >= 0.9999 and bad == 0
+    if agree == 1.0:
+        assert np.abs(packed[:k * d].reshape(k, d) - S).max() / np.abs(S).max() < 1e-5
+        assert np.abs(packed[k * d:k * d + k] - W).max() < 1e-3
+        assert abs(packed[-1] - inertia) / inertia < 1e-6
+        assert np.abs(C_new - C_o).max() / np.abs(C_o).max() < 1e-6
+        assert abs(shift2 - shift_o) <= 1e-4 * max(shift_o, 1e-12)
+
+
+@pytest.mark.parametrize("engine", [1, 2])
+def test_regime2_step_matches_oracle(env, engine):
+    # throughput init (several centroids per blob): single-step check only
+    from oracle import blobs, lloyd
+    X, _, _ = blobs.make_blobs(30000, 32, 16)
+    init = blobs.throughput_init(X, 16)
+    lab, packed, C_new, _ = _step(env, X, init, 16, engine)
+    agree, bad = lloyd.label_disagreements_ok(X, init, lab, FP32_GAP_TOL)
+    assert agree >= 0.9999 and bad == 0
+
+
+def test_weighted_step(env):
+    from oracle import blobs, lloyd
+    X, centres, _ = blobs.make_blobs(6000, 24, 11)
+    init = blobs.parity_init(centres)
+    w = np.random.default_rng(5).uniform(0.25, 4.0, 6000).astype(np.float32)
+    lab, packed, C_new, _ = _step(env, X, init, 11, 0, w=w)
+    _, S, W, C_o, inertia, _ = lloyd.lloyd_step(X, init, w)
+    k, d = 11, 24
+    assert np.abs(packed[:k * d].reshape(k, d) - S).max() / np.abs(S).max() < 1e-5
+    assert np.abs(packed[k * d:k * d + k] - W).max() / W.max() < 1e-5
+    assert abs(packed[-1] - inertia) / inertia < 1e-6
+
+
+def test_tensor_core_dot_accuracy(env):
+    # 3xTF32 on tcgen05: x.c accurate to fp32 level (not tf32 level ~1e-3)
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    rng = np.random.default_rng(0)
+    n, d, k = 1000, 128, 256
+    X = (rng.standard_normal((n, d)) * 5).astype(np.float32)
+    Cc = (rng.standard_normal((k, d)) * 5).astype(np.float32)
+    Xd, Cd = torch.from_numpy(X).cuda(), torch.from_numpy(Cc).cuda()
+    labels = torch.zeros(n, dtype=torch.int32, device="cuda")
+    kp = C.c_int64()
+    _lib.check(lib.cuml_b200_kmeans_debug_dots_f32(h.ptr, Xd.data_ptr(), n, d, k, Cd.data_ptr(), labels.data_ptr(),
+                                                   None, C.byref(kp)))
+    dots = torch.zeros((n, kp.value), dtype=torch.float32, device="cuda")
+    _lib.check(lib.cuml_b200_kmeans_debug_dots_f32(h.ptr, Xd.data_ptr(), n, d, k, Cd.data_ptr(), labels.data_ptr(),
+                                                   dots.data_ptr(), C.byref(kp)))
+    ref = X.astype(np.float64) @ Cc.astype(np.float64).T
+    got = dots.cpu().numpy()[:, :k]
+    scale = np.sqrt((X.astype(np.float64) ** 2).sum(1))[:, None] * np.sqrt((Cc.astype(np.float64) ** 2).sum(1))[None, :]
+    assert (np.abs(got - ref) / scale).max() < 4e-6
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "sk_*.npz"))))
+def test_fit_matches_reference_cpu_path_golden(path):
+    # end-to-end fit vs fixtures generated with the reference's CPU path (tests/golden/make_golden.py)
+    from cuml_b200.cluster import KMeans
+    g = np.load(path)
+    w = g["sample_weight"] if g["sample_weight"].size else None
+    X, init = g["X"], g["init"]
+    n = X.shape[0]
+    km = KMeans(n_clusters=init.shape[0], init=init, max_iter=int(g["max_iter"]), tol=0.0, n_init=1)
+    km.fit(X, sample_weight=w)
+    assert (km.labels_ == g["labels"]).mean() >= 0.9999
+    scale = np.abs(g["centroids64"]).max()
+    assert np.abs(km.cluster_centers_ - g["centroids"]).max() / scale <= 1e-4
+    norm = 1.0 if w is None else n / float(w.astype(np.float64).sum())  # GPU rule: sum(w) = n
+    assert abs(km.inertia_ - float(g["inertia64"]) * norm) / (float(g["inertia64"]) * norm) <= 1e-5
+    assert km.n_iter_ == int(g["max_iter"])  # tol=0 never stops early on the GPU rule
+
+
+def test_fit_c1_shape_vs_live_reference_cpu_path():
+    # BASELINE configs[0] shape at reduced n (the oracle finishes in seconds): regime 1
+    from cuml_b200.cluster import KMeans
+    from oracle import blobs, lloyd, sklearn_ref
+    X, centres, _ = blobs.make_blobs(200000, 32, 16)
+    init = blobs.parity_init(centres)
+    km = KMeans(n_clusters=16, init=init, max_iter=50, tol=0.0, n_init=1).fit(X)
+    sk = sklearn_ref.fit(X, init, max_iter=50, tol=0.0)
+    sk64 = sklearn_ref.fit(X.astype(np.float64), init.astype(np.float64), max_iter=50, tol=0.0)
+    assert abs(km.inertia_ - sk64["inertia"]) / sk64["inertia"] <= 1e-5
+    assert np.abs(km.cluster_centers_ - sk["centroids"]).max() / np.abs(sk["centroids"]).max() <= 1e-4
+    assert (km.labels_ == sk["labels"]).mean() >= 0.9999
+    agree, bad = lloyd.label_disagreements_ok(X, km.cluster_centers_, km.labels_, FP32_GAP_TOL)
+    assert bad == 0
+
+
+def test_fit_stops_on_tolerance_like_oracle():
+    from cuml_b200.cluster import KMeans
+    from oracle import blobs, lloyd
+    X, centres, _ = blobs.make_blobs(20000, 16, 8)
+    init = blobs.parity_init(centres, jitter=2.0)
+    km = KMeans(n_clusters=8, init=init, max_iter=100, tol=1e-6, n_init=1).fit(X)
+    o = lloyd.fit(X, init, max_iter=100, tol=1e-6)
+    assert km.n_iter_ == o["n_iter"]
+    assert abs(km.inertia_ - o["inertia"]) / o["inertia"] <= 1e-5
+
+
+def test_predict_transform_score_match_oracle():
+    from cuml_b200.cluster import KMeans
+    from oracle import blobs, lloyd
+    X, centres, _ = blobs.make_blobs(30000, 64, 50)
+    init = blobs.parity_init(centres)
+    km = KMeans(n_clusters=50, init=init, max_iter=3, tol=0.0, n_init=1).fit(X)
+    Cc = km.cluster_centers_
+    lab_o, inertia_o = lloyd.predict(X, Cc)
+    assert (km.predict(X) == lab_o).mean() >= 0.9999
+    assert abs(-km.score(X) - inertia_o) / inertia_o <= 1e-5
+    T = km.transform(X[:2000])
+    To = lloyd.transform(X[:2000], Cc)
+    assert np.abs(T - To).max() / To.max() < 1e-5
+    # property: argmin of transform == predict (reference test_dask_kmeans.py:234-299)
+    assert (T.argmin(1) == km.predict(X[:2000])).mean() >= 0.9999
+    w = np.random.default_rng(1).uniform(0.5, 2, len(X)).astype(np.float32)
+    _, in_w = lloyd.predict(X, Cc, sample_weight=w)
+    assert abs(-km.score(X, sample_weight=w) - in_w) / in_w <= 1e-5
+
+
+def test_int64_index_overloads(env):
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    from oracle import blobs, lloyd
+    X, centres, _ = blobs.make_blobs(5000, 16, 6)
+    Xd = torch.from_numpy(X).cuda()
+    Cd = torch.from_numpy(blobs.parity_init(centres)).cuda()
+    p = _lib.default_params()
+    p.n_clusters, p.init, p.max_iter, p.tol = 6, _lib.INIT_ARRAY, 5, 0.0
+    inertia, it = C.c_float(), C.c_int64()
+    _lib.check(lib.cuml_b200_kmeans_fit_f32_i64(h.ptr, C.byref(p), Xd.data_ptr(), 5000, 16, None, Cd.data_ptr(),
+                                                C.byref(inertia), C.byref(it)))
+    lab64 = torch.zeros(5000, dtype=torch.int64, device="cuda")
+    _lib.check(lib.cuml_b200_kmeans_predict_f32_i64(h.ptr, C.byref(p), Cd.data_ptr(), Xd.data_ptr(), 5000, 16, None, 1,
+                                                    lab64.data_ptr(), C.byref(inertia)))
+    lab_o, inertia_o = lloyd.predict(X, Cd.cpu().numpy())
+    assert it.value == 5 and (lab64.cpu().numpy() == lab_o).all()
+    assert abs(inertia.value - inertia_o) / inertia_o < 1e-5
+
+
+def test_host_pointer_fit_through_c_abi(env):
+    # ML::kmeans::fit accepts host X (reference kmeans_fit.cu:157-231): same result as device X
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    from oracle import blobs
+    X, centres, _ = blobs.make_blobs(8000, 32, 10)
+    init = blobs.parity_init(centres)
+    p = _lib.default_params()
+    p.n_clusters, p.init, p.max_iter, p.tol = 10, _lib.INIT_ARRAY, 4, 0.0
+    outs = []
+    for host in (True, False):
+        Cd = torch.from_numpy(init).cuda()
+        Xd = torch.from_numpy(X).cuda()
+        inertia, it = C.c_float(), C.c_int32()
+        ptr = X.ctypes.data if host else Xd.data_ptr()
+        _lib.check(lib.cuml_b200_kmeans_fit_f32_i32(h.ptr, C.byref(p), ptr, 8000, 32, None, Cd.data_ptr(),
+                                                    C.byref(inertia), C.byref(it)))
+        outs.append((Cd.cpu().numpy(), inertia.value))
+    assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
+
+
+def test_partition_list_fit_equals_single_array(env):
+    # the partition overload (reference kmeans.hpp:110-130) over ragged + empty partitions
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    from oracle import blobs
+    X, centres, _ = blobs.make_blobs(9000, 32, 12)
+    init = blobs.parity_init(centres)
+    p = _lib.default_params()
+    p.n_clusters, p.init, p.max_iter, p.tol = 12, _lib.INIT_ARRAY, 4, 0.0
+    Xd = torch.from_numpy(X).cuda()
+    C1 = torch.from_numpy(init).cuda()
+    inertia1, it = C.c_float(), C.c_int32()
+    _lib.check(lib.cuml_b200_kmeans_fit_f32_i32(h.ptr, C.byref(p), Xd.data_ptr(), 9000, 32, None, C1.data_ptr(),
+                                                C.byref(inertia1), C.byref(it)))
+    cuts = [0, 1000, 1000, 4097, 9000]
+    parts = [Xd[cuts[i]:cuts[i + 1]].contiguous() for i in range(4)]
+    xp = (C.c_void_p * 4)(*[t.data_ptr() if t.shape[0] else None for t in parts])
+    rows = (C.c_int64 * 4)(*[t.shape[0] for t in parts])
+    C2 = torch.from_numpy(init).cuda()
+    inertia2, it2 = C.c_float(), C.c_int64()
+    _lib.check(lib.cuml_b200_kmeans_fit_parts_f32(h.ptr, C.byref(p), xp, rows, 4, 32, None, C2.data_ptr(),
+                                                  C.byref(inertia2), C.byref(it2)))
+    assert np.abs(C1.cpu().numpy() - C2.cpu().numpy()).max() / np.abs(init).max() < 1e-6
+    assert abs(inertia1.value - inertia2.value) / inertia1.value < 1e-6
+
+
+@pytest.mark.parametrize("init", ["k-means||", "scalable-k-means++", "k-means++", "random"])
+def test_seeded_inits_recover_blobs(init):
+    # reference python/cuml/tests/test_kmeans.py:168-196: ARI >= 0.99 on blobs
+    from sklearn.metrics import adjusted_rand_score
+    from cuml_b200.cluster import KMeans
+    from oracle import blobs
+    X, _, true = blobs.make_blobs(30000, 20, 10)
+    km = KMeans(n_clusters=10, init=init, random_state=11, n_init=10 if init == "random" else 2).fit(X)
+    assert adjusted_rand_score(true, km.labels_) >= 0.99
+    km2 = KMeans(n_clusters=10, init=init, random_state=11, n_init=10 if init == "random" else 2).fit(X)
+    assert np.array_equal(km.cluster_centers_, km2.cluster_centers_)  # same seed -> same model
+
+
+def test_error_messages_match_reference():
+    # reference python/cuml/tests/test_kmeans.py:425-473
+    from cuml_b200.cluster import KMeans
+    X = np.random.default_rng(0).standard_normal((2, 3)).astype(np.float32)
+    with pytest.raises(ValueError, match=r"n_samples=2 should be >= n_clusters=8"):
+        KMeans(n_clusters=8).fit(X)
+    X = np.random.default_rng(0).standard_normal((20, 3)).astype(np.float32)
+    with pytest.raises(ValueError, match=r"does not match the number of clusters"):
+        KMeans(n_clusters=4, init=np.zeros((3, 3), np.float32)).fit(X)
+    with pytest.raises(ValueError, match=r"does not match the number of features"):
+        KMeans(n_clusters=4, init=np.zeros((4, 2), np.float32)).fit(X)
+    km = KMeans(n_clusters=4, init=X[:4].copy(), max_iter=2).fit(X)
+    with pytest.raises(NotImplementedError, match="int64 indexing"):
+        km.n_clusters = 2 ** 29
+        km.transform(np.zeros((8, 3), np.float32))
+
+
+def test_doctest_kat_and_empty_cluster_rule():
+    from cuml_b200.cluster import KMeans
+    X = np.array([[1.0, 1.0], [1.0, 2.0], [3.0, 2.0], [4.0, 3.0]], dtype=np.float32)
+    km = KMeans(n_clusters=2, init=X[[0, 3]].copy(), n_init=1).fit(X)   # kmeans.pyx:464-491
+    assert km.labels_.tolist() == [0, 0, 1, 1]
+    np.testing.assert_allclose(km.cluster_centers_, [[1.0, 1.5], [3.5, 2.5]])
+    X = np.array([[0, 0], [0.5, 0], [0.5, 1], [1, 1]], dtype=np.float32)
+    km = KMeans(n_clusters=2, init=np.array([[0.5, 0.5], [3, 3]], np.float32), max_iter=5, tol=1e-9).fit(X)
+    np.testing.assert_allclose(km.cluster_centers_[1], [3, 3])       # empty cluster keeps its centroid
+    w = np.array([3, 1, 1, 3], np.float32)
+    km = KMeans(n_clusters=2, init=np.array([[0, 0], [1, 1]], np.float32)).fit(X, sample_weight=w)
+    np.testing.assert_allclose(km.inertia_, 0.1875, rtol=1e-6)          # 0.375 * n / sum(w)
+    np.testing.assert_allclose(km.cluster_centers_, [[0.125, 0], [0.875, 1]], rtol=1e-6)
+
+
+def test_sklearn_round_trip_and_pickle():
+    import pickle
+    from cuml_b200.cluster import KMeans
+    from oracle import blobs
+    X, centres, _ = blobs.make_blobs(3000, 8, 4)
+    km = KMeans(n_clusters=4, init=blobs.parity_init(centres), max_iter=5).fit(X)
+    sk = km.as_sklearn()
+    assert (sk.predict(X) == km.labels_).mean() >= 0.999
+    km2 = KMeans.from_sklearn(sk)
+    assert np.array_equal(km2.predict(X), km.predict(X))
+    km3 = pickle.loads(pickle.dumps(km))
+    assert np.array_equal(km3.predict(X), km.predict(X))
+
+
+def test_large_property_checks(env):
+    # size-independent properties at a BASELINE-like scale (C3 shape, 4M rows): counts sum to n,
+    # sums/counts reproduce the centroids, inertia non-increasing over iterations
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    n, d, k = 4_000_000, 64, 256
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    cent = torch.rand((k, d), device="cuda", generator=g) * 20 - 10
+    lab = torch.randint(0, k, (n,), device="cuda", generator=g)
+    X = cent[lab] + torch.randn((n, d), device="cuda", generator=g)
+    Cd = X[torch.randperm(n, device="cuda", generator=g)[:k]].clone()
+    labels = torch.zeros(n, dtype=torch.int32, device="cuda")
+    packed = torch.zeros(k * d + k + 1, dtype=torch.float64, device="cuda")
+    last = None
+    for it in range(4):
+        C_before = Cd.clone()
+        _lib.check(lib.cuml_b200_kmeans_lloyd_step_f32(h.ptr, X.data_ptr(), n, d, None, k, Cd.data_ptr(),
+                                                       labels.data_ptr(), packed.data_ptr(), None, 0))
+        h.sync()
+        W = packed[k * d:k * d + k]
+        assert abs(W.sum().item() - n) < 0.5
+        counts = torch.bincount(labels.long(), minlength=k).double()
+        assert torch.equal(counts, W)
+        S = packed[:k * d].reshape(k, d)
+        S_ref = torch.zeros((k, d), dtype=torch.float64, device="cuda").index_add_(0, labels.long(), X.double())
+        assert (S - S_ref).abs().max().item() / S_ref.abs().max().item() < 1e-6
+        dist = ((X - C_before[labels.long()]).double() ** 2).sum()
+        assert abs(packed[-1].item() - dist.item()) / dist.item() < 1e-6
+        if last is not None:
+            assert packed[-1].item() <= last * (1 + 1e-9)
+        last = packed[-1].item()

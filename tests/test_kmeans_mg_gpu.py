@@ -1,0 +1,72 @@
+"""Multi-GPU (NCCL) test of the row-sharded fit: skipped unless >= 2 GPUs are visible."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q, init_kind):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cuml_b200.cluster.kmeans_mg import KMeansMG, comms_from_torch_distributed, shard_bounds
+    from oracle import blobs
+    n, d, k = 40000, 32, 16
+    X, centres, _ = blobs.make_blobs(n, d, k)
+    lo, hi = shard_bounds(n, rank, world)
+    h = comms_from_torch_distributed()
+    init = blobs.parity_init(centres) if init_kind == "array" else init_kind
+    km = KMeansMG(handle=h, n_clusters=k, init=init, max_iter=10, tol=0.0, random_state=5, n_init=1)
+    # two ragged local partitions per rank
+    mid = lo + (hi - lo) // 3
+    km.fit([X[lo:mid], X[mid:hi]])
+    q.put((rank, km.cluster_centers_, km.inertia_, km.global_inertia_, km.labels_, km.n_iter_))
+    dist.barrier()
+    h.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("init_kind", ["array", "k-means||", "random"])
+def test_two_rank_fit_matches_single_gpu(init_kind):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from cuml_b200.cluster import KMeans
+    from oracle import blobs, lloyd
+    from sklearn.metrics import adjusted_rand_score
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, init_kind)) for r in range(2)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n, d, k = 40000, 32, 16
+    X, centres, true = blobs.make_blobs(n, d, k)
+    assert np.array_equal(outs[0][1], outs[1][1])  # identical centroids on every rank
+    labels = np.concatenate([outs[0][4], outs[1][4]])
+    total_inertia = outs[0][2] + outs[1][2]
+    assert abs(total_inertia - outs[0][3]) / outs[0][3] < 1e-5
+    if init_kind == "array":
+        ref = lloyd.fit(X, blobs.parity_init(centres), max_iter=10, tol=0.0)
+        assert np.abs(outs[0][1] - ref["centroids"]).max() / np.abs(ref["centroids"]).max() <= 1e-4
+        assert abs(total_inertia - ref["inertia"]) / ref["inertia"] <= 1e-5
+        assert (labels == ref["labels"]).mean() >= 0.9999
+    else:
+        assert adjusted_rand_score(true, labels) >= 0.99
