@@ -179,7 +179,11 @@ def run_ours(args):
     if args.n:
         n = args.n
     lib = _lib.load()
+    # a non-default stream shared by torch (events, data generation) and the library handle, so the
+    # CUDA events below bracket exactly the library's launches
+    torch.cuda.set_stream(torch.cuda.Stream())
     stream = torch.cuda.current_stream()
+    assert stream.cuda_stream != 0
     if world > 1:
         h = comms_from_torch_distributed(stream=stream.cuda_stream)
     else:

@@ -35,7 +35,9 @@ def get_handle():
         cache = _tls.handles = {}
     h = cache.get(key)
     if h is None:
-        h = cache[key] = _lib.Handle(stream=stream.cuda_stream)
+        # torch's default stream is the legacy NULL stream: pass cudaStreamLegacy (0x1) explicitly so the
+        # library's work is ordered with torch's (a NULL argument would mean "handle-owned stream")
+        h = cache[key] = _lib.Handle(stream=stream.cuda_stream or 1)
     return h
 
 

@@ -20,6 +20,9 @@ def comms_from_torch_distributed(stream=None):
     """Create a Handle whose NCCL communicator spans the default torch.distributed group."""
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
+    if stream is None:
+        import torch
+        stream = torch.cuda.current_stream().cuda_stream or 1   # 0x1 = cudaStreamLegacy
     h = _lib.Handle(stream=stream, n_ranks=world, rank=rank)
     if world > 1:
         box = [_lib.Handle.nccl_unique_id() if rank == 0 else None]

@@ -190,6 +190,92 @@ __global__ void __launch_bounds__(256) accumulate_kernel(
   }
 }
 
+// exact inertia sum_i w_i ||x_i - c_label(i)||^2 (difference form), rows split across warps, the
+// (small, hot) centroid table gathered through L1.  One fp64 partial per block.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) inertia_kernel(const T* __restrict__ X, int64_t n, int d,
+                                                      const int32_t* __restrict__ labels, const T* __restrict__ w,
+                                                      const T* __restrict__ C, double* __restrict__ partial)
+{
+  __shared__ double red[8];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  int L = 1;
+  while (L < 32 && L * VEC < d) L <<= 1;
+  const int R  = 32 / L;
+  const int g  = lane / L;
+  const int lr = lane % L;
+  const int64_t gwarp  = static_cast<int64_t>(blockIdx.x) * (blockDim.x / 32) + warp;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x / 32);
+  const int n_chunks   = (d + L * VEC - 1) / (L * VEC);
+  double acc = 0.0;
+  for (int64_t rb = gwarp * R * UNROLL; rb < n; rb += nwarps * R * UNROLL) {
+    int lab[UNROLL];
+    T wv[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) {
+      const int64_t r = rb + static_cast<int64_t>(u) * R + g;
+      lab[u] = (r < n) ? labels[r] : 0;
+      wv[u]  = (r < n) ? (w ? w[r] : T(1)) : T(0);
+    }
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int cb = (ch * L + lr) * VEC;
+      T xv[UNROLL][VEC], cv[UNROLL][VEC];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int64_t r = rb + static_cast<int64_t>(u) * R + g;
+        const bool ok   = (r < n) && (cb < d);
+        if (ok && VEC > 1 && cb + VEC <= d) {
+          load_vec<T, VEC>(X + r * d + cb, xv[u]);
+          load_vec<T, VEC>(C + static_cast<int64_t>(lab[u]) * d + cb, cv[u]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) {
+            const bool in = ok && (cb + i < d);
+            xv[u][i] = in ? X[r * d + cb + i] : T(0);
+            cv[u][i] = in ? C[static_cast<int64_t>(lab[u]) * d + cb + i] : T(0);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        T part = T(0);
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const T df = xv[u][i] - cv[u][i];
+          part += df * df;
+        }
+        acc += static_cast<double>(part * wv[u]);
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < blockDim.x / 32; ++i) s += red[i];
+    partial[blockIdx.x] = s;
+  }
+}
+
+__global__ void sum_partials_kernel(const double* __restrict__ partial, int m, double* __restrict__ cell, int accumulate_into)
+{
+  // single thread block, fixed order
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) s += partial[i];
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (threadIdx.x % 32 == 0) red[threadIdx.x / 32] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < blockDim.x / 32; ++i) t += red[i];
+    *cell = accumulate_into ? *cell + t : t;
+  }
+}
+
 // huge-k fallback (table does not fit even one VEC-wide slice): global fp64 atomics
 template <typename T>
 __global__ void accumulate_atomic_kernel(const T* __restrict__ X, int64_t n, int d,
@@ -412,6 +498,26 @@ void update_accumulate(Handle& h, UpdateWorkspace<T>& ws, const T* X, int64_t n,
 }
 
 template <typename T>
+void compute_inertia(Handle& h, const T* X, int64_t n, int d, const int32_t* labels, const T* w, const T* C,
+                     double* cell, bool accumulate_into)
+{
+  if (n == 0) {
+    if (!accumulate_into) CB2_CUDA(cudaMemsetAsync(cell, 0, sizeof(double), h.stream));
+    return;
+  }
+  constexpr int VECW = (sizeof(T) == 4) ? 4 : 2;
+  const bool vec_ok  = (d % VECW == 0) && (reinterpret_cast<uintptr_t>(X) % (VECW * sizeof(T)) == 0) &&
+                      (reinterpret_cast<uintptr_t>(C) % (VECW * sizeof(T)) == 0);
+  const int blocks = static_cast<int>(std::min<int64_t>(static_cast<int64_t>(h.sm_count) * 8, ceil_div(n, 64)));
+  DevBuf<double> partial(blocks, h.stream);
+  if (vec_ok) inertia_kernel<T, VECW><<<blocks, 256, 0, h.stream>>>(X, n, d, labels, w, C, partial.get());
+  else inertia_kernel<T, 1><<<blocks, 256, 0, h.stream>>>(X, n, d, labels, w, C, partial.get());
+  CB2_CHECK_LAUNCH();
+  sum_partials_kernel<<<1, 256, 0, h.stream>>>(partial.get(), blocks, cell, accumulate_into ? 1 : 0);
+  CB2_CHECK_LAUNCH();
+}
+
+template <typename T>
 void finalize_centroids(Handle& h, const double* packed, T* C, int k, int d, double* shift2_out)
 {
   finalize_kernel<T><<<1, 1024, 0, h.stream>>>(packed, C, k, d, shift2_out);
@@ -464,6 +570,8 @@ void weighted_histogram(Handle& h, const int32_t* labels, const T* w, int64_t n,
   template void update_accumulate<T>(Handle&, UpdateWorkspace<T>&, const T*, int64_t, int, const int32_t*,   \
                                      const T*, const T*, int, double*, bool, bool);                          \
   template void finalize_centroids<T>(Handle&, const double*, T*, int, int, double*);                        \
+  template void compute_inertia<T>(Handle&, const T*, int64_t, int, const int32_t*, const T*, const T*,      \
+                                   double*, bool);                                                           \
   template void gather_rows<T>(Handle&, const T*, int, const int64_t*, int, T*);                             \
   template double sum_weights<T>(Handle&, const T*, int64_t);                                                \
   template void weighted_histogram<T>(Handle&, const int32_t*, const T*, int64_t, int, double*);

@@ -1,0 +1,298 @@
+// M-step for fp32 on sm_100a: per-cluster weighted sums and cluster weights in ONE streaming pass
+// over X, TMA-staged, with exclusive table ownership (no atomics of any kind on the hot tile).
+//
+// Roles replaced (cuVS side, reached from reference cpp/src/kmeans/kmeans_fit.cu:58-59,153-154):
+// reduce_rows_by_key (centroid sums) and reduce_cols_by_key (cluster weights).
+//
+// CTA = 1 producer warp + W consumer warps.
+//   producer : one thread streams [TR rows x DS columns] tiles of X (2-D TMA, dense rows) and the
+//              tile's labels (1-D bulk copy) into a 3-stage shared-memory ring; mbarrier full/empty.
+//   consumers: consumer w exclusively owns columns [32w, 32w+32) of the CTA's [k x DS] fp32 table in
+//              shared memory, so no two warps ever touch the same cell.  A warp instruction covers
+//              R = 32/L rows (L lanes x float4 per row); rows in the same instruction that share a
+//              label are ordered with __match_any_sync (segmented in-warp update).
+// The table is written once per CTA to a partials buffer; a second kernel sums the partials in a
+// fixed order in fp64 (deterministic, bitwise identical on every rank after the all-reduce).
+// Memory parallelism comes from the TMA ring (3 tiles in flight per CTA), not from occupancy.
+#include "kernels.cuh"
+#include "ptx.cuh"
+#include "tensormap.cuh"
+
+namespace cb2 {
+
+namespace {
+
+constexpr int NSTAGE = 3;
+
+struct UpdParams {
+  int64_t n;
+  int64_t tiles_total;      // ceil(n / tr)
+  int64_t tiles_per_block;
+  int d, k, ds, cw, tr;
+  uint32_t stage_bytes;     // X tile bytes (tr * ds * 4), multiple of 128
+  const int32_t* labels;    // padded: readable up to n + tr
+  const float* w;           // or null
+  float* partial_S;         // [row_blocks][k][d]
+  float* partial_W;         // [row_blocks][k]
+};
+
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(160)
+accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams p)
+{
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t raw  = ptx::smem_u32(smem_dyn);
+  const uint32_t base = (raw + 127u) & ~127u;
+  uint8_t* g          = smem_dyn + (base - raw);
+  // layout: stages (X tile, labels) | table | wtab | barriers
+  const uint32_t lab_bytes  = static_cast<uint32_t>(p.tr) * 4u;
+  const uint32_t stage_full = p.stage_bytes + ((lab_bytes + 127u) & ~127u);
+  float* tab       = reinterpret_cast<float*>(g + NSTAGE * stage_full);
+  float* wtab      = tab + static_cast<size_t>(p.k) * p.ds;
+  uint64_t* bars   = reinterpret_cast<uint64_t*>(wtab + ((p.k + 3) & ~3));  // full[NSTAGE], empty[NSTAGE]
+
+  const int warp    = threadIdx.x / 32;
+  const int lane    = threadIdx.x % 32;
+  const int nwarps  = blockDim.x / 32;
+  const int ncons   = nwarps - 1;
+  const int slice   = blockIdx.y;
+  const int cs      = slice * p.ds;
+
+  for (int i = threadIdx.x; i < p.k * p.ds; i += blockDim.x) tab[i] = 0.0f;
+  for (int i = threadIdx.x; i < p.k; i += blockDim.x) wtab[i] = 0.0f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars[NSTAGE + s]), ncons);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tm_x);
+  }
+  __syncthreads();
+
+  const int64_t t_begin = static_cast<int64_t>(blockIdx.x) * p.tiles_per_block;
+  const int64_t t_end   = min(p.tiles_total, t_begin + p.tiles_per_block);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int64_t t = t_begin; t < t_end; ++t, ++cnt) {
+        const uint32_t s = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1u;
+        ptx::mbar_wait(ptx::smem_u32(&bars[NSTAGE + s]), ph ^ 1u);
+        const uint32_t full = ptx::smem_u32(&bars[s]);
+        ptx::mbar_arrive_expect_tx(full, p.stage_bytes + lab_bytes);
+        const uint32_t dst = base + s * stage_full;
+        const int64_t row0 = t * p.tr;
+        ptx::tma_load_2d_hint(dst, &tm_x, cs, static_cast<int32_t>(row0), full, ptx::kEvictFirst);
+        bulk_load_1d(dst + p.stage_bytes, p.labels + row0, lab_bytes, full);
+      }
+    }
+  } else {
+    const int cwarp = warp - 1;
+    const int c0    = cwarp * p.cw;                 // first owned column (relative to the slice)
+    const int width = max(0, min(p.ds - c0, p.cw)); // owned columns (multiple of 4)
+    int L = 1;
+    while (L < 32 && L * 4 < width) L <<= 1;
+    const int R  = 32 / L;
+    const int gq = lane / L;
+    const int lr = lane % L;
+    const bool col_ok    = lr * 4 < width;
+    const unsigned below = (gq == 0) ? 0u : ((1u << (gq * L)) - 1u);
+    const bool counts    = (slice == 0 && cwarp == 0 && lr == 0);
+    uint32_t cnt = 0;
+    for (int64_t t = t_begin; t < t_end; ++t, ++cnt) {
+      const uint32_t s = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1u;
+      ptx::mbar_wait(ptx::smem_u32(&bars[s]), ph);
+      const float* xs   = reinterpret_cast<const float*>(g + s * stage_full);
+      const int32_t* ls = reinterpret_cast<const int32_t*>(g + s * stage_full + p.stage_bytes);
+      const int64_t row0 = t * p.tr;
+      const int64_t left = p.n - row0;
+      const int valid    = left < p.tr ? static_cast<int>(left) : p.tr;
+      if (width > 0) {
+#pragma unroll 2
+        for (int r0 = 0; r0 < p.tr; r0 += R) {
+          const int r   = r0 + gq;
+          const bool ok = (r < valid) && col_ok;
+          const int lb  = (r < valid) ? ls[r] : (-1 - gq);
+          float4 x      = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) x = *reinterpret_cast<const float4*>(xs + static_cast<size_t>(r) * p.ds + c0 + lr * 4);
+          float wv = 1.0f;
+          if (p.w != nullptr) {
+            wv = (r < valid) ? __ldg(p.w + row0 + r) : 0.0f;
+            x.x *= wv; x.y *= wv; x.z *= wv; x.w *= wv;
+          }
+          int rank = 0, maxrank = 0;
+          if (R > 1) {
+            const unsigned peers = __match_any_sync(0xffffffffu, lb);
+            rank                 = __popc(peers & below) / L;
+            maxrank              = __reduce_max_sync(0xffffffffu, rank);
+          }
+          for (int rr = 0; rr <= maxrank; ++rr) {
+            if (ok && rank == rr) {
+              float4* cell = reinterpret_cast<float4*>(tab + static_cast<size_t>(lb) * p.ds + c0 + lr * 4);
+              float4 c     = *cell;
+              c.x += x.x; c.y += x.y; c.z += x.z; c.w += x.w;
+              *cell = c;
+              if (counts) wtab[lb] += wv;
+            }
+            if (R > 1) __syncwarp();
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars[NSTAGE + s]));
+    }
+  }
+  __syncthreads();
+  float* outS     = p.partial_S + static_cast<size_t>(blockIdx.x) * p.k * p.d;
+  const int wcols = min(p.ds, p.d - cs);
+  for (int i = threadIdx.x; i < p.k * wcols; i += blockDim.x) {
+    const int j = i / wcols, c = i % wcols;
+    outS[static_cast<size_t>(j) * p.d + cs + c] = tab[static_cast<size_t>(j) * p.ds + c];
+  }
+  if (slice == 0) {
+    float* outW = p.partial_W + static_cast<size_t>(blockIdx.x) * p.k;
+    for (int i = threadIdx.x; i < p.k; i += blockDim.x) outW[i] = wtab[i];
+  }
+}
+
+// packed[e] (+)= sum_b partial[b][e]: fixed order, fp64.  32 elements x 8 partial-lanes per block.
+__global__ void __launch_bounds__(256)
+reduce_partials_f32_kernel(const float* __restrict__ partial_S, const float* __restrict__ partial_W, int row_blocks,
+                           int k, int d, double* __restrict__ packed, int accumulate_into)
+{
+  __shared__ double red[8][33];
+  const int64_t kd    = static_cast<int64_t>(k) * d;
+  const int64_t total = kd + k;
+  const int ex        = threadIdx.x % 32;
+  const int pl        = threadIdx.x / 32;
+  const int64_t e     = static_cast<int64_t>(blockIdx.x) * 32 + ex;
+  double s = 0.0;
+  if (e < total) {
+    const float* src     = (e < kd) ? (partial_S + e) : (partial_W + (e - kd));
+    const int64_t stride = (e < kd) ? kd : k;
+    for (int b = pl; b < row_blocks; b += 8) s += static_cast<double>(src[static_cast<int64_t>(b) * stride]);
+  }
+  red[pl][ex] = s;
+  __syncthreads();
+  if (pl == 0 && e < total) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += red[q][ex];
+    packed[e] = accumulate_into ? packed[e] + t : t;
+  }
+}
+
+}  // namespace
+
+struct TmaUpdatePlan {
+  int ds = 0, cw = 0, tr = 0, warps = 0, slices = 0, ctas_per_sm = 0;
+  size_t smem = 0;
+  uint32_t stage_bytes = 0;
+};
+
+static TmaUpdatePlan plan_tma_update(const Handle& h, int d, int k)
+{
+  TmaUpdatePlan best;
+  int best_score = -1;
+  const size_t sm_total = 228 * 1024;
+  const int cands[]     = {d, 256, 128, 64, 32, 16, 8, 4};
+  for (int ds : cands) {
+    if (ds > d || ds > 256 || ds % 4 != 0 || ds <= 0) continue;
+    if (ds < 16 && d >= 16) continue;  // keep >= 64-byte row segments
+    const size_t table = (static_cast<size_t>(k) * ds + ((k + 3) & ~3)) * 4;
+    const int W        = static_cast<int>(ceil_div(ds, 32));
+    if (W > 4) continue;
+    for (int per_sm = 8; per_sm >= 1; --per_sm) {
+      const size_t budget = std::min<size_t>(h.smem_optin, sm_total / per_sm - 1024);
+      if (table + 256 + 3 * 4096 > budget) continue;
+      size_t stage_budget = (budget - table - 256 - 128) / NSTAGE;
+      stage_budget        = std::min<size_t>(stage_budget, 16384 + 1024);
+      int tr              = static_cast<int>((stage_budget - 128) / (static_cast<size_t>(ds) * 4 + 4));
+      tr                  = std::min(tr, 256);
+      tr -= tr % 32;
+      if (tr < 32) continue;
+      const int score = std::min(per_sm * W, 8) * 16 + std::min(ds, 128) / 16;
+      if (score > best_score) {
+        best_score       = score;
+        best.ds          = ds;
+        best.cw          = std::min(ds, 32);
+        best.tr          = tr;
+        best.warps       = W;
+        best.slices      = static_cast<int>(ceil_div(d, ds));
+        best.ctas_per_sm = per_sm;
+        best.stage_bytes = static_cast<uint32_t>(tr) * ds * 4;
+        const uint32_t lab = (static_cast<uint32_t>(tr) * 4 + 127u) & ~127u;
+        best.smem = NSTAGE * (best.stage_bytes + lab) + table + 2 * NSTAGE * 8 + 128 + 64;
+      }
+      break;  // the largest per_sm that fits for this ds
+    }
+  }
+  return best;
+}
+
+bool tma_update_supported(const Handle& h, int d, int k)
+{
+  if (h.cc_major < 9 || d % 4 != 0) return false;
+  return plan_tma_update(h, d, k).ds > 0;
+}
+
+// sums + weights of one partition into packed[0 .. k*d+k) (the inertia cell is left untouched)
+void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const int32_t* labels_padded, const float* w,
+                           int k, DevBuf<float>& partial_S, DevBuf<float>& partial_W, double* packed,
+                           bool accumulate_into)
+{
+  const int64_t total = static_cast<int64_t>(k) * d + k;
+  if (n == 0) {
+    if (!accumulate_into) CB2_CUDA(cudaMemsetAsync(packed, 0, total * sizeof(double), h.stream));
+    return;
+  }
+  TmaUpdatePlan pl = plan_tma_update(h, d, k);
+  CB2_EXPECTS(pl.ds > 0, "no shared-memory plan for the TMA centroid update");
+  UpdParams p{};
+  p.n           = n;
+  p.d           = d;
+  p.k           = k;
+  p.ds          = pl.ds;
+  p.cw          = pl.cw;
+  p.tr          = pl.tr;
+  p.stage_bytes = pl.stage_bytes;
+  p.tiles_total = ceil_div(n, pl.tr);
+  int64_t row_blocks = std::max<int64_t>(1, static_cast<int64_t>(h.sm_count) * pl.ctas_per_sm / pl.slices);
+  row_blocks         = std::min<int64_t>(row_blocks, p.tiles_total);
+  // bound the partials traffic (row_blocks * k * d * 8 bytes) to ~1/8 of the X traffic
+  row_blocks = std::min<int64_t>(row_blocks, std::max<int64_t>(1, n / (16 * static_cast<int64_t>(k)) + 1));
+  p.tiles_per_block = ceil_div(p.tiles_total, row_blocks);
+  row_blocks        = ceil_div(p.tiles_total, p.tiles_per_block);
+  if (partial_S.n < static_cast<size_t>(row_blocks) * k * d) partial_S.alloc(static_cast<size_t>(row_blocks) * k * d, h.stream);
+  if (partial_W.n < static_cast<size_t>(row_blocks) * k) partial_W.alloc(static_cast<size_t>(row_blocks) * k, h.stream);
+  p.labels    = labels_padded;
+  p.w         = w;
+  p.partial_S = partial_S.get();
+  p.partial_W = partial_W.get();
+
+  CUtensorMap tm = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
+                               static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(pl.ds),
+                               static_cast<uint32_t>(pl.tr), CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB2_CUDA(cudaFuncSetAttribute(accumulate_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(h.smem_optin)));
+    attr_set = true;
+  }
+  dim3 grid(static_cast<unsigned>(row_blocks), static_cast<unsigned>(pl.slices));
+  accumulate_tma_kernel<<<grid, (pl.warps + 1) * 32, pl.smem, h.stream>>>(tm, p);
+  CB2_CHECK_LAUNCH();
+  reduce_partials_f32_kernel<<<static_cast<unsigned>(ceil_div(total, 32)), 256, 0, h.stream>>>(
+    partial_S.get(), partial_W.get(), static_cast<int>(row_blocks), k, d, packed, accumulate_into ? 1 : 0);
+  CB2_CHECK_LAUNCH();
+}
+
+}  // namespace cb2

@@ -17,10 +17,9 @@
 //                            (min, argmin) per row in registers, coalesced label store
 // Pipelines are mbarrier rings: A raw->ready->empty, B full/empty, and two TMEM accumulators
 // (full/empty) so the argmin of N-tile t overlaps the MMAs of N-tile t+1.
-#include <cuda.h>
-
 #include "kernels.cuh"
 #include "ptx.cuh"
+#include "tensormap.cuh"
 
 namespace cb2 {
 
@@ -42,6 +41,7 @@ struct FusedParams {
   int bn;         // centroids per accumulator tile (multiple of 32, <= 256)
   int a_slots;    // ring of X K-block slots (hi 16 KB + lo 16 KB each); >= kb when k_tiles > 1
   int b_stages;   // 2..4
+  int b_resident; // all k_tiles*kb centroid blocks fit the B stages: load once, never release
   uint32_t tmem_cols;
   const float* cnh;  // [k_pad] 1/2 ||c||^2, +inf for padding
   int32_t* labels;
@@ -126,6 +126,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     if (lane == 0) {
       uint32_t b_cnt = 0;
       for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        if (p.b_resident && tile != blockIdx.x) break;  // resident centroids: loaded once per CTA
         for (int nt = 0; nt < p.k_tiles; ++nt) {
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sb = b_cnt % p.b_stages, pb = (b_cnt / p.b_stages) & 1u;
@@ -181,8 +182,14 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             const uint32_t a_cnt = a_cnt0 + kbi;
             const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
             if (nt == 0) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[sa]), pa);  // first use of this X K-block
-            const uint32_t sb = b_cnt % p.b_stages, pb = (b_cnt / p.b_stages) & 1u;
-            ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), pb);
+            uint32_t sb = b_cnt % p.b_stages;
+            const uint32_t pb = (b_cnt / p.b_stages) & 1u;
+            if (p.b_resident) {
+              sb = nt * p.kb + kbi;
+              if (tile == static_cast<int64_t>(blockIdx.x)) ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), 0u);
+            } else {
+              ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), pb);
+            }
             ptx::tc_fence_after();
             const uint64_t da_hi = ptx::umma_desc_sw128(a_base + sa * A_SLOT_BYTES);
             const uint64_t da_lo = ptx::umma_desc_sw128(a_base + sa * A_SLOT_BYTES + KBLOCK_BYTES);
@@ -196,7 +203,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
               ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
               ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
             }
-            ptx::mma_commit(ptx::smem_u32(&bars->b_empty[sb]));  // frees the B stage when these MMAs retire
+            if (!p.b_resident) ptx::mma_commit(ptx::smem_u32(&bars->b_empty[sb]));  // frees the B stage
             // last centroid tile: this X K-block is not needed again -> release its slot early so
             // the next row tile's load + hi/lo split overlaps the remaining K-blocks
             if (nt == p.k_tiles - 1) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[sa]));
@@ -284,43 +291,8 @@ __global__ void prepare_centroids_kernel(const float* __restrict__ C, int k, int
   if (lane == 0) cnh[j] = (j < k) ? static_cast<float>(0.5 * s) : __int_as_float(0x7f800000);
 }
 
-// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn()
-{
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    CB2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-    if (!p || q != cudaDriverEntryPointSuccess)
-      throw Error(CUML_B200_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
-CUtensorMap make_map_2d(const float* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes, uint32_t box_cols,
-                        uint32_t box_rows, CUtensorMapL2promotion promo)
-{
-  CUtensorMap m;
-  cuuint64_t dims[2]    = {cols, rows};
-  cuuint64_t strides[1] = {row_stride_bytes};
-  cuuint32_t box[2]     = {box_cols, box_rows};
-  cuuint32_t estr[2]    = {1, 1};
-  CUresult r = encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    throw Error(CUML_B200_CUDA_ERROR, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
-  return m;
-}
-
 struct TilePlan {
-  int kb, bn, a_slots, b_stages;
+  int kb, bn, a_slots, b_stages, b_resident;
   size_t smem;
 };
 
@@ -347,9 +319,16 @@ TilePlan plan_tiles(int d, int k, size_t smem_limit)
     t.bn       = bn;
     t.a_slots  = std::max(a_min, 2);
     t.b_stages = b_min;
-    // spend what is left: first one extra X slot per K-block (full double buffering), then B depth
-    while (t.a_slots < std::min(2 * t.kb, MAX_A_SLOTS) && bytes(bn, t.a_slots + 1, t.b_stages) <= smem_limit) ++t.a_slots;
-    while (t.b_stages < MAX_STAGES && bytes(bn, t.a_slots, t.b_stages + 1) <= smem_limit) ++t.b_stages;
+    // resident centroids: when every (N tile, K block) fits its own B stage they are loaded once per CTA
+    if (k_tiles * t.kb <= MAX_STAGES && bytes(bn, t.a_slots, k_tiles * t.kb) <= smem_limit) {
+      t.b_stages   = k_tiles * t.kb;
+      t.b_resident = 1;
+    }
+    // spend what is left: X slots first (two row tiles in flight, or >= ~48 KB of loads in flight when
+    // the tile is small), then B depth
+    const int a_want = std::min(MAX_A_SLOTS, std::max(2 * t.kb, 6));
+    while (t.a_slots < a_want && bytes(bn, t.a_slots + 1, t.b_stages) <= smem_limit) ++t.a_slots;
+    while (!t.b_resident && t.b_stages < MAX_STAGES && bytes(bn, t.a_slots, t.b_stages + 1) <= smem_limit) ++t.b_stages;
     t.smem = bytes(bn, t.a_slots, t.b_stages);
   }
   return t;
@@ -398,6 +377,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   p.bn        = t.bn;
   p.a_slots   = t.a_slots;
   p.b_stages  = t.b_stages;
+  p.b_resident = t.b_resident;
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(2 * t.bn)) cols <<= 1;
   p.tmem_cols = cols;
@@ -407,11 +387,11 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
 
   CUtensorMap tm_x  = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
                                   static_cast<uint64_t>(d) * sizeof(float), KBLOCK, TILE_M,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   CUtensorMap tm_hi = make_map_2d(cen.hi.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * sizeof(float),
-                                  KBLOCK, t.bn, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+                                  KBLOCK, t.bn, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   CUtensorMap tm_lo = make_map_2d(cen.lo.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * sizeof(float),
-                                  KBLOCK, t.bn, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+                                  KBLOCK, t.bn, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 
   static bool attr_set = false;
   if (!attr_set) {

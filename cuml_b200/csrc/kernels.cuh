@@ -47,6 +47,15 @@ template <typename T>
 void update_accumulate(Handle& h, UpdateWorkspace<T>& ws, const T* X, int64_t n, int d, const int32_t* labels,
                        const T* w, const T* C_old, int k, double* packed, bool accumulate_into,
                        bool sums /* false: inertia only */);
+// exact inertia of a labelling wrt C into *cell (fp64), deterministic
+template <typename T>
+void compute_inertia(Handle& h, const T* X, int64_t n, int d, const int32_t* labels, const T* w, const T* C,
+                     double* cell, bool accumulate_into);
+// fp32 TMA-staged sums/weights (centroid_update_tma.cu); labels must be readable up to n + 256
+bool tma_update_supported(const Handle& h, int d, int k);
+void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const int32_t* labels_padded, const float* w,
+                           int k, DevBuf<float>& partial_S, DevBuf<float>& partial_W, double* packed,
+                           bool accumulate_into);
 // C_new = S/W (W>0) else C_old; shift2 = sum (C_new-C_old)^2 (deterministic, one block)
 template <typename T>
 void finalize_centroids(Handle& h, const double* packed, T* C, int k, int d, double* shift2_out);

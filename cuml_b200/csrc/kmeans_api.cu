@@ -418,7 +418,7 @@ int cuml_b200_kmeans_lloyd_step_f32(cuml_b200_handle_t* h, const float* X, int64
       cache.X = X; cache.n = n; cache.d = d; cache.k = k; cache.engine = engine; cache.w = w;
     }
     LloydSolver<float>& s = *cache.solver;
-    s.step(centroids);
+    s.step(centroids, sums_out != nullptr);
     const size_t cnt = s.packed_count();
     if (sums_out) CB2_CUDA(cudaMemcpyAsync(sums_out, s.packed(), sizeof(double) * cnt, cudaMemcpyDeviceToDevice, hh.stream));
     if (shift2_out) CB2_CUDA(cudaMemcpyAsync(shift2_out, s.packed() + cnt, sizeof(double), cudaMemcpyDeviceToDevice, hh.stream));

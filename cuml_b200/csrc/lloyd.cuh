@@ -51,27 +51,44 @@ class LloydSolver {
                          "n_features % 4 == 0, n_features <= 128, 16-byte aligned X)");
     }
     use_tc_ = (engine == ENGINE_SIMT) ? false : tc_ok;
-    labels_.alloc(static_cast<size_t>(std::max<int64_t>(n_local_, 1)), h.stream);
+    // label storage: every partition starts on a 16-byte boundary and the tail is padded so the
+    // M-step's bulk copies may read one tile past the end
+    int64_t off = 0;
+    for (auto& p : parts_) {
+      label_off_.push_back(off);
+      off += (p.n + 3) & ~int64_t(3);
+    }
+    labels_.alloc(static_cast<size_t>(off + 512), h.stream);
+    CB2_CUDA(cudaMemsetAsync(labels_.get(), 0, (off + 512) * sizeof(int32_t), h.stream));
     cnorm_.alloc(k, h.stream);
     packed_.alloc(static_cast<size_t>(k) * d + k + 2, h.stream);
-    update_plan<T>(h, std::max<int64_t>(nmx, 1), d, k, ws_);
+    use_tma_update_ = false;
+    if constexpr (std::is_same<T, float>::value) {
+      use_tma_update_ = aligned && tma_update_supported(h, d, k) && engine != ENGINE_SIMT;
+    }
+    if (!use_tma_update_) update_plan<T>(h, std::max<int64_t>(nmx, 1), d, k, ws_);
   }
 
   bool uses_tensor_cores() const { return use_tc_; }
   int64_t n_local() const { return n_local_; }
-  int32_t* labels() { return labels_.get(); }
+  int32_t* labels(size_t part = 0) { return labels_.get() + label_off_[part]; }
+  // copy the labels of all partitions, densely concatenated, to out (device)
+  void export_labels(int32_t* out)
+  {
+    int64_t o = 0;
+    for (size_t i = 0; i < parts_.size(); ++i) {
+      CB2_CUDA(cudaMemcpyAsync(out + o, labels(i), sizeof(int32_t) * parts_[i].n, cudaMemcpyDeviceToDevice, h_.stream));
+      o += parts_[i].n;
+    }
+  }
   double* packed() { return packed_.get(); }  // S | W | inertia | shift2
   size_t packed_count() const { return static_cast<size_t>(k_) * d_ + k_ + 1; }
 
-  // E-step for every partition -> labels_ (concatenated in partition order)
+  // E-step for every partition -> labels
   void assign(const T* C)
   {
     prepare(C);
-    int64_t off = 0;
-    for (auto& p : parts_) {
-      assign_one(C, p.X, p.n, labels_.get() + off);
-      off += p.n;
-    }
+    for (size_t i = 0; i < parts_.size(); ++i) assign_one(C, parts_[i].X, parts_[i].n, labels(i));
   }
 
   // E-step on arbitrary rows with the operand buffers of the last prepare()/assign()
@@ -92,27 +109,46 @@ class LloydSolver {
     }
   }
 
-  // M-step accumulation over all partitions using labels_: packed = S | W | inertia(C)
-  void accumulate(const T* C, bool sums)
+  // M-step accumulation over all partitions using the current labels: packed = S | W | inertia.
+  // The inertia cell (wrt C, exact difference form) is only filled when with_inertia is set; the
+  // Lloyd loop itself does not need it (the stopping rule is the centroid shift).
+  void accumulate(const T* C, bool with_inertia)
   {
-    int64_t off = 0;
-    bool first  = true;
     EventPair ev{};
     if (h_.timing) ev = h_.begin_event();
-    for (auto& p : parts_) {
-      update_accumulate<T>(h_, ws_, p.X, p.n, d_, labels_.get() + off, p.w, C, k_, packed_.get(), !first, sums);
-      first = false;
-      off += p.n;
-    }
+    double* inertia_cell = packed_.get() + packed_count() - 1;
     if (parts_.empty()) CB2_CUDA(cudaMemsetAsync(packed_.get(), 0, packed_count() * sizeof(double), h_.stream));
+    bool need_separate_inertia = with_inertia;
+    if (use_tma_update_) {
+      if constexpr (std::is_same<T, float>::value) {
+        for (size_t i = 0; i < parts_.size(); ++i)
+          tma_update_accumulate(h_, parts_[i].X, parts_[i].n, d_, labels(i), parts_[i].w, k_, tma_S_, tma_W_,
+                                packed_.get(), i != 0);
+      }
+      if (!with_inertia) CB2_CUDA(cudaMemsetAsync(inertia_cell, 0, sizeof(double), h_.stream));
+    } else {
+      for (size_t i = 0; i < parts_.size(); ++i)
+        update_accumulate<T>(h_, ws_, parts_[i].X, parts_[i].n, d_, labels(i), parts_[i].w, C, k_, packed_.get(),
+                             i != 0, true);
+      need_separate_inertia = false;  // the generic kernel produces it in the same pass
+    }
+    if (need_separate_inertia) inertia_only(C);
     if (h_.timing) h_.end_event(ev, false);
   }
 
+  void inertia_only(const T* C)
+  {
+    double* inertia_cell = packed_.get() + packed_count() - 1;
+    if (parts_.empty()) CB2_CUDA(cudaMemsetAsync(inertia_cell, 0, sizeof(double), h_.stream));
+    for (size_t i = 0; i < parts_.size(); ++i)
+      compute_inertia<T>(h_, parts_[i].X, parts_[i].n, d_, labels(i), parts_[i].w, C, inertia_cell, i != 0);
+  }
+
   // One full Lloyd iteration, centroids updated in place; squared shift left at packed[count]
-  void step(T* C)
+  void step(T* C, bool with_inertia = false)
   {
     assign(C);
-    accumulate(C, true);
+    accumulate(C, with_inertia);
     nccl::allreduce_sum_f64(h_, packed_.get(), packed_count());
     finalize_centroids<T>(h_, packed_.get(), C, k_, d_, packed_.get() + packed_count());
   }
@@ -120,7 +156,7 @@ class LloydSolver {
   // inertia of the current labelling wrt C (exact difference form), all ranks; host result
   double inertia(const T* C)
   {
-    accumulate(C, false);
+    inertia_only(C);
     double* cell = packed_.get() + packed_count() - 1;
     nccl::allreduce_sum_f64(h_, cell, 1);
     CB2_CUDA(cudaMemcpyAsync(h_.pinned, cell, sizeof(double), cudaMemcpyDeviceToHost, h_.stream));
@@ -153,6 +189,9 @@ class LloydSolver {
   int d_, k_;
   int64_t n_local_ = 0;
   bool use_tc_     = false;
+  bool use_tma_update_ = false;
+  std::vector<int64_t> label_off_;
+  DevBuf<float> tma_S_, tma_W_;
   DevBuf<int32_t> labels_;
   DevBuf<T> cnorm_;
   DevBuf<double> packed_;

@@ -492,11 +492,8 @@ void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params,
   {
     LloydSolver<T> all(h, ctx.parts, d, m, ctx.engine);
     all.assign(cand.get());
-    int64_t off = 0;
-    for (auto& pt : ctx.parts) {
-      weighted_histogram<T>(h, all.labels() + off, pt.w, pt.n, m, cw64.get());
-      off += pt.n;
-    }
+    for (size_t pi = 0; pi < ctx.parts.size(); ++pi)
+      weighted_histogram<T>(h, all.labels(pi), ctx.parts[pi].w, ctx.parts[pi].n, m, cw64.get());
     nccl::allreduce_sum_f64(h, cw64.get(), m);
   }
   std::vector<double> cw_h(m);
