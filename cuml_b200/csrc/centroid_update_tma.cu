@@ -4,13 +4,18 @@
 // Roles replaced (cuVS side, reached from reference cpp/src/kmeans/kmeans_fit.cu:58-59,153-154):
 // reduce_rows_by_key (centroid sums) and reduce_cols_by_key (cluster weights).
 //
-// CTA = 1 producer warp + W consumer warps.
-//   producer : one thread streams [TR rows x DS columns] tiles of X (2-D TMA, dense rows) and the
-//              tile's labels (1-D bulk copy) into a 3-stage shared-memory ring; mbarrier full/empty.
-//   consumers: consumer w exclusively owns columns [32w, 32w+32) of the CTA's [k x DS] fp32 table in
-//              shared memory, so no two warps ever touch the same cell.  A warp instruction covers
-//              R = 32/L rows (L lanes x float4 per row); rows in the same instruction that share a
-//              label are ordered with __match_any_sync (segmented in-warp update).
+// CTA = 1 producer warp + W consumer warps; a CTA works on a 32-column slice of X (128-byte row
+// segments) when n_features >= 32, on whole rows otherwise.
+//   producer : one thread streams [TR rows x DS columns] tiles of X (2-D TMA, 128B-swizzled when
+//              DS == 32) and the tile's labels (1-D bulk copy) into a 3-stage shared-memory ring;
+//              mbarrier full/empty.
+//   consumers: consumer w exclusively owns 8 columns (DS == 32: four consumers) or the whole slice
+//              (DS < 32: one consumer) of the CTA's [k x DS] fp32 table in shared memory, so no two
+//              warps ever touch the same cell.  One warp instruction covers R = 32/L rows (L lanes x
+//              float4 per row); rows in the same instruction that share a label are ordered with
+//              __match_any_sync (segmented in-warp update).  The table rows are XOR-swizzled by label
+//              like the X tile is by row, so both the tile reads and the table read-modify-writes
+//              are bank-conflict free.
 // The table is written once per CTA to a partials buffer; a second kernel sums the partials in a
 // fixed order in fp64 (deterministic, bitwise identical on every rank after the all-reduce).
 // Memory parallelism comes from the TMA ring (3 tiles in flight per CTA), not from occupancy.
@@ -28,8 +33,10 @@ struct UpdParams {
   int64_t n;
   int64_t tiles_total;      // ceil(n / tr)
   int64_t tiles_per_block;
-  int d, k, ds, cw, tr;
-  uint32_t stage_bytes;     // X tile bytes (tr * ds * 4), multiple of 128
+  int d, k, ds, tr;
+  int log2L;                // lanes per row = 1 << log2L
+  int swizzled;             // ds == 32: 128B swizzle on the X tile and the table
+  uint32_t stage_bytes;     // X tile bytes (tr * ds * 4), multiple of 1024
   const int32_t* labels;    // padded: readable up to n + tr
   const float* w;           // or null
   float* partial_S;         // [row_blocks][k][d]
@@ -42,25 +49,54 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr)
+{
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v)
+{
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ int lds32(uint32_t addr)
+{
+  int v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+// plain spin on an mbarrier phase (the bounded variant in ptx.cuh costs issue slots in hot loops)
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity)
+{
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) {
+      printf("cuml_b200: update-kernel mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
 
 __global__ void __launch_bounds__(160)
 accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams p)
 {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t raw  = ptx::smem_u32(smem_dyn);
-  const uint32_t base = (raw + 127u) & ~127u;
+  const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* g          = smem_dyn + (base - raw);
   // layout: stages (X tile, labels) | table | wtab | barriers
   const uint32_t lab_bytes  = static_cast<uint32_t>(p.tr) * 4u;
-  const uint32_t stage_full = p.stage_bytes + ((lab_bytes + 127u) & ~127u);
+  const uint32_t stage_full = p.stage_bytes + ((lab_bytes + 1023u) & ~1023u);
+  const uint32_t tab_u32    = base + NSTAGE * stage_full;
   float* tab       = reinterpret_cast<float*>(g + NSTAGE * stage_full);
   float* wtab      = tab + static_cast<size_t>(p.k) * p.ds;
   uint64_t* bars   = reinterpret_cast<uint64_t*>(wtab + ((p.k + 3) & ~3));  // full[NSTAGE], empty[NSTAGE]
+  const uint32_t bars_u32 = ptx::smem_u32(bars);
 
   const int warp    = threadIdx.x / 32;
   const int lane    = threadIdx.x % 32;
-  const int nwarps  = blockDim.x / 32;
-  const int ncons   = nwarps - 1;
+  const int ncons   = blockDim.x / 32 - 1;
   const int slice   = blockIdx.y;
   const int cs      = slice * p.ds;
 
@@ -68,8 +104,8 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
   for (int i = threadIdx.x; i < p.k; i += blockDim.x) wtab[i] = 0.0f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&bars[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars[NSTAGE + s]), ncons);
+      ptx::mbar_init(bars_u32 + s * 8, 1);
+      ptx::mbar_init(bars_u32 + (NSTAGE + s) * 8, ncons);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tm_x);
@@ -81,72 +117,78 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t cnt = 0;
-      for (int64_t t = t_begin; t < t_end; ++t, ++cnt) {
-        const uint32_t s = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1u;
-        ptx::mbar_wait(ptx::smem_u32(&bars[NSTAGE + s]), ph ^ 1u);
-        const uint32_t full = ptx::smem_u32(&bars[s]);
+      uint32_t s = 0, ph = 0;
+      for (int64_t t = t_begin; t < t_end; ++t) {
+        mbar_wait_spin(bars_u32 + (NSTAGE + s) * 8, ph ^ 1u);
+        const uint32_t full = bars_u32 + s * 8;
         ptx::mbar_arrive_expect_tx(full, p.stage_bytes + lab_bytes);
         const uint32_t dst = base + s * stage_full;
         const int64_t row0 = t * p.tr;
         ptx::tma_load_2d_hint(dst, &tm_x, cs, static_cast<int32_t>(row0), full, ptx::kEvictFirst);
         bulk_load_1d(dst + p.stage_bytes, p.labels + row0, lab_bytes, full);
+        if (++s == NSTAGE) { s = 0; ph ^= 1u; }
       }
     }
   } else {
-    const int cwarp = warp - 1;
-    const int c0    = cwarp * p.cw;                 // first owned column (relative to the slice)
-    const int width = max(0, min(p.ds - c0, p.cw)); // owned columns (multiple of 4)
-    int L = 1;
-    while (L < 32 && L * 4 < width) L <<= 1;
-    const int R  = 32 / L;
-    const int gq = lane / L;
-    const int lr = lane % L;
-    const bool col_ok    = lr * 4 < width;
-    const unsigned below = (gq == 0) ? 0u : ((1u << (gq * L)) - 1u);
+    const int cwarp   = warp - 1;
+    const int log2L   = p.log2L;
+    const int L       = 1 << log2L;
+    const int R       = 32 >> log2L;
+    const int gq      = lane >> log2L;            // row group within the instruction
+    const int lr      = lane & (L - 1);           // float4 chunk within the owned columns
+    const int chunk   = cwarp * L + lr;           // logical 16-byte chunk within the slice row
+    const unsigned below = (gq == 0) ? 0u : ((1u << (gq << log2L)) - 1u);
     const bool counts    = (slice == 0 && cwarp == 0 && lr == 0);
-    uint32_t cnt = 0;
-    for (int64_t t = t_begin; t < t_end; ++t, ++cnt) {
-      const uint32_t s = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1u;
-      ptx::mbar_wait(ptx::smem_u32(&bars[s]), ph);
-      const float* xs   = reinterpret_cast<const float*>(g + s * stage_full);
-      const int32_t* ls = reinterpret_cast<const int32_t*>(g + s * stage_full + p.stage_bytes);
+    const uint32_t row_bytes = static_cast<uint32_t>(p.ds) * 4u;
+    const bool has_w  = p.w != nullptr;
+    uint32_t s = 0, ph = 0;
+    for (int64_t t = t_begin; t < t_end; ++t) {
+      mbar_wait_spin(bars_u32 + s * 8, ph);
+      const uint32_t xs = base + s * stage_full;
+      const uint32_t ls = xs + p.stage_bytes;
       const int64_t row0 = t * p.tr;
       const int64_t left = p.n - row0;
       const int valid    = left < p.tr ? static_cast<int>(left) : p.tr;
-      if (width > 0) {
 #pragma unroll 2
-        for (int r0 = 0; r0 < p.tr; r0 += R) {
-          const int r   = r0 + gq;
-          const bool ok = (r < valid) && col_ok;
-          const int lb  = (r < valid) ? ls[r] : (-1 - gq);
-          float4 x      = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) x = *reinterpret_cast<const float4*>(xs + static_cast<size_t>(r) * p.ds + c0 + lr * 4);
-          float wv = 1.0f;
-          if (p.w != nullptr) {
-            wv = (r < valid) ? __ldg(p.w + row0 + r) : 0.0f;
-            x.x *= wv; x.y *= wv; x.z *= wv; x.w *= wv;
+      for (int r0 = 0; r0 < p.tr; r0 += R) {
+        const int r   = r0 + gq;
+        const bool ok = r < valid;
+        const int lb  = ok ? lds32(ls + r * 4) : (-1 - gq);
+        const uint32_t xchunk = p.swizzled ? static_cast<uint32_t>(chunk ^ (r & 7)) : static_cast<uint32_t>(chunk);
+        float4 x = lds128(xs + r * row_bytes + xchunk * 16u);
+        float wv = 1.0f;
+        if (has_w) {
+          wv = ok ? __ldg(p.w + row0 + r) : 0.0f;
+          x.x *= wv; x.y *= wv; x.z *= wv; x.w *= wv;
+        }
+        const uint32_t tchunk = p.swizzled ? static_cast<uint32_t>(chunk ^ (lb & 7)) : static_cast<uint32_t>(chunk);
+        const uint32_t cell   = tab_u32 + static_cast<uint32_t>(lb) * row_bytes + tchunk * 16u;
+        const unsigned peers  = __match_any_sync(0xffffffffu, lb);
+        const int rank        = __popc(peers & below) >> log2L;
+        if (__all_sync(0xffffffffu, rank == 0)) {
+          if (ok) {
+            float4 c = lds128(cell);
+            c.x += x.x; c.y += x.y; c.z += x.z; c.w += x.w;
+            sts128(cell, c);
+            if (counts) wtab[lb] += wv;
           }
-          int rank = 0, maxrank = 0;
-          if (R > 1) {
-            const unsigned peers = __match_any_sync(0xffffffffu, lb);
-            rank                 = __popc(peers & below) / L;
-            maxrank              = __reduce_max_sync(0xffffffffu, rank);
-          }
-          for (int rr = 0; rr <= maxrank; ++rr) {
+        } else {
+          // some rows of this instruction share a label: apply them in rank order
+          for (int rr = 0; rr < R; ++rr) {
             if (ok && rank == rr) {
-              float4* cell = reinterpret_cast<float4*>(tab + static_cast<size_t>(lb) * p.ds + c0 + lr * 4);
-              float4 c     = *cell;
+              float4 c = lds128(cell);
               c.x += x.x; c.y += x.y; c.z += x.z; c.w += x.w;
-              *cell = c;
+              sts128(cell, c);
               if (counts) wtab[lb] += wv;
             }
-            if (R > 1) __syncwarp();
+            __syncwarp();
+            if (__all_sync(0xffffffffu, rank <= rr)) break;
           }
         }
       }
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars[NSTAGE + s]));
+      if (lane == 0) ptx::mbar_arrive(bars_u32 + (NSTAGE + s) * 8);
+      if (++s == NSTAGE) { s = 0; ph ^= 1u; }
     }
   }
   __syncthreads();
@@ -154,7 +196,8 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
   const int wcols = min(p.ds, p.d - cs);
   for (int i = threadIdx.x; i < p.k * wcols; i += blockDim.x) {
     const int j = i / wcols, c = i % wcols;
-    outS[static_cast<size_t>(j) * p.d + cs + c] = tab[static_cast<size_t>(j) * p.ds + c];
+    const int pc = p.swizzled ? ((((c >> 2) ^ (j & 7)) << 2) | (c & 3)) : c;
+    outS[static_cast<size_t>(j) * p.d + cs + c] = tab[static_cast<size_t>(j) * p.ds + pc];
   }
   if (slice == 0) {
     float* outW = p.partial_W + static_cast<size_t>(blockIdx.x) * p.k;
@@ -192,54 +235,53 @@ reduce_partials_f32_kernel(const float* __restrict__ partial_S, const float* __r
 }  // namespace
 
 struct TmaUpdatePlan {
-  int ds = 0, cw = 0, tr = 0, warps = 0, slices = 0, ctas_per_sm = 0;
+  int ds = 0, tr = 0, warps = 0, slices = 0, ctas_per_sm = 0, log2L = 0, swizzled = 0;
   size_t smem = 0;
   uint32_t stage_bytes = 0;
 };
 
 static TmaUpdatePlan plan_tma_update(const Handle& h, int d, int k)
 {
-  TmaUpdatePlan best;
-  int best_score = -1;
+  TmaUpdatePlan pl;
+  const int ds = d >= 32 ? 32 : d;   // 128-byte row segments, or whole (short) rows
+  if (ds % 4 != 0) return pl;
+  const size_t table    = (static_cast<size_t>(k) * ds + ((k + 3) & ~3)) * 4;
   const size_t sm_total = 228 * 1024;
-  const int cands[]     = {d, 256, 128, 64, 32, 16, 8, 4};
-  for (int ds : cands) {
-    if (ds > d || ds > 256 || ds % 4 != 0 || ds <= 0) continue;
-    if (ds < 16 && d >= 16) continue;  // keep >= 64-byte row segments
-    const size_t table = (static_cast<size_t>(k) * ds + ((k + 3) & ~3)) * 4;
-    const int W        = static_cast<int>(ceil_div(ds, 32));
-    if (W > 4) continue;
-    for (int per_sm = 8; per_sm >= 1; --per_sm) {
-      const size_t budget = std::min<size_t>(h.smem_optin, sm_total / per_sm - 1024);
-      if (table + 256 + 3 * 4096 > budget) continue;
-      size_t stage_budget = (budget - table - 256 - 128) / NSTAGE;
-      stage_budget        = std::min<size_t>(stage_budget, 16384 + 1024);
-      int tr              = static_cast<int>((stage_budget - 128) / (static_cast<size_t>(ds) * 4 + 4));
-      tr                  = std::min(tr, 256);
-      tr -= tr % 32;
-      if (tr < 32) continue;
-      const int score = std::min(per_sm * W, 8) * 16 + std::min(ds, 128) / 16;
-      if (score > best_score) {
-        best_score       = score;
-        best.ds          = ds;
-        best.cw          = std::min(ds, 32);
-        best.tr          = tr;
-        best.warps       = W;
-        best.slices      = static_cast<int>(ceil_div(d, ds));
-        best.ctas_per_sm = per_sm;
-        best.stage_bytes = static_cast<uint32_t>(tr) * ds * 4;
-        const uint32_t lab = (static_cast<uint32_t>(tr) * 4 + 127u) & ~127u;
-        best.smem = NSTAGE * (best.stage_bytes + lab) + table + 2 * NSTAGE * 8 + 128 + 64;
-      }
-      break;  // the largest per_sm that fits for this ds
+  for (int per_sm = 8; per_sm >= 1; --per_sm) {
+    const size_t budget = std::min<size_t>(h.smem_optin, sm_total / per_sm - 1024);
+    if (table + 1024 + 256 + NSTAGE * (4096 + 1024) > budget) continue;
+    size_t stage_budget = (budget - table - 1024 - 256) / NSTAGE;
+    stage_budget        = std::min<size_t>(stage_budget, 16384 + 1024);
+    int tr              = static_cast<int>((stage_budget - 1024) / (static_cast<size_t>(ds) * 4));
+    tr                  = std::min(tr, 256);
+    // tile bytes must be a multiple of 1024 (swizzle atom) and tr a multiple of the rows per instruction
+    const int gran = std::max(32, 1024 / (ds * 4));
+    tr -= tr % gran;
+    if (tr < gran) continue;
+    pl.ds          = ds;
+    pl.tr          = tr;
+    pl.swizzled    = (ds == 32) ? 1 : 0;
+    pl.warps       = (ds == 32) ? 4 : 1;
+    pl.log2L       = (ds == 32) ? 1 : (ds >= 16 ? 2 : (ds >= 8 ? 1 : 0));  // lanes per row (float4 each)
+    if (ds < 32) {
+      int L = 1, lg = 0;
+      while (L * 4 < ds) { L <<= 1; ++lg; }
+      pl.log2L = lg;
     }
+    pl.slices      = static_cast<int>(ceil_div(d, ds));
+    pl.ctas_per_sm = per_sm;
+    pl.stage_bytes = static_cast<uint32_t>(tr) * ds * 4;
+    const uint32_t lab = (static_cast<uint32_t>(tr) * 4 + 1023u) & ~1023u;
+    pl.smem = NSTAGE * (pl.stage_bytes + lab) + table + 2 * NSTAGE * 8 + 1024 + 64;
+    return pl;
   }
-  return best;
+  return pl;
 }
 
 bool tma_update_supported(const Handle& h, int d, int k)
 {
   if (h.cc_major < 9 || d % 4 != 0) return false;
+  if (d < 32 && (d & (d - 1)) != 0) return false;  // short rows: power-of-two widths only
   return plan_tma_update(h, d, k).ds > 0;
 }
 
@@ -260,8 +302,9 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
   p.d           = d;
   p.k           = k;
   p.ds          = pl.ds;
-  p.cw          = pl.cw;
   p.tr          = pl.tr;
+  p.log2L       = pl.log2L;
+  p.swizzled    = pl.swizzled;
   p.stage_bytes = pl.stage_bytes;
   p.tiles_total = ceil_div(n, pl.tr);
   int64_t row_blocks = std::max<int64_t>(1, static_cast<int64_t>(h.sm_count) * pl.ctas_per_sm / pl.slices);
@@ -279,7 +322,7 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
 
   CUtensorMap tm = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
                                static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(pl.ds),
-                               static_cast<uint32_t>(pl.tr), CU_TENSOR_MAP_SWIZZLE_NONE,
+                               static_cast<uint32_t>(pl.tr), pl.swizzled ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   static bool attr_set = false;
   if (!attr_set) {
