@@ -78,9 +78,16 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity)
   }
 }
 
+// NC = 16-byte chunks per slice row (ds / 4): 8 (128B-swizzled), 4 (64B), 2 (32B) or 1 (dense).
+// Lane = row: every consumer lane owns CPL chunks of one row per iteration (32 rows / warp instruction).
+template <int NC, bool HAS_W>
 __global__ void __launch_bounds__(160)
 accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams p)
 {
+  constexpr int CPL      = NC >= 2 ? 2 : 1;                           // chunks per lane
+  constexpr int SH       = NC == 8 ? 0 : (NC == 4 ? 1 : (NC == 2 ? 2 : 0));  // swizzle: chunk ^= (row >> SH) & (NC-1)
+  constexpr uint32_t MSK = NC - 1;
+  constexpr uint32_t ROWB = NC * 16;
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t raw  = ptx::smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -90,17 +97,18 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
   const uint32_t stage_full = p.stage_bytes + ((lab_bytes + 1023u) & ~1023u);
   const uint32_t tab_u32    = base + NSTAGE * stage_full;
   float* tab       = reinterpret_cast<float*>(g + NSTAGE * stage_full);
-  float* wtab      = tab + static_cast<size_t>(p.k) * p.ds;
+  float* wtab      = tab + static_cast<size_t>(p.k) * (NC * 4);
   uint64_t* bars   = reinterpret_cast<uint64_t*>(wtab + ((p.k + 3) & ~3));  // full[NSTAGE], empty[NSTAGE]
   const uint32_t bars_u32 = ptx::smem_u32(bars);
+  const uint32_t wtab_u32 = ptx::smem_u32(wtab);
 
   const int warp    = threadIdx.x / 32;
   const int lane    = threadIdx.x % 32;
   const int ncons   = blockDim.x / 32 - 1;
   const int slice   = blockIdx.y;
-  const int cs      = slice * p.ds;
+  const int cs      = slice * (NC * 4);
 
-  for (int i = threadIdx.x; i < p.k * p.ds; i += blockDim.x) tab[i] = 0.0f;
+  for (int i = threadIdx.x; i < p.k * NC * 4; i += blockDim.x) tab[i] = 0.0f;
   for (int i = threadIdx.x; i < p.k; i += blockDim.x) wtab[i] = 0.0f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
@@ -130,17 +138,9 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
       }
     }
   } else {
-    const int cwarp   = warp - 1;
-    const int log2L   = p.log2L;
-    const int L       = 1 << log2L;
-    const int R       = 32 >> log2L;
-    const int gq      = lane >> log2L;            // row group within the instruction
-    const int lr      = lane & (L - 1);           // float4 chunk within the owned columns
-    const int chunk   = cwarp * L + lr;           // logical 16-byte chunk within the slice row
-    const unsigned below = (gq == 0) ? 0u : ((1u << (gq << log2L)) - 1u);
-    const bool counts    = (slice == 0 && cwarp == 0 && lr == 0);
-    const uint32_t row_bytes = static_cast<uint32_t>(p.ds) * 4u;
-    const bool has_w  = p.w != nullptr;
+    const uint32_t j0    = static_cast<uint32_t>(warp - 1) * CPL;   // first owned logical chunk (even)
+    const unsigned below = (1u << lane) - 1u;
+    const bool counts    = (slice == 0 && warp == 1);
     uint32_t s = 0, ph = 0;
     for (int64_t t = t_begin; t < t_end; ++t) {
       mbar_wait_spin(bars_u32 + s * 8, ph);
@@ -149,41 +149,41 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
       const int64_t row0 = t * p.tr;
       const int64_t left = p.n - row0;
       const int valid    = left < p.tr ? static_cast<int>(left) : p.tr;
-#pragma unroll 2
-      for (int r0 = 0; r0 < p.tr; r0 += R) {
-        const int r   = r0 + gq;
+      for (int r = lane; r < p.tr; r += 32) {
         const bool ok = r < valid;
-        const int lb  = ok ? lds32(ls + r * 4) : (-1 - gq);
-        const uint32_t xchunk = p.swizzled ? static_cast<uint32_t>(chunk ^ (r & 7)) : static_cast<uint32_t>(chunk);
-        float4 x = lds128(xs + r * row_bytes + xchunk * 16u);
+        const int lb  = ok ? lds32(ls + r * 4) : ~lane;          // invalid rows: unique negative labels
+        const uint32_t xa = xs + static_cast<uint32_t>(r) * ROWB + ((j0 ^ ((static_cast<uint32_t>(r) >> SH) & MSK)) << 4);
+        float4 x0 = lds128(xa);
+        float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (CPL == 2) x1 = lds128(xa ^ 16u);
         float wv = 1.0f;
-        if (has_w) {
+        if (HAS_W) {
           wv = ok ? __ldg(p.w + row0 + r) : 0.0f;
-          x.x *= wv; x.y *= wv; x.z *= wv; x.w *= wv;
+          x0.x *= wv; x0.y *= wv; x0.z *= wv; x0.w *= wv;
+          x1.x *= wv; x1.y *= wv; x1.z *= wv; x1.w *= wv;
         }
-        const uint32_t tchunk = p.swizzled ? static_cast<uint32_t>(chunk ^ (lb & 7)) : static_cast<uint32_t>(chunk);
-        const uint32_t cell   = tab_u32 + static_cast<uint32_t>(lb) * row_bytes + tchunk * 16u;
-        const unsigned peers  = __match_any_sync(0xffffffffu, lb);
-        const int rank        = __popc(peers & below) >> log2L;
-        if (__all_sync(0xffffffffu, rank == 0)) {
-          if (ok) {
-            float4 c = lds128(cell);
-            c.x += x.x; c.y += x.y; c.z += x.z; c.w += x.w;
-            sts128(cell, c);
-            if (counts) wtab[lb] += wv;
-          }
-        } else {
-          // some rows of this instruction share a label: apply them in rank order
-          for (int rr = 0; rr < R; ++rr) {
-            if (ok && rank == rr) {
-              float4 c = lds128(cell);
-              c.x += x.x; c.y += x.y; c.z += x.z; c.w += x.w;
-              sts128(cell, c);
-              if (counts) wtab[lb] += wv;
+        const uint32_t ca = tab_u32 + static_cast<uint32_t>(lb) * ROWB + ((j0 ^ ((static_cast<uint32_t>(lb) >> SH) & MSK)) << 4);
+        const unsigned peers = __match_any_sync(0xffffffffu, lb);
+        const int rank       = __popc(peers & below);
+        int rr = 0;
+        // rows of this instruction that share a label are applied in rank order (usually one round)
+        while (true) {
+          if (ok && rank == rr) {
+            float4 c = lds128(ca);
+            c.x += x0.x; c.y += x0.y; c.z += x0.z; c.w += x0.w;
+            sts128(ca, c);
+            if (CPL == 2) {
+              float4 e = lds128(ca ^ 16u);
+              e.x += x1.x; e.y += x1.y; e.z += x1.z; e.w += x1.w;
+              sts128(ca ^ 16u, e);
             }
-            __syncwarp();
-            if (__all_sync(0xffffffffu, rank <= rr)) break;
+            if (counts) {
+              float* wc = wtab + lb;
+              *wc += wv;
+            }
           }
+          if (__all_sync(0xffffffffu, rank <= rr)) break;
+          ++rr;
         }
       }
       __syncwarp();
@@ -191,13 +191,14 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
       if (++s == NSTAGE) { s = 0; ph ^= 1u; }
     }
   }
+  (void)wtab_u32;
   __syncthreads();
   float* outS     = p.partial_S + static_cast<size_t>(blockIdx.x) * p.k * p.d;
-  const int wcols = min(p.ds, p.d - cs);
+  const int wcols = min(NC * 4, p.d - cs);
   for (int i = threadIdx.x; i < p.k * wcols; i += blockDim.x) {
     const int j = i / wcols, c = i % wcols;
-    const int pc = p.swizzled ? ((((c >> 2) ^ (j & 7)) << 2) | (c & 3)) : c;
-    outS[static_cast<size_t>(j) * p.d + cs + c] = tab[static_cast<size_t>(j) * p.ds + pc];
+    const int pc = ((((c >> 2) ^ ((j >> SH) & MSK)) << 2) | (c & 3));
+    outS[static_cast<size_t>(j) * p.d + cs + c] = tab[static_cast<size_t>(j) * (NC * 4) + pc];
   }
   if (slice == 0) {
     float* outW = p.partial_W + static_cast<size_t>(blockIdx.x) * p.k;
@@ -260,14 +261,9 @@ static TmaUpdatePlan plan_tma_update(const Handle& h, int d, int k)
     if (tr < gran) continue;
     pl.ds          = ds;
     pl.tr          = tr;
-    pl.swizzled    = (ds == 32) ? 1 : 0;
-    pl.warps       = (ds == 32) ? 4 : 1;
-    pl.log2L       = (ds == 32) ? 1 : (ds >= 16 ? 2 : (ds >= 8 ? 1 : 0));  // lanes per row (float4 each)
-    if (ds < 32) {
-      int L = 1, lg = 0;
-      while (L * 4 < ds) { L <<= 1; ++lg; }
-      pl.log2L = lg;
-    }
+    pl.swizzled    = ds >= 8 ? 1 : 0;
+    pl.warps       = std::max(1, ds / 8);   // consumers: two 16-byte chunks of every row each
+    pl.log2L       = 0;
     pl.slices      = static_cast<int>(ceil_div(d, ds));
     pl.ctas_per_sm = per_sm;
     pl.stage_bytes = static_cast<uint32_t>(tr) * ds * 4;
@@ -320,18 +316,26 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
   p.partial_S = partial_S.get();
   p.partial_W = partial_W.get();
 
+  const CUtensorMapSwizzle swz = pl.ds == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : pl.ds == 16 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : pl.ds == 8  ? CU_TENSOR_MAP_SWIZZLE_32B
+                                              : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUtensorMap tm = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
                                static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(pl.ds),
-                               static_cast<uint32_t>(pl.tr), pl.swizzled ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CB2_CUDA(cudaFuncSetAttribute(accumulate_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(h.smem_optin)));
-    attr_set = true;
-  }
+                               static_cast<uint32_t>(pl.tr), swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   dim3 grid(static_cast<unsigned>(row_blocks), static_cast<unsigned>(pl.slices));
-  accumulate_tma_kernel<<<grid, (pl.warps + 1) * 32, pl.smem, h.stream>>>(tm, p);
+  const unsigned threads = (pl.warps + 1) * 32;
+  auto launch = [&](auto kern) {
+    CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
+    kern<<<grid, threads, pl.smem, h.stream>>>(tm, p);
+  };
+  const bool hw = w != nullptr;
+  switch (pl.ds) {
+    case 32: hw ? launch(accumulate_tma_kernel<8, true>) : launch(accumulate_tma_kernel<8, false>); break;
+    case 16: hw ? launch(accumulate_tma_kernel<4, true>) : launch(accumulate_tma_kernel<4, false>); break;
+    case 8: hw ? launch(accumulate_tma_kernel<2, true>) : launch(accumulate_tma_kernel<2, false>); break;
+    default: hw ? launch(accumulate_tma_kernel<1, true>) : launch(accumulate_tma_kernel<1, false>); break;
+  }
   CB2_CHECK_LAUNCH();
   reduce_partials_f32_kernel<<<static_cast<unsigned>(ceil_div(total, 32)), 256, 0, h.stream>>>(
     partial_S.get(), partial_W.get(), static_cast<int>(row_blocks), k, d, packed, accumulate_into ? 1 : 0);
