@@ -79,9 +79,13 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity)
 }
 
 // NC = 16-byte chunks per slice row (ds / 4): 8 (128B-swizzled), 4 (64B), 2 (32B) or 1 (dense).
-// Lane = row: every consumer lane owns CPL chunks of one row per iteration (32 rows / warp instruction).
+// Warp roles: 0 = TMA producer, 1 = analyst, 2.. = consumers.  Lane = row: one warp instruction
+// covers 32 consecutive rows.  The analyst computes, once per 32-row group, each row's rank among
+// the rows of the group that share its label (match_any) and the group's maximum rank; consumers
+// then apply the group in (max rank + 1) conflict-free rounds without any warp-wide matching on
+// their critical path.  Every consumer lane owns CPL 16-byte chunks of its row.
 template <int NC, bool HAS_W>
-__global__ void __launch_bounds__(160)
+__global__ void __launch_bounds__(192)
 accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams p)
 {
   constexpr int CPL      = NC >= 2 ? 2 : 1;                           // chunks per lane
@@ -92,19 +96,18 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
   const uint32_t raw  = ptx::smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* g          = smem_dyn + (base - raw);
-  // layout: stages (X tile, labels) | table | wtab | barriers
+  // layout: stages (X tile | labels | meta) | table | wtab | barriers
   const uint32_t lab_bytes  = static_cast<uint32_t>(p.tr) * 4u;
-  const uint32_t stage_full = p.stage_bytes + ((lab_bytes + 1023u) & ~1023u);
+  const uint32_t stage_full = p.stage_bytes + ((2u * lab_bytes + 1023u) & ~1023u);
   const uint32_t tab_u32    = base + NSTAGE * stage_full;
   float* tab       = reinterpret_cast<float*>(g + NSTAGE * stage_full);
   float* wtab      = tab + static_cast<size_t>(p.k) * (NC * 4);
-  uint64_t* bars   = reinterpret_cast<uint64_t*>(wtab + ((p.k + 3) & ~3));  // full[NSTAGE], empty[NSTAGE]
+  uint64_t* bars   = reinterpret_cast<uint64_t*>(wtab + ((p.k + 3) & ~3));  // full | ready | empty, NSTAGE each
   const uint32_t bars_u32 = ptx::smem_u32(bars);
-  const uint32_t wtab_u32 = ptx::smem_u32(wtab);
 
   const int warp    = threadIdx.x / 32;
   const int lane    = threadIdx.x % 32;
-  const int ncons   = blockDim.x / 32 - 1;
+  const int ncons   = blockDim.x / 32 - 2;
   const int slice   = blockIdx.y;
   const int cs      = slice * (NC * 4);
 
@@ -113,7 +116,8 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NSTAGE; ++s) {
       ptx::mbar_init(bars_u32 + s * 8, 1);
-      ptx::mbar_init(bars_u32 + (NSTAGE + s) * 8, ncons);
+      ptx::mbar_init(bars_u32 + (NSTAGE + s) * 8, 1);
+      ptx::mbar_init(bars_u32 + (2 * NSTAGE + s) * 8, ncons);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tm_x);
@@ -124,10 +128,11 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
   const int64_t t_end   = min(p.tiles_total, t_begin + p.tiles_per_block);
 
   if (warp == 0) {
+    // ---------------- producer ----------------
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       for (int64_t t = t_begin; t < t_end; ++t) {
-        mbar_wait_spin(bars_u32 + (NSTAGE + s) * 8, ph ^ 1u);
+        mbar_wait_spin(bars_u32 + (2 * NSTAGE + s) * 8, ph ^ 1u);
         const uint32_t full = bars_u32 + s * 8;
         ptx::mbar_arrive_expect_tx(full, p.stage_bytes + lab_bytes);
         const uint32_t dst = base + s * stage_full;
@@ -137,21 +142,49 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
         if (++s == NSTAGE) { s = 0; ph ^= 1u; }
       }
     }
-  } else {
-    const uint32_t j0    = static_cast<uint32_t>(warp - 1) * CPL;   // first owned logical chunk (even)
+  } else if (warp == 1) {
+    // ---------------- analyst: per-row rank among equal labels of its 32-row group ----------------
     const unsigned below = (1u << lane) - 1u;
-    const bool counts    = (slice == 0 && warp == 1);
     uint32_t s = 0, ph = 0;
     for (int64_t t = t_begin; t < t_end; ++t) {
       mbar_wait_spin(bars_u32 + s * 8, ph);
+      const uint32_t ls = base + s * stage_full + p.stage_bytes;
+      const uint32_t ms = ls + lab_bytes;
+      const int64_t left = p.n - t * p.tr;
+      const int valid    = left < p.tr ? static_cast<int>(left) : p.tr;
+#pragma unroll 4
+      for (int r = lane; r < p.tr; r += 32) {
+        const int lb         = (r < valid) ? lds32(ls + r * 4) : ~lane;   // invalid rows: unique labels
+        const unsigned peers = __match_any_sync(0xffffffffu, lb);
+        const int rank       = __popc(peers & below);
+        const int maxr       = __reduce_max_sync(0xffffffffu, rank);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(ms + r * 4), "r"(rank | (maxr << 8)) : "memory");
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bars_u32 + (NSTAGE + s) * 8);
+      if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+    }
+  } else {
+    // ---------------- consumers ----------------
+    const uint32_t j0 = static_cast<uint32_t>(warp - 2) * CPL;   // first owned logical chunk (even)
+    const bool counts = (slice == 0 && warp == 2);
+    uint32_t s = 0, ph = 0;
+    for (int64_t t = t_begin; t < t_end; ++t) {
+      mbar_wait_spin(bars_u32 + s * 8, ph);               // TMA bytes landed
+      mbar_wait_spin(bars_u32 + (NSTAGE + s) * 8, ph);    // ranks written
       const uint32_t xs = base + s * stage_full;
       const uint32_t ls = xs + p.stage_bytes;
+      const uint32_t ms = ls + lab_bytes;
       const int64_t row0 = t * p.tr;
       const int64_t left = p.n - row0;
       const int valid    = left < p.tr ? static_cast<int>(left) : p.tr;
+#pragma unroll 2
       for (int r = lane; r < p.tr; r += 32) {
-        const bool ok = r < valid;
-        const int lb  = ok ? lds32(ls + r * 4) : ~lane;          // invalid rows: unique negative labels
+        const bool ok    = r < valid;
+        const int lb     = ok ? lds32(ls + r * 4) : 0;
+        const int meta   = lds32(ms + r * 4);
+        const int rank   = meta & 0xff;
+        const int maxr   = meta >> 8;                       // warp-uniform
         const uint32_t xa = xs + static_cast<uint32_t>(r) * ROWB + ((j0 ^ ((static_cast<uint32_t>(r) >> SH) & MSK)) << 4);
         float4 x0 = lds128(xa);
         float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -163,35 +196,27 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
           x1.x *= wv; x1.y *= wv; x1.z *= wv; x1.w *= wv;
         }
         const uint32_t ca = tab_u32 + static_cast<uint32_t>(lb) * ROWB + ((j0 ^ ((static_cast<uint32_t>(lb) >> SH) & MSK)) << 4);
-        const unsigned peers = __match_any_sync(0xffffffffu, lb);
-        const int rank       = __popc(peers & below);
-        int rr = 0;
-        // rows of this instruction that share a label are applied in rank order (usually one round)
-        while (true) {
+        for (int rr = 0; rr <= maxr; ++rr) {
           if (ok && rank == rr) {
             float4 c = lds128(ca);
+            float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (CPL == 2) e = lds128(ca ^ 16u);
             c.x += x0.x; c.y += x0.y; c.z += x0.z; c.w += x0.w;
             sts128(ca, c);
             if (CPL == 2) {
-              float4 e = lds128(ca ^ 16u);
               e.x += x1.x; e.y += x1.y; e.z += x1.z; e.w += x1.w;
               sts128(ca ^ 16u, e);
             }
-            if (counts) {
-              float* wc = wtab + lb;
-              *wc += wv;
-            }
+            if (counts) wtab[lb] += wv;
           }
-          if (__all_sync(0xffffffffu, rank <= rr)) break;
-          ++rr;
+          if (maxr) __syncwarp();
         }
       }
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bars_u32 + (NSTAGE + s) * 8);
+      if (lane == 0) ptx::mbar_arrive(bars_u32 + (2 * NSTAGE + s) * 8);
       if (++s == NSTAGE) { s = 0; ph ^= 1u; }
     }
   }
-  (void)wtab_u32;
   __syncthreads();
   float* outS     = p.partial_S + static_cast<size_t>(blockIdx.x) * p.k * p.d;
   const int wcols = min(NC * 4, p.d - cs);
@@ -248,28 +273,33 @@ static TmaUpdatePlan plan_tma_update(const Handle& h, int d, int k)
   if (ds % 4 != 0) return pl;
   const size_t table    = (static_cast<size_t>(k) * ds + ((k + 3) & ~3)) * 4;
   const size_t sm_total = 228 * 1024;
-  for (int per_sm = 8; per_sm >= 1; --per_sm) {
-    const size_t budget = std::min<size_t>(h.smem_optin, sm_total / per_sm - 1024);
-    if (table + 1024 + 256 + NSTAGE * (4096 + 1024) > budget) continue;
-    size_t stage_budget = (budget - table - 1024 - 256) / NSTAGE;
-    stage_budget        = std::min<size_t>(stage_budget, 16384 + 1024);
-    int tr              = static_cast<int>((stage_budget - 1024) / (static_cast<size_t>(ds) * 4));
-    tr                  = std::min(tr, 256);
-    // tile bytes must be a multiple of 1024 (swizzle atom) and tr a multiple of the rows per instruction
-    const int gran = std::max(32, 1024 / (ds * 4));
-    tr -= tr % gran;
-    if (tr < gran) continue;
-    pl.ds          = ds;
-    pl.tr          = tr;
-    pl.swizzled    = ds >= 8 ? 1 : 0;
-    pl.warps       = std::max(1, ds / 8);   // consumers: two 16-byte chunks of every row each
-    pl.log2L       = 0;
-    pl.slices      = static_cast<int>(ceil_div(d, ds));
-    pl.ctas_per_sm = per_sm;
-    pl.stage_bytes = static_cast<uint32_t>(tr) * ds * 4;
-    const uint32_t lab = (static_cast<uint32_t>(tr) * 4 + 1023u) & ~1023u;
-    pl.smem = NSTAGE * (pl.stage_bytes + lab) + table + 2 * NSTAGE * 8 + 1024 + 64;
-    return pl;
+  const int warps       = std::max(1, ds / 8);   // consumers: two 16-byte chunks of every row each
+  // candidates: as many CTAs per SM as fit with >= 8 KB tiles (>= 64 rows of 128 B), up to 16 consumer warps
+  for (int min_tile : {8192, 4096, 2048}) {
+    for (int per_sm = std::max(1, std::min(8, 16 / warps)); per_sm >= 1; --per_sm) {
+      const size_t budget = std::min<size_t>(h.smem_optin, sm_total / per_sm - 1024);
+      const size_t fixed  = table + 1024 + 256;
+      if (fixed + NSTAGE * (static_cast<size_t>(min_tile) + 1024) > budget) continue;
+      size_t stage_budget = (budget - fixed) / NSTAGE;
+      stage_budget        = std::min<size_t>(stage_budget, 16384 + 2048);
+      // X tile + (labels + meta) rounded up to 1 KB
+      int tr = static_cast<int>((stage_budget - 1024) / (static_cast<size_t>(ds) * 4 + 8));
+      tr     = std::min(tr, 256);
+      const int gran = std::max(32, 1024 / (ds * 4));  // tile bytes multiple of 1 KB; whole 32-row groups
+      tr -= tr % gran;
+      if (tr < gran || static_cast<size_t>(tr) * ds * 4 < static_cast<size_t>(min_tile)) continue;
+      pl.ds          = ds;
+      pl.tr          = tr;
+      pl.swizzled    = ds >= 8 ? 1 : 0;
+      pl.warps       = warps;
+      pl.log2L       = 0;
+      pl.slices      = static_cast<int>(ceil_div(d, ds));
+      pl.ctas_per_sm = per_sm;
+      pl.stage_bytes = static_cast<uint32_t>(tr) * ds * 4;
+      const uint32_t lab = (static_cast<uint32_t>(tr) * 8 + 1023u) & ~1023u;
+      pl.smem = NSTAGE * (pl.stage_bytes + lab) + table + 3 * NSTAGE * 8 + 1024 + 64;
+      return pl;
+    }
   }
   return pl;
 }
@@ -324,7 +354,7 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
                                static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(pl.ds),
                                static_cast<uint32_t>(pl.tr), swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   dim3 grid(static_cast<unsigned>(row_blocks), static_cast<unsigned>(pl.slices));
-  const unsigned threads = (pl.warps + 1) * 32;
+  const unsigned threads = (pl.warps + 2) * 32;
   auto launch = [&](auto kern) {
     CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
     kern<<<grid, threads, pl.smem, h.stream>>>(tm, p);

@@ -218,14 +218,33 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     const int quarter = warp & 3;            // warps 8..11 -> TMEM lanes [32q, 32q+32)
     uint32_t acc_cnt  = 0;
     const float inf   = __int_as_float(0x7f800000);
+    // 1/2||c||^2 of the next centroid tile is fetched one tile ahead (registers), so its global-load
+    // latency never sits on the epilogue's critical path
+    float pre0 = 0.f, pre1 = 0.f;
+    auto fetch_cn = [&](int nt) {
+      pre0 = __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + (et < p.bn ? et : 0));
+      pre1 = (p.bn > 128) ? __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + 128 + et) : 0.f;
+    };
+    fetch_cn(0);
+    if (p.k_tiles == 1) {  // single centroid tile: stage the half norms once
+      if (et < p.bn) cn_s[et] = pre0;
+      if (p.bn > 128) cn_s[128 + et] = pre1;
+      ptx::named_bar_sync(1, 128);
+    }
     for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-      float best = inf;
-      int bidx   = 0;
+      // four independent running (min, argmin) chains over interleaved columns: instruction-level
+      // parallelism instead of one 4-instruction dependency per column
+      float b0 = inf, b1 = inf, b2 = inf, b3 = inf;
+      int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
       for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
         const uint32_t acc = acc_cnt & 1u, pacc = (acc_cnt >> 1) & 1u;
-        float* cn = cn_s + acc * p.bn;
-        for (int i = et; i < p.bn; i += 128) cn[i] = __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + i);
-        ptx::named_bar_sync(1, 128);
+        float* cn = cn_s + ((p.k_tiles == 1) ? 0 : acc * p.bn);
+        if (p.k_tiles > 1) {
+          if (et < p.bn) cn[et] = pre0;
+          if (p.bn > 128) cn[128 + et] = pre1;
+          fetch_cn(nt + 1 == p.k_tiles ? 0 : nt + 1);
+          ptx::named_bar_sync(1, 128);
+        }
         ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[acc]), pacc);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.bn;
@@ -243,25 +262,29 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             }
           }
           const float4* cn4 = reinterpret_cast<const float4*>(cn + c0);
+          const int jb      = jbase + c0;
 #pragma unroll
           for (int q4 = 0; q4 < 8; ++q4) {
             const float4 c4 = cn4[q4];
-            float v;
-            v = c4.x - __uint_as_float(r[q4 * 4 + 0]);
-            if (v < best) { best = v; bidx = jbase + c0 + q4 * 4 + 0; }
-            v = c4.y - __uint_as_float(r[q4 * 4 + 1]);
-            if (v < best) { best = v; bidx = jbase + c0 + q4 * 4 + 1; }
-            v = c4.z - __uint_as_float(r[q4 * 4 + 2]);
-            if (v < best) { best = v; bidx = jbase + c0 + q4 * 4 + 2; }
-            v = c4.w - __uint_as_float(r[q4 * 4 + 3]);
-            if (v < best) { best = v; bidx = jbase + c0 + q4 * 4 + 3; }
+            const float v0 = c4.x - __uint_as_float(r[q4 * 4 + 0]);
+            const float v1 = c4.y - __uint_as_float(r[q4 * 4 + 1]);
+            const float v2 = c4.z - __uint_as_float(r[q4 * 4 + 2]);
+            const float v3 = c4.w - __uint_as_float(r[q4 * 4 + 3]);
+            if (v0 < b0) { b0 = v0; i0 = jb + q4 * 4 + 0; }
+            if (v1 < b1) { b1 = v1; i1 = jb + q4 * 4 + 1; }
+            if (v2 < b2) { b2 = v2; i2 = jb + q4 * 4 + 2; }
+            if (v3 < b3) { b3 = v3; i3 = jb + q4 * 4 + 3; }
           }
         }
         ptx::tc_fence_before();
         ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[acc]));
       }
+      // merge the chains: smaller value wins, equal values -> smaller index (first minimum)
+      if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
+      if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
+      if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
       const int64_t row = tile * TILE_M + et;
-      if (row < p.n) p.labels[row] = bidx;
+      if (row < p.n) p.labels[row] = i0;
     }
   }
 
