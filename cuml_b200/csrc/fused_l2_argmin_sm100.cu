@@ -17,6 +17,8 @@
 //                            (min, argmin) per row in registers, coalesced label store
 // Pipelines are mbarrier rings: A raw->ready->empty, B full/empty, and two TMEM accumulators
 // (full/empty) so the argmin of N-tile t overlaps the MMAs of N-tile t+1.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include "tensormap.cuh"
@@ -31,27 +33,31 @@ constexpr int KBLOCK_BYTES = TILE_M * 128;    // one K-block of an A tile: 16 KB
 constexpr int NUM_THREADS  = 384;
 constexpr int MAX_STAGES   = 4;
 constexpr int MAX_A_SLOTS  = 8;
+constexpr int MAX_ACC      = 8;   // TMEM accumulator stages (512 columns / BN, at most 8)
 constexpr int A_SLOT_BYTES = 2 * KBLOCK_BYTES;  // hi then lo
 
 struct FusedParams {
   int64_t n;
   int64_t m_tiles;
   int k_tiles;    // k_pad / bn
+  int d;          // true feature count (K steps past it are skipped)
   int kb;         // d_pad / 32
   int bn;         // centroids per accumulator tile (multiple of 32, <= 256)
   int a_slots;    // ring of X K-block slots (hi 16 KB + lo 16 KB each); >= kb when k_tiles > 1
   int b_stages;   // 2..4
   int b_resident; // all k_tiles*kb centroid blocks fit the B stages: load once, never release
+  int n_acc;      // TMEM accumulator stages: min(MAX_ACC, 512 / bn)
   uint32_t tmem_cols;
   const float* cnh;  // [k_pad] 1/2 ||c||^2, +inf for padding
   int32_t* labels;
   float* dbg_dots;   // optional [n, k_pad] dump of the x.c accumulators (tests only)
+  int dbg_skip;      // profiling knob (env CUML_B200_DBG_SKIP): 1 = no hi/lo split, 2 = no MMA, 4 = no argmin
 };
 
 struct Barriers {
   uint64_t a_raw_full[MAX_A_SLOTS], a_ready[MAX_A_SLOTS], a_empty[MAX_A_SLOTS];
   uint64_t b_full[MAX_STAGES], b_empty[MAX_STAGES];
-  uint64_t acc_full[2], acc_empty[2];
+  uint64_t acc_full[MAX_ACC], acc_empty[MAX_ACC];
   uint32_t tmem_base;
 };
 
@@ -82,7 +88,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
       ptx::mbar_init(ptx::smem_u32(&bars->a_ready[s]), 128);
       ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < MAX_ACC; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 128);
     }
@@ -150,9 +156,14 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         ptx::mbar_wait(ptx::smem_u32(&bars->a_raw_full[sa]), pa);
         uint4* hi = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES);
+        // 16-byte chunks the tensor core will read in this K-block: 2 per K=8 step that holds real columns
+        const int live_chunks = 2 * min(4, (p.d - kbi * KBLOCK + 7) / 8);
 #pragma unroll
         for (int i = 0; i < KBLOCK_BYTES / 16 / 128; ++i) {
+          if (p.dbg_skip & 1) break;
           const int e = ct + i * 128;
+          // logical chunk of this physical position under the 128B swizzle: pos ^ (row & 7)
+          if (((e & 7) ^ ((e >> 3) & 7)) >= live_chunks) continue;
           uint4 v = hi[e];
           uint4 h, l;
           h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
@@ -174,7 +185,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
       uint32_t a_cnt0 = 0, b_cnt = 0, acc_cnt = 0;
       for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, a_cnt0 += p.kb) {
         for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
-          const uint32_t acc = acc_cnt & 1u, pacc = (acc_cnt >> 1) & 1u;
+          const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
           ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * p.bn;
@@ -195,8 +206,10 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             const uint64_t da_lo = ptx::umma_desc_sw128(a_base + sa * A_SLOT_BYTES + KBLOCK_BYTES);
             const uint64_t db_hi = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes);
             const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
+            const int nks = min(4, (p.d - kbi * KBLOCK + 7) / 8);  // K=8 steps that hold real columns
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
+              if (ks >= nks || (p.dbg_skip & 2)) break;
               const uint64_t adv = static_cast<uint64_t>(ks * 2);  // 8 tf32 = 32 bytes = 2 x 16B units
               // small terms first, then the dominant hi.hi term
               ptx::mma_tf32_ss(d_tmem, da_lo + adv, db_hi + adv, idesc, (kbi | ks) != 0 ? 1u : 0u);
@@ -237,8 +250,8 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
       float b0 = inf, b1 = inf, b2 = inf, b3 = inf;
       int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
       for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
-        const uint32_t acc = acc_cnt & 1u, pacc = (acc_cnt >> 1) & 1u;
-        float* cn = cn_s + ((p.k_tiles == 1) ? 0 : acc * p.bn);
+        const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
+        float* cn = cn_s + ((p.k_tiles == 1) ? 0 : (acc_cnt & 1u) * p.bn);
         if (p.k_tiles > 1) {
           if (et < p.bn) cn[et] = pre0;
           if (p.bn > 128) cn[128 + et] = pre1;
@@ -251,6 +264,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         const int jbase      = nt * p.bn;
         uint32_t r[32];
         for (int c0 = 0; c0 < p.bn; c0 += 32) {
+          if (p.dbg_skip & 4) break;
           ptx::tmem_ld_32x32(taddr + c0, r);
           ptx::tmem_ld_wait();
           if (p.dbg_dots) {
@@ -396,17 +410,23 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   p.n         = n;
   p.m_tiles   = ceil_div(n, TILE_M);
   p.k_tiles   = cen.k_pad / t.bn;
+  p.d         = d;
   p.kb        = t.kb;
   p.bn        = t.bn;
   p.a_slots   = t.a_slots;
   p.b_stages  = t.b_stages;
   p.b_resident = t.b_resident;
+  p.n_acc = std::min(MAX_ACC, 512 / t.bn);
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(2 * t.bn)) cols <<= 1;
+  while (cols < static_cast<uint32_t>(p.n_acc * t.bn)) cols <<= 1;
   p.tmem_cols = cols;
   p.cnh       = cen.cnh.get();
   p.labels    = labels;
   p.dbg_dots  = dbg_dots;
+  {
+    const char* e = std::getenv("CUML_B200_DBG_SKIP");
+    p.dbg_skip    = e ? std::atoi(e) : 0;
+  }
 
   CUtensorMap tm_x  = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
                                   static_cast<uint64_t>(d) * sizeof(float), KBLOCK, TILE_M,
