@@ -327,3 +327,23 @@ def test_large_property_checks(env):
         if last is not None:
             assert packed[-1].item() <= last * (1 + 1e-9)
         last = packed[-1].item()
+
+
+def test_cpp_surface_example_kat(tmp_path):
+    # the C++ ML::kmeans::{fit,predict} mirror (include/cuml/cluster/kmeans.hpp) on the reference's own
+    # example KAT (cpp/examples/kmeans/kmeans_example.cpp:110-113,172-191)
+    import shutil
+    import subprocess
+    from cuml_b200 import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "kmeans_example")
+    libdir = os.path.dirname(build.lib_path())
+    cmd = [gxx, "-std=c++17", "-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include",
+           os.path.join(root, "examples", "kmeans_example.cpp"), "-L" + libdir, "-lcuml_b200",
+           "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir, "-o", exe]
+    subprocess.run(cmd, check=True, capture_output=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout + r.stderr
