@@ -308,6 +308,261 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
   if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// =================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2).  Two CTAs on one TPC work on a 256-row tile: each loads and
+// splits its own 128 rows of X, each holds HALF of every centroid block (BN/2 rows), and the pair leader
+// issues M=256 MMAs that read both CTAs' shared memory and write both CTAs' TMEM.  Per CTA this halves
+// the shared-memory footprint and read bandwidth of the centroid operand, which buys a deeper X ring
+// (the limiter of the single-CTA kernel at d=64, k=256).  Same pipelines as above; barriers that gate
+// the MMA issuer live in the leader and are arrived on remotely, barriers released by MMA completion
+// are signalled in both CTAs with a multicast tcgen05.commit.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
+                            const __grid_constant__ CUtensorMap tm_lo, const FusedParams p)
+{
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t raw_base = ptx::smem_u32(smem_dyn);
+  const uint32_t base     = (raw_base + 1023u) & ~1023u;
+  uint8_t* gbase          = smem_dyn + (base - raw_base);
+
+  const uint32_t cta_rank = ptx::cluster_ctarank();
+  const bool leader       = cta_rank == 0;
+  const int64_t pair      = blockIdx.x >> 1;
+  const int64_t n_pairs   = gridDim.x >> 1;
+  const int half_n        = p.bn / 2;                                   // centroid rows held by this CTA
+
+  const uint32_t b_half_bytes  = static_cast<uint32_t>(half_n) * 128u;   // hi (or lo) rows of this CTA
+  const uint32_t b_stage_bytes = 2u * b_half_bytes;                     // hi then lo
+  const uint32_t a_base  = base;
+  const uint32_t b_base  = a_base + p.a_slots * A_SLOT_BYTES;
+  const uint32_t cn_off  = p.a_slots * A_SLOT_BYTES + p.b_stages * b_stage_bytes;
+  float* cn_s            = reinterpret_cast<float*>(gbase + cn_off);    // [2][bn]
+  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float));
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_A_SLOTS; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->a_raw_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->a_ready[s]), 8);     // 4 converter warps x 2 CTAs (leader's copy is used)
+      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), 1);
+    }
+    for (int s = 0; s < MAX_ACC; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 8);   // 4 epilogue warps x 2 CTAs (leader's copy)
+    }
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);      // leader's copy: expect_tx covers both CTAs
+      ptx::mbar_init(ptx::smem_u32(&bars->b_empty[s]), 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_x);
+    ptx::prefetch_tmap(&tm_hi);
+    ptx::prefetch_tmap(&tm_lo);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_2cta(ptx::smem_u32(&bars->tmem_base), p.tmem_cols);
+    ptx::tmem_relinquish_2cta();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();   // both CTAs' barriers are initialised before any remote arrive / multicast commit
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int64_t pair_tiles = (p.m_tiles + 1) / 2;   // 256-row tiles
+
+  if (warp == 0) {
+    // ===================== X producer (own 128 rows) =====================
+    if (lane == 0) {
+      uint32_t a_cnt = 0;
+      for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
+        const int32_t row0 = static_cast<int32_t>(pt * 2 * TILE_M + cta_rank * TILE_M);
+        for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
+          const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
+          ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[sa]), pa ^ 1u);
+          const uint32_t full = ptx::smem_u32(&bars->a_raw_full[sa]);
+          ptx::mbar_arrive_expect_tx(full, KBLOCK_BYTES);
+          ptx::tma_load_2d_hint(a_base + sa * A_SLOT_BYTES, &tm_x, kbi * KBLOCK, row0, full, ptx::kEvictFirst);
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== centroid producer (own half of every block) =====================
+    if (lane == 0) {
+      uint32_t b_cnt = 0;
+      for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
+        if (p.b_resident && pt != pair) break;
+        for (int nt = 0; nt < p.k_tiles; ++nt) {
+          for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
+            const uint32_t sb = b_cnt % p.b_stages, pb = (b_cnt / p.b_stages) & 1u;
+            ptx::mbar_wait(ptx::smem_u32(&bars->b_empty[sb]), pb ^ 1u);
+            const uint32_t full_local  = ptx::smem_u32(&bars->b_full[sb]);
+            const uint32_t full_leader = ptx::mapa(full_local, 0);
+            if (leader) ptx::mbar_arrive_expect_tx(full_local, 2u * b_stage_bytes);  // bytes of BOTH CTAs
+            const uint32_t dst = b_base + sb * b_stage_bytes;
+            const int32_t crow = nt * p.bn + static_cast<int32_t>(cta_rank) * half_n;
+            ptx::tma_load_2d_2cta(dst, &tm_hi, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+            ptx::tma_load_2d_2cta(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== converter =====================
+    const int ct = threadIdx.x - 128;
+    uint32_t a_cnt = 0;
+    for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
+      for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
+        const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
+        ptx::mbar_wait(ptx::smem_u32(&bars->a_raw_full[sa]), pa);
+        uint4* hi = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES);
+        uint4* lo = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES);
+        const int live_chunks = 2 * min(4, (p.d - kbi * KBLOCK + 7) / 8);
+#pragma unroll
+        for (int i = 0; i < KBLOCK_BYTES / 16 / 128; ++i) {
+          const int e = ct + i * 128;
+          if (((e & 7) ^ ((e >> 3) & 7)) >= live_chunks) continue;
+          uint4 v = hi[e];
+          uint4 h, l;
+          h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
+          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          hi[e] = h;
+          lo[e] = l;
+        }
+        ptx::fence_proxy_async_all();   // generic-proxy writes -> visible to the pair's tensor cores
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->a_ready[sa]), 0));
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (pair leader only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_tf32(2 * TILE_M, p.bn);
+      uint32_t a_cnt0 = 0, b_cnt = 0, acc_cnt = 0;
+      for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs, a_cnt0 += p.kb) {
+        for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
+          const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
+          ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * p.bn;
+          for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
+            const uint32_t a_cnt = a_cnt0 + kbi;
+            const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
+            if (nt == 0) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[sa]), pa);
+            uint32_t sb = b_cnt % p.b_stages;
+            const uint32_t pb = (b_cnt / p.b_stages) & 1u;
+            if (p.b_resident) {
+              sb = nt * p.kb + kbi;
+              if (pt == pair) ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), 0u);
+            } else {
+              ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), pb);
+            }
+            ptx::tc_fence_after();
+            const uint64_t da_hi = ptx::umma_desc_sw128(a_base + sa * A_SLOT_BYTES);
+            const uint64_t da_lo = ptx::umma_desc_sw128(a_base + sa * A_SLOT_BYTES + KBLOCK_BYTES);
+            const uint64_t db_hi = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes);
+            const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
+            const int nks = min(4, (p.d - kbi * KBLOCK + 7) / 8);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks >= nks) break;
+              const uint64_t adv = static_cast<uint64_t>(ks * 2);
+              ptx::mma_tf32_ss_2cta(d_tmem, da_lo + adv, db_hi + adv, idesc, (kbi | ks) != 0 ? 1u : 0u);
+              ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+              ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+            }
+            if (!p.b_resident) ptx::mma_commit_2cta(ptx::smem_u32(&bars->b_empty[sb]), 3);
+            if (nt == p.k_tiles - 1) ptx::mma_commit_2cta(ptx::smem_u32(&bars->a_empty[sa]), 3);
+          }
+          ptx::mma_commit_2cta(ptx::smem_u32(&bars->acc_full[acc]), 3);
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue (own 128 rows of the pair tile) =====================
+    const int et      = threadIdx.x - 256;
+    const int quarter = warp & 3;
+    uint32_t acc_cnt  = 0;
+    const float inf   = __int_as_float(0x7f800000);
+    float pre0 = 0.f, pre1 = 0.f;
+    auto fetch_cn = [&](int nt) {
+      pre0 = __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + (et < p.bn ? et : 0));
+      pre1 = (p.bn > 128) ? __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + 128 + et) : 0.f;
+    };
+    fetch_cn(0);
+    if (p.k_tiles == 1) {
+      if (et < p.bn) cn_s[et] = pre0;
+      if (p.bn > 128) cn_s[128 + et] = pre1;
+      ptx::named_bar_sync(1, 128);
+    }
+    for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
+      float b0 = inf, b1 = inf, b2 = inf, b3 = inf;
+      int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+      for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
+        const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
+        float* cn = cn_s + ((p.k_tiles == 1) ? 0 : (acc_cnt & 1u) * p.bn);
+        if (p.k_tiles > 1) {
+          if (et < p.bn) cn[et] = pre0;
+          if (p.bn > 128) cn[128 + et] = pre1;
+          fetch_cn(nt + 1 == p.k_tiles ? 0 : nt + 1);
+          ptx::named_bar_sync(1, 128);
+        }
+        ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[acc]), pacc);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.bn;
+        const int jbase      = nt * p.bn;
+        uint32_t r[32];
+        for (int c0 = 0; c0 < p.bn; c0 += 32) {
+          ptx::tmem_ld_32x32(taddr + c0, r);
+          ptx::tmem_ld_wait();
+          if (p.dbg_dots) {
+            const int64_t row = pt * 2 * TILE_M + cta_rank * TILE_M + et;
+            if (row < p.n) {
+              float* o = p.dbg_dots + row * (static_cast<int64_t>(p.k_tiles) * p.bn) + jbase + c0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+            }
+          }
+          const float4* cn4 = reinterpret_cast<const float4*>(cn + c0);
+          const int jb      = jbase + c0;
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 c4 = cn4[q4];
+            const float v0 = c4.x - __uint_as_float(r[q4 * 4 + 0]);
+            const float v1 = c4.y - __uint_as_float(r[q4 * 4 + 1]);
+            const float v2 = c4.z - __uint_as_float(r[q4 * 4 + 2]);
+            const float v3 = c4.w - __uint_as_float(r[q4 * 4 + 3]);
+            if (v0 < b0) { b0 = v0; i0 = jb + q4 * 4 + 0; }
+            if (v1 < b1) { b1 = v1; i1 = jb + q4 * 4 + 1; }
+            if (v2 < b2) { b2 = v2; i2 = jb + q4 * 4 + 2; }
+            if (v3 < b3) { b3 = v3; i3 = jb + q4 * 4 + 3; }
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->acc_empty[acc]), 0));
+      }
+      if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
+      if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
+      if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
+      const int64_t row = pt * 2 * TILE_M + cta_rank * TILE_M + et;
+      if (row < p.n) p.labels[row] = i0;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();   // the peer may still be reading this CTA's shared memory / barriers
+  ptx::tc_fence_after();
+  if (warp == 1) ptx::tmem_dealloc_2cta(tmem_base, p.tmem_cols);
+}
+
 // hi/lo split + half norms of the centroids into padded operand buffers
 __global__ void prepare_centroids_kernel(const float* __restrict__ C, int k, int d, int k_pad, int d_pad,
                                          float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ cnh)
@@ -371,6 +626,45 @@ TilePlan plan_tiles(int d, int k, size_t smem_limit)
   return t;
 }
 
+// CTA-pair plan: BN = 256 split across the pair (128 centroid rows per CTA), deeper X ring.
+TilePlan plan_tiles_2cta(int d, int k, size_t smem_limit)
+{
+  TilePlan t{};
+  t.kb = static_cast<int>(ceil_div(d, KBLOCK));
+  const int bn = 256;
+  auto bytes = [&](int as_, int bs_) {
+    return static_cast<size_t>(as_) * A_SLOT_BYTES + static_cast<size_t>(bs_) * bn * 128 + 2 * bn * sizeof(float) +
+           sizeof(Barriers) + 1024;
+  };
+  const int k_tiles = static_cast<int>(ceil_div(k, bn));
+  const int a_min   = (k_tiles > 1) ? t.kb : std::min(t.kb, 2);
+  int b_stages      = 2;
+  int resident      = 0;
+  if (k_tiles * t.kb <= MAX_STAGES && bytes(std::max(a_min, 2), k_tiles * t.kb) <= smem_limit) {
+    b_stages = k_tiles * t.kb;
+    resident = 1;
+  }
+  if (bytes(std::max(a_min, 2), b_stages) > smem_limit) return t;  // bn stays 0: not available
+  t.bn = bn;
+  t.a_slots = std::max(a_min, 2);
+  t.b_stages = b_stages;
+  t.b_resident = resident;
+  const int a_want = std::min(MAX_A_SLOTS, std::max(2 * t.kb, 6));
+  while (t.a_slots < a_want && bytes(t.a_slots + 1, t.b_stages) <= smem_limit) ++t.a_slots;
+  while (!t.b_resident && t.b_stages < MAX_STAGES && bytes(t.a_slots, t.b_stages + 1) <= smem_limit) ++t.b_stages;
+  t.smem = bytes(t.a_slots, t.b_stages);
+  return t;
+}
+
+// CTA pairs pay off when the single-CTA plan is starved of X slots or cannot use N = 256
+bool use_2cta(const Handle& h, int d, int k)
+{
+  const char* e = std::getenv("CUML_B200_2CTA");
+  if (e) return std::atoi(e) != 0 && k > 128;
+  if (k <= 128 || (h.sm_count % 2) != 0) return false;
+  return plan_tiles_2cta(d, k, h.smem_optin).bn > 0;
+}
+
 }  // namespace
 
 bool tc_supported(int64_t d, int k)
@@ -380,7 +674,8 @@ bool tc_supported(int64_t d, int k)
 
 void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out)
 {
-  TilePlan t = plan_tiles(d, k, h.smem_optin);
+  const bool pair = use_2cta(h, d, k);
+  TilePlan t = pair ? plan_tiles_2cta(d, k, h.smem_optin) : plan_tiles(d, k, h.smem_optin);
   CB2_EXPECTS(t.bn > 0, "tcgen05 k-means tile plan does not fit shared memory");
   const int d_pad = t.kb * KBLOCK;
   const int k_pad = static_cast<int>(ceil_div(k, t.bn)) * t.bn;
@@ -403,7 +698,8 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   if (n == 0) return;
   CB2_EXPECTS(h.cc_major == 10, "the tcgen05 k-means engine needs an sm_100-class GPU (B200)");
   CB2_EXPECTS(reinterpret_cast<uintptr_t>(X) % 16 == 0, "X must be 16-byte aligned for TMA");
-  TilePlan t = plan_tiles(d, k, h.smem_optin);
+  const bool pair = use_2cta(h, d, k);
+  TilePlan t = pair ? plan_tiles_2cta(d, k, h.smem_optin) : plan_tiles(d, k, h.smem_optin);
   CB2_EXPECTS(t.bn == cen.block_n, "centroid operand buffers were prepared for a different tile plan");
 
   FusedParams p{};
@@ -431,21 +727,31 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   CUtensorMap tm_x  = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
                                   static_cast<uint64_t>(d) * sizeof(float), KBLOCK, TILE_M,
                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+  const uint32_t b_box_rows = pair ? t.bn / 2 : t.bn;
   CUtensorMap tm_hi = make_map_2d(cen.hi.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * sizeof(float),
-                                  KBLOCK, t.bn, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+                                  KBLOCK, b_box_rows, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   CUtensorMap tm_lo = make_map_2d(cen.lo.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * sizeof(float),
-                                  KBLOCK, t.bn, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+                                  KBLOCK, b_box_rows, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 
   static bool attr_set = false;
   if (!attr_set) {
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(h.smem_optin)));
     attr_set = true;
   }
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
   EventPair ev{};
   if (h.timing) ev = h.begin_event();
-  fused_l2_argmin_kernel<<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+  if (pair) {
+    // one CTA pair per TPC; grid must be even (cluster dims 2x1x1 are compiled into the kernel)
+    const int64_t pair_tiles = (p.m_tiles + 1) / 2;
+    const unsigned grid = 2u * static_cast<unsigned>(std::min<int64_t>(pair_tiles, h.sm_count / 2));
+    fused_l2_argmin_2cta_kernel<<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+  } else {
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
+    fused_l2_argmin_kernel<<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+  }
   CB2_CHECK_LAUNCH();
   if (h.timing) h.end_event(ev, true);
 }

@@ -145,6 +145,73 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
     : "memory");
 }
 
+// ---------------------------------------------------------------- CTA pairs (cta_group::2)
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank)
+{
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
+{
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t cols)
+{
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta()
+{
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t cols)
+{
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[smem of both CTAs, 256 rows] * B[smem halves of both CTAs]^T; leader thread only
+__device__ __forceinline__ void mma_tf32_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate)
+{
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "setp.ne.b32 p, %4, 0;\n\t"
+    "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+    "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+    : "memory");
+}
+// arrive on the barrier at this offset in every CTA of `mask` once the issued MMAs have retired
+__device__ __forceinline__ void mma_commit_2cta(uint32_t bar, uint16_t mask)
+{
+  asm volatile(
+    "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+    "h"(mask)
+    : "memory");
+}
+// TMA load into this CTA's shared memory whose bytes are accounted on the PAIR LEADER's mbarrier
+__device__ __forceinline__ void tma_load_2d_2cta(uint32_t dst, const void* tmap, int32_t c0, int32_t c1,
+                                                 uint32_t leader_bar, uint64_t hint)
+{
+  asm volatile(
+    "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+    "[%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+    "l"(reinterpret_cast<uint64_t>(tmap)), "r"(leader_bar), "r"(c0), "r"(c1), "l"(hint)
+    : "memory");
+}
+
 // K-major, 128-byte-swizzled shared-memory operand descriptor (tile rows are 128 B, 8-row
 // swizzle atoms of 1024 B): start address >> 4 | LBO (unused for swizzled K-major) |
 // SBO = 1024 B | descriptor version 1 (sm_100) | layout type 2 = SWIZZLE_128B.
