@@ -30,7 +30,7 @@ namespace {
 constexpr int TILE_M       = 128;
 constexpr int KBLOCK       = 32;              // fp32 elements per 128-byte swizzle row
 constexpr int KBLOCK_BYTES = TILE_M * 128;    // one K-block of an A tile: 16 KB
-constexpr int NUM_THREADS  = 384;
+constexpr int NUM_THREADS  = 512;             // 16 warps: producers, MMA issuer, 4 converter, 8 epilogue
 constexpr int MAX_STAGES   = 4;
 constexpr int MAX_A_SLOTS  = 8;
 constexpr int MAX_ACC      = 8;   // TMEM accumulator stages (512 columns / BN, at most 8)
@@ -61,6 +61,105 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
+// ===================== epilogue role (shared by the single-CTA and the CTA-pair kernels) ============
+// 8 warps: warp e handles TMEM lanes [32*(e&3), +32) (its rows) and the column half (e>>2) of every
+// accumulator tile; thread = row.  Per row: four independent running (min, argmin) chains, merged with
+// the first-minimum rule; the two column halves are merged through shared memory.
+template <bool PAIR>
+__device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* bars, float* cn_s, float* mrg_v,
+                                              int* mrg_i, uint32_t tmem_base, int64_t first_row, int64_t row_stride,
+                                              int64_t n_tiles_cta)
+{
+  const int et      = threadIdx.x - 256;      // 0..255
+  const int ew      = et >> 5;                // epilogue warp 0..7
+  const int lane    = et & 31;
+  const int quarter = ew & 3;                 // TMEM lane quarter this warp may access
+  const int half    = ew >> 2;                // column half of the accumulator tile
+  const int rit     = quarter * 32 + lane;    // row within the 128-row tile
+  const float inf   = __int_as_float(0x7f800000);
+  const int cbeg    = (p.bn >= 64) ? half * (p.bn / 2) : 0;
+  const int cend    = (p.bn >= 64) ? cbeg + p.bn / 2 : (half == 0 ? p.bn : 0);
+  uint32_t acc_cnt  = 0;
+  // 1/2||c||^2 of the next centroid tile is fetched one tile ahead (registers), so its global-load
+  // latency never sits on the epilogue's critical path
+  float pre = 0.f;
+  auto fetch_cn = [&](int nt) { pre = __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + (et < p.bn ? et : 0)); };
+  fetch_cn(0);
+  if (p.k_tiles == 1) {  // single centroid tile: stage the half norms once
+    if (et < p.bn) cn_s[et] = pre;
+    ptx::named_bar_sync(1, 256);
+  }
+  for (int64_t t = 0; t < n_tiles_cta; ++t) {
+    float b0 = inf, b1 = inf, b2 = inf, b3 = inf;
+    int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+    for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
+      const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
+      float* cn = cn_s + ((p.k_tiles == 1) ? 0 : (acc_cnt & 1u) * p.bn);
+      if (p.k_tiles > 1) {
+        if (et < p.bn) cn[et] = pre;
+        fetch_cn(nt + 1 == p.k_tiles ? 0 : nt + 1);
+        ptx::named_bar_sync(1, 256);
+      }
+      ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[acc]), pacc);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.bn;
+      const int jbase      = nt * p.bn;
+      uint32_t r[32];
+      for (int c0 = cbeg; c0 < cend; c0 += 32) {
+        if (p.dbg_skip & 4) break;
+        ptx::tmem_ld_32x32(taddr + c0, r);
+        ptx::tmem_ld_wait();
+        if (p.dbg_dots) {
+          const int64_t row = first_row + t * row_stride + rit;
+          if (row < p.n) {
+            float* o = p.dbg_dots + row * (static_cast<int64_t>(p.k_tiles) * p.bn) + jbase + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
+          }
+        }
+        const float4* cn4 = reinterpret_cast<const float4*>(cn + c0);
+        const int jb      = jbase + c0;
+#pragma unroll
+        for (int q4 = 0; q4 < 8; ++q4) {
+          const float4 c4 = cn4[q4];
+          const float v0 = c4.x - __uint_as_float(r[q4 * 4 + 0]);
+          const float v1 = c4.y - __uint_as_float(r[q4 * 4 + 1]);
+          const float v2 = c4.z - __uint_as_float(r[q4 * 4 + 2]);
+          const float v3 = c4.w - __uint_as_float(r[q4 * 4 + 3]);
+          if (v0 < b0) { b0 = v0; i0 = jb + q4 * 4 + 0; }
+          if (v1 < b1) { b1 = v1; i1 = jb + q4 * 4 + 1; }
+          if (v2 < b2) { b2 = v2; i2 = jb + q4 * 4 + 2; }
+          if (v3 < b3) { b3 = v3; i3 = jb + q4 * 4 + 3; }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->acc_empty[acc]), 0));
+        else ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[acc]));
+      }
+    }
+    // merge the chains: smaller value wins, equal values -> smaller index (first minimum)
+    if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
+    if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
+    if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
+    // merge the two column halves through shared memory
+    if (half == 1) {
+      mrg_v[rit] = b0;
+      mrg_i[rit] = i0;
+    }
+    ptx::named_bar_sync(2, 256);
+    if (half == 0) {
+      const float ov = mrg_v[rit];
+      const int oi   = mrg_i[rit];
+      if (ov < b0 || (ov == b0 && oi < i0)) { b0 = ov; i0 = oi; }
+      const int64_t row = first_row + t * row_stride + rit;
+      if (row < p.n) p.labels[row] = i0;
+    }
+    ptx::named_bar_sync(3, 256);  // mrg_* may be overwritten by the next tile
+  }
+}
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                        const __grid_constant__ CUtensorMap tm_lo, const FusedParams p)
@@ -77,7 +176,9 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
   const uint32_t b_base  = a_base + p.a_slots * A_SLOT_BYTES;
   const uint32_t cn_off  = p.a_slots * A_SLOT_BYTES + p.b_stages * b_stage_bytes;
   float* cn_s            = reinterpret_cast<float*>(gbase + cn_off);               // [2][bn]
-  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float));
+  float* mrg_v           = cn_s + 2 * p.bn;                                         // [128] epilogue half merge
+  int* mrg_i             = reinterpret_cast<int*>(mrg_v + TILE_M);                  // [128]
+  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 2u * TILE_M * 4u);
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -90,7 +191,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     }
     for (int s = 0; s < MAX_ACC; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 128);
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 8);    // one arrive per epilogue warp
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);
@@ -227,79 +328,10 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     }
   } else if (warp >= 8) {
     // ===================== epilogue: argmin over the accumulator =====================
-    const int et      = threadIdx.x - 256;   // 0..127 == row within the tile == TMEM lane
-    const int quarter = warp & 3;            // warps 8..11 -> TMEM lanes [32q, 32q+32)
-    uint32_t acc_cnt  = 0;
-    const float inf   = __int_as_float(0x7f800000);
-    // 1/2||c||^2 of the next centroid tile is fetched one tile ahead (registers), so its global-load
-    // latency never sits on the epilogue's critical path
-    float pre0 = 0.f, pre1 = 0.f;
-    auto fetch_cn = [&](int nt) {
-      pre0 = __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + (et < p.bn ? et : 0));
-      pre1 = (p.bn > 128) ? __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + 128 + et) : 0.f;
-    };
-    fetch_cn(0);
-    if (p.k_tiles == 1) {  // single centroid tile: stage the half norms once
-      if (et < p.bn) cn_s[et] = pre0;
-      if (p.bn > 128) cn_s[128 + et] = pre1;
-      ptx::named_bar_sync(1, 128);
-    }
-    for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-      // four independent running (min, argmin) chains over interleaved columns: instruction-level
-      // parallelism instead of one 4-instruction dependency per column
-      float b0 = inf, b1 = inf, b2 = inf, b3 = inf;
-      int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-      for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
-        const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
-        float* cn = cn_s + ((p.k_tiles == 1) ? 0 : (acc_cnt & 1u) * p.bn);
-        if (p.k_tiles > 1) {
-          if (et < p.bn) cn[et] = pre0;
-          if (p.bn > 128) cn[128 + et] = pre1;
-          fetch_cn(nt + 1 == p.k_tiles ? 0 : nt + 1);
-          ptx::named_bar_sync(1, 128);
-        }
-        ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[acc]), pacc);
-        ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.bn;
-        const int jbase      = nt * p.bn;
-        uint32_t r[32];
-        for (int c0 = 0; c0 < p.bn; c0 += 32) {
-          if (p.dbg_skip & 4) break;
-          ptx::tmem_ld_32x32(taddr + c0, r);
-          ptx::tmem_ld_wait();
-          if (p.dbg_dots) {
-            const int64_t row = tile * TILE_M + et;
-            if (row < p.n) {
-              float* o = p.dbg_dots + row * (static_cast<int64_t>(p.k_tiles) * p.bn) + jbase + c0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
-            }
-          }
-          const float4* cn4 = reinterpret_cast<const float4*>(cn + c0);
-          const int jb      = jbase + c0;
-#pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            const float4 c4 = cn4[q4];
-            const float v0 = c4.x - __uint_as_float(r[q4 * 4 + 0]);
-            const float v1 = c4.y - __uint_as_float(r[q4 * 4 + 1]);
-            const float v2 = c4.z - __uint_as_float(r[q4 * 4 + 2]);
-            const float v3 = c4.w - __uint_as_float(r[q4 * 4 + 3]);
-            if (v0 < b0) { b0 = v0; i0 = jb + q4 * 4 + 0; }
-            if (v1 < b1) { b1 = v1; i1 = jb + q4 * 4 + 1; }
-            if (v2 < b2) { b2 = v2; i2 = jb + q4 * 4 + 2; }
-            if (v3 < b3) { b3 = v3; i3 = jb + q4 * 4 + 3; }
-          }
-        }
-        ptx::tc_fence_before();
-        ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[acc]));
-      }
-      // merge the chains: smaller value wins, equal values -> smaller index (first minimum)
-      if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
-      if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
-      if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
-      const int64_t row = tile * TILE_M + et;
-      if (row < p.n) p.labels[row] = i0;
-    }
+    const int64_t n_mine = (p.m_tiles > static_cast<int64_t>(blockIdx.x))
+                             ? (p.m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    epilogue_role<false>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, static_cast<int64_t>(blockIdx.x) * TILE_M,
+                         static_cast<int64_t>(gridDim.x) * TILE_M, n_mine);
   }
 
   ptx::tc_fence_before();
@@ -337,7 +369,9 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   const uint32_t b_base  = a_base + p.a_slots * A_SLOT_BYTES;
   const uint32_t cn_off  = p.a_slots * A_SLOT_BYTES + p.b_stages * b_stage_bytes;
   float* cn_s            = reinterpret_cast<float*>(gbase + cn_off);    // [2][bn]
-  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float));
+  float* mrg_v           = cn_s + 2 * p.bn;                              // [128] epilogue half merge
+  int* mrg_i             = reinterpret_cast<int*>(mrg_v + TILE_M);       // [128]
+  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 2u * TILE_M * 4u);
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -350,7 +384,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     }
     for (int s = 0; s < MAX_ACC; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 8);   // 4 epilogue warps x 2 CTAs (leader's copy)
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 16);  // 8 epilogue warps x 2 CTAs (leader's copy)
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);      // leader's copy: expect_tx covers both CTAs
@@ -486,74 +520,9 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     }
   } else if (warp >= 8) {
     // ===================== epilogue (own 128 rows of the pair tile) =====================
-    const int et      = threadIdx.x - 256;
-    const int quarter = warp & 3;
-    uint32_t acc_cnt  = 0;
-    const float inf   = __int_as_float(0x7f800000);
-    float pre0 = 0.f, pre1 = 0.f;
-    auto fetch_cn = [&](int nt) {
-      pre0 = __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + (et < p.bn ? et : 0));
-      pre1 = (p.bn > 128) ? __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + 128 + et) : 0.f;
-    };
-    fetch_cn(0);
-    if (p.k_tiles == 1) {
-      if (et < p.bn) cn_s[et] = pre0;
-      if (p.bn > 128) cn_s[128 + et] = pre1;
-      ptx::named_bar_sync(1, 128);
-    }
-    for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
-      float b0 = inf, b1 = inf, b2 = inf, b3 = inf;
-      int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
-      for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
-        const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
-        float* cn = cn_s + ((p.k_tiles == 1) ? 0 : (acc_cnt & 1u) * p.bn);
-        if (p.k_tiles > 1) {
-          if (et < p.bn) cn[et] = pre0;
-          if (p.bn > 128) cn[128 + et] = pre1;
-          fetch_cn(nt + 1 == p.k_tiles ? 0 : nt + 1);
-          ptx::named_bar_sync(1, 128);
-        }
-        ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[acc]), pacc);
-        ptx::tc_fence_after();
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.bn;
-        const int jbase      = nt * p.bn;
-        uint32_t r[32];
-        for (int c0 = 0; c0 < p.bn; c0 += 32) {
-          ptx::tmem_ld_32x32(taddr + c0, r);
-          ptx::tmem_ld_wait();
-          if (p.dbg_dots) {
-            const int64_t row = pt * 2 * TILE_M + cta_rank * TILE_M + et;
-            if (row < p.n) {
-              float* o = p.dbg_dots + row * (static_cast<int64_t>(p.k_tiles) * p.bn) + jbase + c0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
-            }
-          }
-          const float4* cn4 = reinterpret_cast<const float4*>(cn + c0);
-          const int jb      = jbase + c0;
-#pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            const float4 c4 = cn4[q4];
-            const float v0 = c4.x - __uint_as_float(r[q4 * 4 + 0]);
-            const float v1 = c4.y - __uint_as_float(r[q4 * 4 + 1]);
-            const float v2 = c4.z - __uint_as_float(r[q4 * 4 + 2]);
-            const float v3 = c4.w - __uint_as_float(r[q4 * 4 + 3]);
-            if (v0 < b0) { b0 = v0; i0 = jb + q4 * 4 + 0; }
-            if (v1 < b1) { b1 = v1; i1 = jb + q4 * 4 + 1; }
-            if (v2 < b2) { b2 = v2; i2 = jb + q4 * 4 + 2; }
-            if (v3 < b3) { b3 = v3; i3 = jb + q4 * 4 + 3; }
-          }
-        }
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->acc_empty[acc]), 0));
-      }
-      if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
-      if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
-      if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
-      const int64_t row = pt * 2 * TILE_M + cta_rank * TILE_M + et;
-      if (row < p.n) p.labels[row] = i0;
-    }
+    const int64_t n_mine = (pair_tiles > pair) ? (pair_tiles - pair + n_pairs - 1) / n_pairs : 0;
+    epilogue_role<true>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, pair * 2 * TILE_M + cta_rank * TILE_M,
+                        n_pairs * 2 * TILE_M, n_mine);
   }
 
   ptx::tc_fence_before();
@@ -599,7 +568,7 @@ TilePlan plan_tiles(int d, int k, size_t smem_limit)
   else if (k <= 128) bn0 = 128;
   auto bytes = [&](int bn_, int as_, int bs_) {
     return static_cast<size_t>(as_) * A_SLOT_BYTES + static_cast<size_t>(bs_) * 2 * bn_ * 128 +
-           2 * bn_ * sizeof(float) + sizeof(Barriers) + 1024;
+           2 * bn_ * sizeof(float) + 2 * TILE_M * 4 + sizeof(Barriers) + 1024;
   };
   t.bn = 0;
   for (int bn = bn0; bn >= 32 && t.bn == 0; bn /= 2) {
@@ -634,7 +603,7 @@ TilePlan plan_tiles_2cta(int d, int k, size_t smem_limit)
   const int bn = 256;
   auto bytes = [&](int as_, int bs_) {
     return static_cast<size_t>(as_) * A_SLOT_BYTES + static_cast<size_t>(bs_) * bn * 128 + 2 * bn * sizeof(float) +
-           sizeof(Barriers) + 1024;
+           2 * TILE_M * 4 + sizeof(Barriers) + 1024;
   };
   const int k_tiles = static_cast<int>(ceil_div(k, bn));
   const int a_min   = (k_tiles > 1) ? t.kb : std::min(t.kb, 2);
