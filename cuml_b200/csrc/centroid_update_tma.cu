@@ -27,16 +27,16 @@ namespace cb2 {
 
 namespace {
 
-constexpr int NSTAGE = 3;
+constexpr int MAX_NSTAGE = 8;
 
 struct UpdParams {
   int64_t n;
   int64_t tiles_total;      // ceil(n / tr)
   int64_t tiles_per_block;
   int d, k, ds, tr;
-  int log2L;                // lanes per row = 1 << log2L
-  int swizzled;             // ds == 32: 128B swizzle on the X tile and the table
-  uint32_t stage_bytes;     // X tile bytes (tr * ds * 4), multiple of 1024
+  int nb;                   // 128-byte sub-slices per CTA slice (1 or 2) when ds >= 32
+  int nstage;               // ring depth (2..8)
+  uint32_t sub_bytes;       // one sub-tile: tr * min(ds,32) * 4, multiple of 1024
   const int32_t* labels;    // padded: readable up to n + tr
   const float* w;           // or null
   float* partial_S;         // [row_blocks][k][d]
@@ -78,46 +78,50 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity)
   }
 }
 
-// NC = 16-byte chunks per slice row (ds / 4): 8 (128B-swizzled), 4 (64B), 2 (32B) or 1 (dense).
+// NC = 16-byte chunks per sub-slice row: 8 (128B-swizzled, ds >= 32), 4 (64B), 2 (32B) or 1 (dense).
 // Warp roles: 0 = TMA producer, 1 = analyst, 2.. = consumers.  Lane = row: one warp instruction
 // covers 32 consecutive rows.  The analyst computes, once per 32-row group, each row's rank among
-// the rows of the group that share its label (match_any) and the group's maximum rank; consumers
-// then apply the group in (max rank + 1) conflict-free rounds without any warp-wide matching on
-// their critical path.  Every consumer lane owns CPL 16-byte chunks of its row.
+// the rows of the group that share its label (match_any) and the group's maximum rank, and keeps the
+// per-cluster weights; consumers then apply the group in (max rank + 1) conflict-free rounds with no
+// warp-wide matching on their critical path.  Every consumer lane owns CPL 16-byte chunks of its row.
 template <int NC, bool HAS_W>
-__global__ void __launch_bounds__(192)
+__global__ void __launch_bounds__(320)
 accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams p)
 {
   constexpr int CPL      = NC >= 2 ? 2 : 1;                           // chunks per lane
   constexpr int SH       = NC == 8 ? 0 : (NC == 4 ? 1 : (NC == 2 ? 2 : 0));  // swizzle: chunk ^= (row >> SH) & (NC-1)
   constexpr uint32_t MSK = NC - 1;
   constexpr uint32_t ROWB = NC * 16;
+  constexpr int CONS_PER_SUB = NC / CPL;                              // consumer warps per sub-slice
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t raw  = ptx::smem_u32(smem_dyn);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* g          = smem_dyn + (base - raw);
-  // layout: stages (X tile | labels | meta) | table | wtab | barriers
+  // layout: stages (nb sub-tiles | labels | meta) | tables (nb) | wtab | barriers
   const uint32_t lab_bytes  = static_cast<uint32_t>(p.tr) * 4u;
-  const uint32_t stage_full = p.stage_bytes + ((2u * lab_bytes + 1023u) & ~1023u);
-  const uint32_t tab_u32    = base + NSTAGE * stage_full;
-  float* tab       = reinterpret_cast<float*>(g + NSTAGE * stage_full);
-  float* wtab      = tab + static_cast<size_t>(p.k) * (NC * 4);
-  uint64_t* bars   = reinterpret_cast<uint64_t*>(wtab + ((p.k + 3) & ~3));  // full | ready | empty, NSTAGE each
+  const uint32_t x_bytes    = static_cast<uint32_t>(p.nb) * p.sub_bytes;
+  const uint32_t stage_full = x_bytes + ((2u * lab_bytes + 1023u) & ~1023u);
+  const uint32_t tab_bytes  = static_cast<uint32_t>(p.k) * ROWB;       // one sub-slice table
+  const uint32_t tab_u32    = base + p.nstage * stage_full;
+  float* tab       = reinterpret_cast<float*>(g + p.nstage * stage_full);
+  float* wtab      = tab + static_cast<size_t>(p.nb) * p.k * (NC * 4);
+  uint64_t* bars   = reinterpret_cast<uint64_t*>(wtab + ((p.k + 3) & ~3));  // full | ready | empty, MAX_NSTAGE each
   const uint32_t bars_u32 = ptx::smem_u32(bars);
+  const uint32_t B_FULL = 0, B_READY = MAX_NSTAGE * 8, B_EMPTY = 2 * MAX_NSTAGE * 8;
 
   const int warp    = threadIdx.x / 32;
   const int lane    = threadIdx.x % 32;
   const int ncons   = blockDim.x / 32 - 2;
   const int slice   = blockIdx.y;
-  const int cs      = slice * (NC * 4);
+  const int cs      = slice * p.ds;
 
-  for (int i = threadIdx.x; i < p.k * NC * 4; i += blockDim.x) tab[i] = 0.0f;
+  for (int i = threadIdx.x; i < p.nb * p.k * NC * 4; i += blockDim.x) tab[i] = 0.0f;
   for (int i = threadIdx.x; i < p.k; i += blockDim.x) wtab[i] = 0.0f;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NSTAGE; ++s) {
-      ptx::mbar_init(bars_u32 + s * 8, 1);
-      ptx::mbar_init(bars_u32 + (NSTAGE + s) * 8, 1);
-      ptx::mbar_init(bars_u32 + (2 * NSTAGE + s) * 8, ncons);
+    for (int s = 0; s < MAX_NSTAGE; ++s) {
+      ptx::mbar_init(bars_u32 + B_FULL + s * 8, 1);
+      ptx::mbar_init(bars_u32 + B_READY + s * 8, 1);
+      ptx::mbar_init(bars_u32 + B_EMPTY + s * 8, ncons);
     }
     ptx::fence_barrier_init();
     ptx::prefetch_tmap(&tm_x);
@@ -132,48 +136,69 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
     if (lane == 0) {
       uint32_t s = 0, ph = 0;
       for (int64_t t = t_begin; t < t_end; ++t) {
-        mbar_wait_spin(bars_u32 + (2 * NSTAGE + s) * 8, ph ^ 1u);
-        const uint32_t full = bars_u32 + s * 8;
-        ptx::mbar_arrive_expect_tx(full, p.stage_bytes + lab_bytes);
+        mbar_wait_spin(bars_u32 + B_EMPTY + s * 8, ph ^ 1u);
+        const uint32_t full = bars_u32 + B_FULL + s * 8;
+        ptx::mbar_arrive_expect_tx(full, x_bytes + lab_bytes);
         const uint32_t dst = base + s * stage_full;
         const int64_t row0 = t * p.tr;
-        ptx::tma_load_2d_hint(dst, &tm_x, cs, static_cast<int32_t>(row0), full, ptx::kEvictFirst);
-        bulk_load_1d(dst + p.stage_bytes, p.labels + row0, lab_bytes, full);
-        if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+        for (int sb = 0; sb < p.nb; ++sb)
+          ptx::tma_load_2d_hint(dst + sb * p.sub_bytes, &tm_x, cs + sb * 32, static_cast<int32_t>(row0), full,
+                                ptx::kEvictFirst);
+        bulk_load_1d(dst + x_bytes, p.labels + row0, lab_bytes, full);
+        if (++s == static_cast<uint32_t>(p.nstage)) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ---------------- analyst: per-row rank among equal labels of its 32-row group ----------------
+    // ---------------- analyst: ranks among equal labels per 32-row group; cluster weights ----------------
     const unsigned below = (1u << lane) - 1u;
+    const bool counts    = (slice == 0);
     uint32_t s = 0, ph = 0;
     for (int64_t t = t_begin; t < t_end; ++t) {
-      mbar_wait_spin(bars_u32 + s * 8, ph);
-      const uint32_t ls = base + s * stage_full + p.stage_bytes;
+      mbar_wait_spin(bars_u32 + B_FULL + s * 8, ph);
+      const uint32_t ls = base + s * stage_full + x_bytes;
       const uint32_t ms = ls + lab_bytes;
-      const int64_t left = p.n - t * p.tr;
+      const int64_t row0 = t * p.tr;
+      const int64_t left = p.n - row0;
       const int valid    = left < p.tr ? static_cast<int>(left) : p.tr;
-#pragma unroll 4
+#pragma unroll 2
       for (int r = lane; r < p.tr; r += 32) {
-        const int lb         = (r < valid) ? lds32(ls + r * 4) : ~lane;   // invalid rows: unique labels
+        const bool ok        = r < valid;
+        const int lb         = ok ? lds32(ls + r * 4) : ~lane;   // invalid rows: unique labels
         const unsigned peers = __match_any_sync(0xffffffffu, lb);
         const int rank       = __popc(peers & below);
         const int maxr       = __reduce_max_sync(0xffffffffu, rank);
         asm volatile("st.shared.b32 [%0], %1;" ::"r"(ms + r * 4), "r"(rank | (maxr << 8)) : "memory");
+        if (counts) {
+          if (!HAS_W) {
+            // the last of each set of equal labels adds the set's size: distinct addresses, no conflict
+            const int cnt = __popc(peers);
+            if (ok && rank == cnt - 1) wtab[lb] += static_cast<float>(cnt);
+          } else {
+            const float wv = ok ? __ldg(p.w + row0 + r) : 0.0f;
+            for (int rr = 0; rr <= maxr; ++rr) {
+              if (ok && rank == rr) wtab[lb] += wv;
+              __syncwarp();
+            }
+          }
+        }
       }
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bars_u32 + (NSTAGE + s) * 8);
-      if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+      if (lane == 0) ptx::mbar_arrive(bars_u32 + B_READY + s * 8);
+      if (++s == static_cast<uint32_t>(p.nstage)) { s = 0; ph ^= 1u; }
     }
   } else {
     // ---------------- consumers ----------------
-    const uint32_t j0 = static_cast<uint32_t>(warp - 2) * CPL;   // first owned logical chunk (even)
-    const bool counts = (slice == 0 && warp == 2);
+    const int cw      = warp - 2;
+    const int sub     = cw / CONS_PER_SUB;                                   // 128-byte sub-slice
+    const uint32_t j0 = static_cast<uint32_t>(cw % CONS_PER_SUB) * CPL;     // first owned logical chunk (even)
+    const uint32_t tab_sub = tab_u32 + sub * tab_bytes;
     uint32_t s = 0, ph = 0;
     for (int64_t t = t_begin; t < t_end; ++t) {
-      mbar_wait_spin(bars_u32 + s * 8, ph);               // TMA bytes landed
-      mbar_wait_spin(bars_u32 + (NSTAGE + s) * 8, ph);    // ranks written
-      const uint32_t xs = base + s * stage_full;
-      const uint32_t ls = xs + p.stage_bytes;
+      mbar_wait_spin(bars_u32 + B_FULL + s * 8, ph);     // TMA bytes landed
+      mbar_wait_spin(bars_u32 + B_READY + s * 8, ph);    // ranks written
+      const uint32_t st = base + s * stage_full;
+      const uint32_t xs = st + sub * p.sub_bytes;
+      const uint32_t ls = st + x_bytes;
       const uint32_t ms = ls + lab_bytes;
       const int64_t row0 = t * p.tr;
       const int64_t left = p.n - row0;
@@ -189,13 +214,12 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
         float4 x0 = lds128(xa);
         float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (CPL == 2) x1 = lds128(xa ^ 16u);
-        float wv = 1.0f;
         if (HAS_W) {
-          wv = ok ? __ldg(p.w + row0 + r) : 0.0f;
+          const float wv = ok ? __ldg(p.w + row0 + r) : 0.0f;
           x0.x *= wv; x0.y *= wv; x0.z *= wv; x0.w *= wv;
           x1.x *= wv; x1.y *= wv; x1.z *= wv; x1.w *= wv;
         }
-        const uint32_t ca = tab_u32 + static_cast<uint32_t>(lb) * ROWB + ((j0 ^ ((static_cast<uint32_t>(lb) >> SH) & MSK)) << 4);
+        const uint32_t ca = tab_sub + static_cast<uint32_t>(lb) * ROWB + ((j0 ^ ((static_cast<uint32_t>(lb) >> SH) & MSK)) << 4);
         for (int rr = 0; rr <= maxr; ++rr) {
           if (ok && rank == rr) {
             float4 c = lds128(ca);
@@ -207,23 +231,24 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
               e.x += x1.x; e.y += x1.y; e.z += x1.z; e.w += x1.w;
               sts128(ca ^ 16u, e);
             }
-            if (counts) wtab[lb] += wv;
           }
           if (maxr) __syncwarp();
         }
       }
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bars_u32 + (2 * NSTAGE + s) * 8);
-      if (++s == NSTAGE) { s = 0; ph ^= 1u; }
+      if (lane == 0) ptx::mbar_arrive(bars_u32 + B_EMPTY + s * 8);
+      if (++s == static_cast<uint32_t>(p.nstage)) { s = 0; ph ^= 1u; }
     }
   }
   __syncthreads();
-  float* outS     = p.partial_S + static_cast<size_t>(blockIdx.x) * p.k * p.d;
-  const int wcols = min(NC * 4, p.d - cs);
+  float* outS      = p.partial_S + static_cast<size_t>(blockIdx.x) * p.k * p.d;
+  const int scols  = NC * 4;                              // columns per sub-slice
+  const int wcols  = min(p.nb * scols, p.d - cs);
   for (int i = threadIdx.x; i < p.k * wcols; i += blockDim.x) {
     const int j = i / wcols, c = i % wcols;
-    const int pc = ((((c >> 2) ^ ((j >> SH) & MSK)) << 2) | (c & 3));
-    outS[static_cast<size_t>(j) * p.d + cs + c] = tab[static_cast<size_t>(j) * (NC * 4) + pc];
+    const int sb = c / scols, cc = c % scols;
+    const int pc = ((((cc >> 2) ^ ((j >> SH) & MSK)) << 2) | (cc & 3));
+    outS[static_cast<size_t>(j) * p.d + cs + c] = tab[static_cast<size_t>(sb) * p.k * scols + static_cast<size_t>(j) * scols + pc];
   }
   if (slice == 0) {
     float* outW = p.partial_W + static_cast<size_t>(blockIdx.x) * p.k;
@@ -261,47 +286,63 @@ reduce_partials_f32_kernel(const float* __restrict__ partial_S, const float* __r
 }  // namespace
 
 struct TmaUpdatePlan {
-  int ds = 0, tr = 0, warps = 0, slices = 0, ctas_per_sm = 0, log2L = 0, swizzled = 0;
+  int ds = 0, tr = 0, warps = 0, slices = 0, ctas_per_sm = 0, nb = 1, nstage = 3;
   size_t smem = 0;
-  uint32_t stage_bytes = 0;
+  uint32_t sub_bytes = 0;
 };
 
+// Choose (sub-slices per CTA, CTAs per SM, ring depth, tile rows) to maximise the bytes the TMA ring keeps
+// in flight per SM (the measured limiter: ring turn-around is ~2-3 us) with >= 8 consumer warps per SM
+// when the table allows it.
 static TmaUpdatePlan plan_tma_update(const Handle& h, int d, int k)
 {
-  TmaUpdatePlan pl;
-  const int ds = d >= 32 ? 32 : d;   // 128-byte row segments, or whole (short) rows
-  if (ds % 4 != 0) return pl;
-  const size_t table    = (static_cast<size_t>(k) * ds + ((k + 3) & ~3)) * 4;
+  TmaUpdatePlan best;
+  double best_score = -1.0;
+  if (d % 4 != 0) return best;
   const size_t sm_total = 228 * 1024;
-  const int warps       = std::max(1, ds / 8);   // consumers: two 16-byte chunks of every row each
-  // candidates: as many CTAs per SM as fit with >= 8 KB tiles (>= 64 rows of 128 B), up to 16 consumer warps
-  for (int min_tile : {8192, 4096, 2048}) {
-    for (int per_sm = std::max(1, std::min(8, 16 / warps)); per_sm >= 1; --per_sm) {
+  const int sub_cols    = d >= 32 ? 32 : d;
+  const int cons_per_sub = std::max(1, sub_cols / 8);
+  for (int nb = 1; nb <= ((d >= 64) ? 2 : 1); ++nb) {
+    const int ds       = sub_cols * nb;
+    const size_t table = (static_cast<size_t>(k) * ds + ((k + 3) & ~3)) * 4;
+    for (int per_sm = 1; per_sm <= 8; ++per_sm) {
       const size_t budget = std::min<size_t>(h.smem_optin, sm_total / per_sm - 1024);
-      const size_t fixed  = table + 1024 + 256;
-      if (fixed + NSTAGE * (static_cast<size_t>(min_tile) + 1024) > budget) continue;
-      size_t stage_budget = (budget - fixed) / NSTAGE;
-      stage_budget        = std::min<size_t>(stage_budget, 16384 + 2048);
-      // X tile + (labels + meta) rounded up to 1 KB
-      int tr = static_cast<int>((stage_budget - 1024) / (static_cast<size_t>(ds) * 4 + 8));
-      tr     = std::min(tr, 256);
-      const int gran = std::max(32, 1024 / (ds * 4));  // tile bytes multiple of 1 KB; whole 32-row groups
-      tr -= tr % gran;
-      if (tr < gran || static_cast<size_t>(tr) * ds * 4 < static_cast<size_t>(min_tile)) continue;
-      pl.ds          = ds;
-      pl.tr          = tr;
-      pl.swizzled    = ds >= 8 ? 1 : 0;
-      pl.warps       = warps;
-      pl.log2L       = 0;
-      pl.slices      = static_cast<int>(ceil_div(d, ds));
-      pl.ctas_per_sm = per_sm;
-      pl.stage_bytes = static_cast<uint32_t>(tr) * ds * 4;
-      const uint32_t lab = (static_cast<uint32_t>(tr) * 8 + 1023u) & ~1023u;
-      pl.smem = NSTAGE * (pl.stage_bytes + lab) + table + 3 * NSTAGE * 8 + 1024 + 64;
-      return pl;
+      const size_t fixed  = table + 1024 + 3 * MAX_NSTAGE * 8 + 256;
+      if (fixed + 2 * 5120 > budget) continue;
+      for (int nstage = 2; nstage <= MAX_NSTAGE; ++nstage) {
+        const size_t stage_budget = (budget - fixed) / nstage;
+        if (stage_budget < 4096 + 1024) break;
+        // rows per tile: tile = nb sub-tiles of tr x sub_cols floats + labels/meta (8 B per row, 1 KB granules)
+        int tr = static_cast<int>((stage_budget - 1024) / (static_cast<size_t>(ds) * 4 + 8));
+        tr     = std::min(tr, 256);
+        const int gran = std::max(32, 1024 / (sub_cols * 4));
+        tr -= tr % gran;
+        if (tr < gran) continue;
+        const size_t tile_bytes = static_cast<size_t>(tr) * ds * 4;
+        if (tile_bytes < 4096) continue;
+        const int cons_sm       = per_sm * nb * cons_per_sub;
+        const double inflight   = static_cast<double>(per_sm) * nstage * tile_bytes;       // bytes per SM
+        // consumers below 8 per SM are the limiter; beyond ~12 extra warps do not help
+        const double score = std::min(inflight, 160.0 * 1024) * std::min(cons_sm, 12) / 12.0 +
+                             (tile_bytes >= 8192 ? 1.0 : 0.0);
+        if (score > best_score) {
+          best_score       = score;
+          best.ds          = ds;
+          best.nb          = nb;
+          best.tr          = tr;
+          best.nstage      = nstage;
+          best.warps       = nb * cons_per_sub;
+          best.slices      = static_cast<int>(ceil_div(d, ds));
+          best.ctas_per_sm = per_sm;
+          best.sub_bytes   = static_cast<uint32_t>(tr) * sub_cols * 4;
+          const uint32_t lab = (static_cast<uint32_t>(tr) * 8 + 1023u) & ~1023u;
+          best.smem = static_cast<size_t>(nstage) * (static_cast<size_t>(nb) * best.sub_bytes + lab) + table +
+                      3 * MAX_NSTAGE * 8 + 1024 + 64;
+        }
+      }
     }
   }
-  return pl;
+  return best;
 }
 
 bool tma_update_supported(const Handle& h, int d, int k)
@@ -329,9 +370,9 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
   p.k           = k;
   p.ds          = pl.ds;
   p.tr          = pl.tr;
-  p.log2L       = pl.log2L;
-  p.swizzled    = pl.swizzled;
-  p.stage_bytes = pl.stage_bytes;
+  p.nb          = pl.nb;
+  p.nstage      = pl.nstage;
+  p.sub_bytes   = pl.sub_bytes;
   p.tiles_total = ceil_div(n, pl.tr);
   int64_t row_blocks = std::max<int64_t>(1, static_cast<int64_t>(h.sm_count) * pl.ctas_per_sm / pl.slices);
   row_blocks         = std::min<int64_t>(row_blocks, p.tiles_total);
@@ -346,12 +387,13 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
   p.partial_S = partial_S.get();
   p.partial_W = partial_W.get();
 
-  const CUtensorMapSwizzle swz = pl.ds == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
-                                : pl.ds == 16 ? CU_TENSOR_MAP_SWIZZLE_64B
-                                : pl.ds == 8  ? CU_TENSOR_MAP_SWIZZLE_32B
-                                              : CU_TENSOR_MAP_SWIZZLE_NONE;
+  const int sub_cols = pl.ds / pl.nb;
+  const CUtensorMapSwizzle swz = sub_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : sub_cols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : sub_cols == 8  ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                 : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUtensorMap tm = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
-                               static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(pl.ds),
+                               static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(sub_cols),
                                static_cast<uint32_t>(pl.tr), swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   dim3 grid(static_cast<unsigned>(row_blocks), static_cast<unsigned>(pl.slices));
   const unsigned threads = (pl.warps + 2) * 32;
@@ -360,7 +402,7 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
     kern<<<grid, threads, pl.smem, h.stream>>>(tm, p);
   };
   const bool hw = w != nullptr;
-  switch (pl.ds) {
+  switch (sub_cols) {
     case 32: hw ? launch(accumulate_tma_kernel<8, true>) : launch(accumulate_tma_kernel<8, false>); break;
     case 16: hw ? launch(accumulate_tma_kernel<4, true>) : launch(accumulate_tma_kernel<4, false>); break;
     case 8: hw ? launch(accumulate_tma_kernel<2, true>) : launch(accumulate_tma_kernel<2, false>); break;
