@@ -19,6 +19,8 @@
 // The table is written once per CTA to a partials buffer; a second kernel sums the partials in a
 // fixed order in fp64 (deterministic, bitwise identical on every rank after the all-reduce).
 // Memory parallelism comes from the TMA ring (3 tiles in flight per CTA), not from occupancy.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 #include "tensormap.cuh"
@@ -36,6 +38,7 @@ struct UpdParams {
   int d, k, ds, tr;
   int nb;                   // 128-byte sub-slices per CTA slice (1 or 2) when ds >= 32
   int nstage;               // ring depth (2..8)
+  int na;                   // analyst warps (tile t is analysed by analyst t % na)
   uint32_t sub_bytes;       // one sub-tile: tr * min(ds,32) * 4, multiple of 1024
   const int32_t* labels;    // padded: readable up to n + tr
   const float* w;           // or null
@@ -79,13 +82,13 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity)
 }
 
 // NC = 16-byte chunks per sub-slice row: 8 (128B-swizzled, ds >= 32), 4 (64B), 2 (32B) or 1 (dense).
-// Warp roles: 0 = TMA producer, 1 = analyst, 2.. = consumers.  Lane = row: one warp instruction
+// Warp roles: 0 = TMA producer, 1..na = analysts (round-robin over tiles), then the consumers.  Lane = row: one warp instruction
 // covers 32 consecutive rows.  The analyst computes, once per 32-row group, each row's rank among
 // the rows of the group that share its label (match_any) and the group's maximum rank, and keeps the
 // per-cluster weights; consumers then apply the group in (max rank + 1) conflict-free rounds with no
 // warp-wide matching on their critical path.  Every consumer lane owns CPL 16-byte chunks of its row.
 template <int NC, bool HAS_W>
-__global__ void __launch_bounds__(320)
+__global__ void __launch_bounds__(416)
 accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams p)
 {
   constexpr int CPL      = NC >= 2 ? 2 : 1;                           // chunks per lane
@@ -104,19 +107,20 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
   const uint32_t tab_bytes  = static_cast<uint32_t>(p.k) * ROWB;       // one sub-slice table
   const uint32_t tab_u32    = base + p.nstage * stage_full;
   float* tab       = reinterpret_cast<float*>(g + p.nstage * stage_full);
-  float* wtab      = tab + static_cast<size_t>(p.nb) * p.k * (NC * 4);
-  uint64_t* bars   = reinterpret_cast<uint64_t*>(wtab + ((p.k + 3) & ~3));  // full | ready | empty, MAX_NSTAGE each
+  float* wtab      = tab + static_cast<size_t>(p.nb) * p.k * (NC * 4);     // [na][k4]: one weight table per analyst
+  const int k4     = (p.k + 3) & ~3;
+  uint64_t* bars   = reinterpret_cast<uint64_t*>(wtab + static_cast<size_t>(p.na) * k4);  // full | ready | empty
   const uint32_t bars_u32 = ptx::smem_u32(bars);
   const uint32_t B_FULL = 0, B_READY = MAX_NSTAGE * 8, B_EMPTY = 2 * MAX_NSTAGE * 8;
 
   const int warp    = threadIdx.x / 32;
   const int lane    = threadIdx.x % 32;
-  const int ncons   = blockDim.x / 32 - 2;
+  const int ncons   = blockDim.x / 32 - 1 - p.na;
   const int slice   = blockIdx.y;
   const int cs      = slice * p.ds;
 
   for (int i = threadIdx.x; i < p.nb * p.k * NC * 4; i += blockDim.x) tab[i] = 0.0f;
-  for (int i = threadIdx.x; i < p.k; i += blockDim.x) wtab[i] = 0.0f;
+  for (int i = threadIdx.x; i < p.na * k4; i += blockDim.x) wtab[i] = 0.0f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_NSTAGE; ++s) {
       ptx::mbar_init(bars_u32 + B_FULL + s * 8, 1);
@@ -148,12 +152,18 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
         if (++s == static_cast<uint32_t>(p.nstage)) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ---------------- analyst: ranks among equal labels per 32-row group; cluster weights ----------------
+  } else if (warp <= p.na) {
+    // ---------------- analysts: ranks among equal labels per 32-row group; cluster weights ----------------
     const unsigned below = (1u << lane) - 1u;
     const bool counts    = (slice == 0);
+    const int me         = warp - 1;
+    float* wtab_me       = wtab + static_cast<size_t>(me) * k4;
     uint32_t s = 0, ph = 0;
     for (int64_t t = t_begin; t < t_end; ++t) {
+      if (static_cast<int>((t - t_begin) % p.na) != me) {   // another analyst's tile
+        if (++s == static_cast<uint32_t>(p.nstage)) { s = 0; ph ^= 1u; }
+        continue;
+      }
       mbar_wait_spin(bars_u32 + B_FULL + s * 8, ph);
       const uint32_t ls = base + s * stage_full + x_bytes;
       const uint32_t ms = ls + lab_bytes;
@@ -172,11 +182,11 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
           if (!HAS_W) {
             // the last of each set of equal labels adds the set's size: distinct addresses, no conflict
             const int cnt = __popc(peers);
-            if (ok && rank == cnt - 1) wtab[lb] += static_cast<float>(cnt);
+            if (ok && rank == cnt - 1) wtab_me[lb] += static_cast<float>(cnt);
           } else {
             const float wv = ok ? __ldg(p.w + row0 + r) : 0.0f;
             for (int rr = 0; rr <= maxr; ++rr) {
-              if (ok && rank == rr) wtab[lb] += wv;
+              if (ok && rank == rr) wtab_me[lb] += wv;
               __syncwarp();
             }
           }
@@ -188,7 +198,7 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
     }
   } else {
     // ---------------- consumers ----------------
-    const int cw      = warp - 2;
+    const int cw      = warp - 1 - p.na;
     const int sub     = cw / CONS_PER_SUB;                                   // 128-byte sub-slice
     const uint32_t j0 = static_cast<uint32_t>(cw % CONS_PER_SUB) * CPL;     // first owned logical chunk (even)
     const uint32_t tab_sub = tab_u32 + sub * tab_bytes;
@@ -252,7 +262,11 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
   }
   if (slice == 0) {
     float* outW = p.partial_W + static_cast<size_t>(blockIdx.x) * p.k;
-    for (int i = threadIdx.x; i < p.k; i += blockDim.x) outW[i] = wtab[i];
+    for (int i = threadIdx.x; i < p.k; i += blockDim.x) {
+      float acc = 0.0f;
+      for (int a = 0; a < p.na; ++a) acc += wtab[static_cast<size_t>(a) * k4 + i];
+      outW[i] = acc;
+    }
   }
 }
 
@@ -286,7 +300,7 @@ reduce_partials_f32_kernel(const float* __restrict__ partial_S, const float* __r
 }  // namespace
 
 struct TmaUpdatePlan {
-  int ds = 0, tr = 0, warps = 0, slices = 0, ctas_per_sm = 0, nb = 1, nstage = 3;
+  int ds = 0, tr = 0, warps = 0, slices = 0, ctas_per_sm = 0, nb = 1, nstage = 3, na = 2;
   size_t smem = 0;
   uint32_t sub_bytes = 0;
 };
@@ -294,6 +308,13 @@ struct TmaUpdatePlan {
 // Choose (sub-slices per CTA, CTAs per SM, ring depth, tile rows) to maximise the bytes the TMA ring keeps
 // in flight per SM (the measured limiter: ring turn-around is ~2-3 us) with >= 8 consumer warps per SM
 // when the table allows it.
+static int tma_analysts()
+{
+  const char* e = std::getenv("CUML_B200_ANALYSTS");
+  int na        = e ? std::atoi(e) : 2;
+  return std::max(1, std::min(4, na));
+}
+
 static TmaUpdatePlan plan_tma_update(const Handle& h, int d, int k)
 {
   TmaUpdatePlan best;
@@ -304,7 +325,8 @@ static TmaUpdatePlan plan_tma_update(const Handle& h, int d, int k)
   const int cons_per_sub = std::max(1, sub_cols / 8);
   for (int nb = 1; nb <= ((d >= 64) ? 2 : 1); ++nb) {
     const int ds       = sub_cols * nb;
-    const size_t table = (static_cast<size_t>(k) * ds + ((k + 3) & ~3)) * 4;
+    const int na       = tma_analysts();
+    const size_t table = (static_cast<size_t>(k) * ds + static_cast<size_t>(na) * ((k + 3) & ~3)) * 4;
     for (int per_sm = 1; per_sm <= 8; ++per_sm) {
       const size_t budget = std::min<size_t>(h.smem_optin, sm_total / per_sm - 1024);
       const size_t fixed  = table + 1024 + 3 * MAX_NSTAGE * 8 + 256;
@@ -331,6 +353,7 @@ static TmaUpdatePlan plan_tma_update(const Handle& h, int d, int k)
           best.nb          = nb;
           best.tr          = tr;
           best.nstage      = nstage;
+          best.na          = na;
           best.warps       = nb * cons_per_sub;
           best.slices      = static_cast<int>(ceil_div(d, ds));
           best.ctas_per_sm = per_sm;
@@ -372,6 +395,7 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
   p.tr          = pl.tr;
   p.nb          = pl.nb;
   p.nstage      = pl.nstage;
+  p.na          = pl.na;
   p.sub_bytes   = pl.sub_bytes;
   p.tiles_total = ceil_div(n, pl.tr);
   int64_t row_blocks = std::max<int64_t>(1, static_cast<int64_t>(h.sm_count) * pl.ctas_per_sm / pl.slices);
@@ -396,7 +420,7 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
                                static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(sub_cols),
                                static_cast<uint32_t>(pl.tr), swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
   dim3 grid(static_cast<unsigned>(row_blocks), static_cast<unsigned>(pl.slices));
-  const unsigned threads = (pl.warps + 2) * 32;
+  const unsigned threads = (pl.warps + 1 + pl.na) * 32;
   auto launch = [&](auto kern) {
     CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
     kern<<<grid, threads, pl.smem, h.stream>>>(tm, p);

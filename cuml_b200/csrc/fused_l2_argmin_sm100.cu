@@ -27,6 +27,14 @@ namespace cb2 {
 
 namespace {
 
+// timed mbarrier wait: accumulates the cycles spent waiting (role-level profiling, CTA 0 only)
+#define CB2_TIMED_WAIT(bar, parity, acc)            \
+  do {                                              \
+    const long long t__ = clock64();                \
+    ptx::mbar_wait((bar), (parity));                \
+    (acc) += clock64() - t__;                       \
+  } while (0)
+
 constexpr int TILE_M       = 128;
 constexpr int KBLOCK       = 32;              // fp32 elements per 128-byte swizzle row
 constexpr int KBLOCK_BYTES = TILE_M * 128;    // one K-block of an A tile: 16 KB
@@ -51,6 +59,7 @@ struct FusedParams {
   const float* cnh;  // [k_pad] 1/2 ||c||^2, +inf for padding
   int32_t* labels;
   float* dbg_dots;   // optional [n, k_pad] dump of the x.c accumulators (tests only)
+  long long* dbg_clk; // optional [16]: per-role (wait cycles, total cycles) of CTA 0 (env CUML_B200_DBG_CLK)
   int dbg_skip;      // profiling knob (env CUML_B200_DBG_SKIP): 1 = no hi/lo split, 2 = no MMA, 4 = no argmin
 };
 
@@ -80,6 +89,8 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
   const int cbeg    = (p.bn >= 64) ? half * (p.bn / 2) : 0;
   const int cend    = (p.bn >= 64) ? cbeg + p.bn / 2 : (half == 0 ? p.bn : 0);
   uint32_t acc_cnt  = 0;
+  long long ewait = 0;
+  const long long estart = clock64();
   // 1/2||c||^2 of the next centroid tile is fetched one tile ahead (registers), so its global-load
   // latency never sits on the epilogue's critical path
   float pre = 0.f;
@@ -100,7 +111,11 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
         fetch_cn(nt + 1 == p.k_tiles ? 0 : nt + 1);
         ptx::named_bar_sync(1, 256);
       }
-      ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[acc]), pacc);
+      {
+        const long long t__ = clock64();
+        ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[acc]), pacc);
+        ewait += clock64() - t__;
+      }
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.bn;
       const int jbase      = nt * p.bn;
@@ -158,6 +173,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
     }
     ptx::named_bar_sync(3, 256);  // mrg_* may be overwritten by the next tile
   }
+  if (p.dbg_clk && blockIdx.x == 0 && et == 0) { p.dbg_clk[8] = ewait; p.dbg_clk[9] = clock64() - estart; }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -215,22 +231,28 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
 
   if (warp == 0) {
     // ===================== A producer: raw X K-blocks into the slot ring =====================
-    if (lane == 0) {
+    {
       uint32_t a_cnt = 0;
+      long long wcyc = 0;
+      const long long tstart = clock64();
       for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
         for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
           const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
-          ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[sa]), pa ^ 1u);
-          const uint32_t full = ptx::smem_u32(&bars->a_raw_full[sa]);
-          ptx::mbar_arrive_expect_tx(full, KBLOCK_BYTES);
-          ptx::tma_load_2d_hint(a_base + sa * A_SLOT_BYTES, &tm_x, kbi * KBLOCK, static_cast<int32_t>(tile * TILE_M),
-                                full, ptx::kEvictFirst);
+          CB2_TIMED_WAIT(ptx::smem_u32(&bars->a_empty[sa]), pa ^ 1u, wcyc);
+          if (ptx::elect_one()) {
+            const uint32_t full = ptx::smem_u32(&bars->a_raw_full[sa]);
+            ptx::mbar_arrive_expect_tx(full, KBLOCK_BYTES);
+            ptx::tma_load_2d_hint(a_base + sa * A_SLOT_BYTES, &tm_x, kbi * KBLOCK, static_cast<int32_t>(tile * TILE_M),
+                                  full, ptx::kEvictFirst);
+          }
+          __syncwarp();
         }
       }
+      if (p.dbg_clk && blockIdx.x == 0 && lane == 0) { p.dbg_clk[0] = wcyc; p.dbg_clk[1] = clock64() - tstart; }
     }
   } else if (warp == 2) {
     // ===================== B producer: centroid hi/lo K-blocks =====================
-    if (lane == 0) {
+    {
       uint32_t b_cnt = 0;
       for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
         if (p.b_resident && tile != blockIdx.x) break;  // resident centroids: loaded once per CTA
@@ -238,11 +260,14 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sb = b_cnt % p.b_stages, pb = (b_cnt / p.b_stages) & 1u;
             ptx::mbar_wait(ptx::smem_u32(&bars->b_empty[sb]), pb ^ 1u);
-            const uint32_t full = ptx::smem_u32(&bars->b_full[sb]);
-            ptx::mbar_arrive_expect_tx(full, b_stage_bytes);
-            const uint32_t dst = b_base + sb * b_stage_bytes;
-            ptx::tma_load_2d_hint(dst, &tm_hi, kbi * KBLOCK, nt * p.bn, full, ptx::kEvictLast);
-            ptx::tma_load_2d_hint(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, nt * p.bn, full, ptx::kEvictLast);
+            if (ptx::elect_one()) {
+              const uint32_t full = ptx::smem_u32(&bars->b_full[sb]);
+              ptx::mbar_arrive_expect_tx(full, b_stage_bytes);
+              const uint32_t dst = b_base + sb * b_stage_bytes;
+              ptx::tma_load_2d_hint(dst, &tm_hi, kbi * KBLOCK, nt * p.bn, full, ptx::kEvictLast);
+              ptx::tma_load_2d_hint(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, nt * p.bn, full, ptx::kEvictLast);
+            }
+            __syncwarp();
           }
         }
       }
@@ -251,10 +276,12 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     // ===================== converter: raw -> (hi in place, lo) =====================
     const int ct = threadIdx.x - 128;  // 0..127
     uint32_t a_cnt = 0;
+    long long wcyc = 0;
+    const long long tstart = clock64();
     for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
       for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
         const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
-        ptx::mbar_wait(ptx::smem_u32(&bars->a_raw_full[sa]), pa);
+        CB2_TIMED_WAIT(ptx::smem_u32(&bars->a_raw_full[sa]), pa, wcyc);
         uint4* hi = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES);
         // 16-byte chunks the tensor core will read in this K-block: 2 per K=8 step that holds real columns
@@ -279,28 +306,33 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready[sa]));
       }
     }
+    if (p.dbg_clk && blockIdx.x == 0 && ct == 0) { p.dbg_clk[2] = wcyc; p.dbg_clk[3] = clock64() - tstart; }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp runs the loop in uniform control flow (so descriptors live in uniform registers and
+    // each tcgen05.mma is a single predicated instruction); one elected lane issues.
+    {
       const uint32_t idesc = ptx::umma_idesc_tf32(TILE_M, p.bn);
       uint32_t a_cnt0 = 0, b_cnt = 0, acc_cnt = 0;
+      long long wacc = 0, wa = 0, wb = 0;
+      const long long tstart = clock64();
       for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, a_cnt0 += p.kb) {
         for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
           const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
-          ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
+          CB2_TIMED_WAIT(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u, wacc);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * p.bn;
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t a_cnt = a_cnt0 + kbi;
             const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
-            if (nt == 0) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[sa]), pa);  // first use of this X K-block
+            if (nt == 0) CB2_TIMED_WAIT(ptx::smem_u32(&bars->a_ready[sa]), pa, wa);  // first use of this X K-block
             uint32_t sb = b_cnt % p.b_stages;
             const uint32_t pb = (b_cnt / p.b_stages) & 1u;
             if (p.b_resident) {
               sb = nt * p.kb + kbi;
               if (tile == static_cast<int64_t>(blockIdx.x)) ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), 0u);
             } else {
-              ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), pb);
+              CB2_TIMED_WAIT(ptx::smem_u32(&bars->b_full[sb]), pb, wb);
             }
             ptx::tc_fence_after();
             const uint64_t da_hi = ptx::umma_desc_sw128(a_base + sa * A_SLOT_BYTES);
@@ -308,22 +340,29 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             const uint64_t db_hi = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes);
             const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
             const int nks = min(4, (p.d - kbi * KBLOCK + 7) / 8);  // K=8 steps that hold real columns
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              if (ks >= nks || (p.dbg_skip & 2)) break;
-              const uint64_t adv = static_cast<uint64_t>(ks * 2);  // 8 tf32 = 32 bytes = 2 x 16B units
-              // small terms first, then the dominant hi.hi term
-              ptx::mma_tf32_ss(d_tmem, da_lo + adv, db_hi + adv, idesc, (kbi | ks) != 0 ? 1u : 0u);
-              ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
-              ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+              for (int ks = 0; ks < 4; ++ks) {
+                if (ks >= nks || (p.dbg_skip & 2)) break;
+                const uint64_t adv = static_cast<uint64_t>(ks * 2);  // 8 tf32 = 32 bytes = 2 x 16B units
+                // small terms first, then the dominant hi.hi term
+                ptx::mma_tf32_ss(d_tmem, da_lo + adv, db_hi + adv, idesc, (kbi | ks) != 0 ? 1u : 0u);
+                ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+                ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+              }
+              if (!p.b_resident) ptx::mma_commit(ptx::smem_u32(&bars->b_empty[sb]));  // frees the B stage
+              // last centroid tile: this X K-block is not needed again -> release its slot early so
+              // the next row tile's load + hi/lo split overlaps the remaining K-blocks
+              if (nt == p.k_tiles - 1) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[sa]));
             }
-            if (!p.b_resident) ptx::mma_commit(ptx::smem_u32(&bars->b_empty[sb]));  // frees the B stage
-            // last centroid tile: this X K-block is not needed again -> release its slot early so
-            // the next row tile's load + hi/lo split overlaps the remaining K-blocks
-            if (nt == p.k_tiles - 1) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[sa]));
+            __syncwarp();
           }
-          ptx::mma_commit(ptx::smem_u32(&bars->acc_full[acc]));  // accumulator ready for the epilogue
+          if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->acc_full[acc]));  // accumulator ready
+          __syncwarp();
         }
+      }
+      if (p.dbg_clk && blockIdx.x == 0 && lane == 0) {
+        p.dbg_clk[4] = wacc; p.dbg_clk[5] = wa; p.dbg_clk[6] = wb; p.dbg_clk[7] = clock64() - tstart;
       }
     }
   } else if (warp >= 8) {
@@ -410,22 +449,25 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
 
   if (warp == 0) {
     // ===================== X producer (own 128 rows) =====================
-    if (lane == 0) {
+    {
       uint32_t a_cnt = 0;
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
         const int32_t row0 = static_cast<int32_t>(pt * 2 * TILE_M + cta_rank * TILE_M);
         for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
           const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
           ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[sa]), pa ^ 1u);
-          const uint32_t full = ptx::smem_u32(&bars->a_raw_full[sa]);
-          ptx::mbar_arrive_expect_tx(full, KBLOCK_BYTES);
-          ptx::tma_load_2d_hint(a_base + sa * A_SLOT_BYTES, &tm_x, kbi * KBLOCK, row0, full, ptx::kEvictFirst);
+          if (ptx::elect_one()) {
+            const uint32_t full = ptx::smem_u32(&bars->a_raw_full[sa]);
+            ptx::mbar_arrive_expect_tx(full, KBLOCK_BYTES);
+            ptx::tma_load_2d_hint(a_base + sa * A_SLOT_BYTES, &tm_x, kbi * KBLOCK, row0, full, ptx::kEvictFirst);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 2) {
     // ===================== centroid producer (own half of every block) =====================
-    if (lane == 0) {
+    {
       uint32_t b_cnt = 0;
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
         if (p.b_resident && pt != pair) break;
@@ -433,13 +475,16 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sb = b_cnt % p.b_stages, pb = (b_cnt / p.b_stages) & 1u;
             ptx::mbar_wait(ptx::smem_u32(&bars->b_empty[sb]), pb ^ 1u);
-            const uint32_t full_local  = ptx::smem_u32(&bars->b_full[sb]);
-            const uint32_t full_leader = ptx::mapa(full_local, 0);
-            if (leader) ptx::mbar_arrive_expect_tx(full_local, 2u * b_stage_bytes);  // bytes of BOTH CTAs
-            const uint32_t dst = b_base + sb * b_stage_bytes;
-            const int32_t crow = nt * p.bn + static_cast<int32_t>(cta_rank) * half_n;
-            ptx::tma_load_2d_2cta(dst, &tm_hi, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
-            ptx::tma_load_2d_2cta(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+            if (ptx::elect_one()) {
+              const uint32_t full_local  = ptx::smem_u32(&bars->b_full[sb]);
+              const uint32_t full_leader = ptx::mapa(full_local, 0);
+              if (leader) ptx::mbar_arrive_expect_tx(full_local, 2u * b_stage_bytes);  // bytes of BOTH CTAs
+              const uint32_t dst = b_base + sb * b_stage_bytes;
+              const int32_t crow = nt * p.bn + static_cast<int32_t>(cta_rank) * half_n;
+              ptx::tma_load_2d_2cta(dst, &tm_hi, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+              ptx::tma_load_2d_2cta(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+            }
+            __syncwarp();
           }
         }
       }
@@ -475,8 +520,8 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (pair leader only) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (pair leader only; warp-uniform loop, one elected lane issues) ====
+    if (leader) {
       const uint32_t idesc = ptx::umma_idesc_tf32(2 * TILE_M, p.bn);
       uint32_t a_cnt0 = 0, b_cnt = 0, acc_cnt = 0;
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs, a_cnt0 += p.kb) {
@@ -503,18 +548,22 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
             const uint64_t db_hi = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes);
             const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
             const int nks = min(4, (p.d - kbi * KBLOCK + 7) / 8);
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              if (ks >= nks) break;
-              const uint64_t adv = static_cast<uint64_t>(ks * 2);
-              ptx::mma_tf32_ss_2cta(d_tmem, da_lo + adv, db_hi + adv, idesc, (kbi | ks) != 0 ? 1u : 0u);
-              ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
-              ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+              for (int ks = 0; ks < 4; ++ks) {
+                if (ks >= nks) break;
+                const uint64_t adv = static_cast<uint64_t>(ks * 2);
+                ptx::mma_tf32_ss_2cta(d_tmem, da_lo + adv, db_hi + adv, idesc, (kbi | ks) != 0 ? 1u : 0u);
+                ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+                ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+              }
+              if (!p.b_resident) ptx::mma_commit_2cta(ptx::smem_u32(&bars->b_empty[sb]), 3);
+              if (nt == p.k_tiles - 1) ptx::mma_commit_2cta(ptx::smem_u32(&bars->a_empty[sa]), 3);
             }
-            if (!p.b_resident) ptx::mma_commit_2cta(ptx::smem_u32(&bars->b_empty[sb]), 3);
-            if (nt == p.k_tiles - 1) ptx::mma_commit_2cta(ptx::smem_u32(&bars->a_empty[sa]), 3);
+            __syncwarp();
           }
-          ptx::mma_commit_2cta(ptx::smem_u32(&bars->acc_full[acc]), 3);
+          if (ptx::elect_one()) ptx::mma_commit_2cta(ptx::smem_u32(&bars->acc_full[acc]), 3);
+          __syncwarp();
         }
       }
     }
@@ -692,6 +741,13 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     const char* e = std::getenv("CUML_B200_DBG_SKIP");
     p.dbg_skip    = e ? std::atoi(e) : 0;
   }
+  DevBuf<long long> clk;
+  const bool want_clk = std::getenv("CUML_B200_DBG_CLK") != nullptr;
+  if (want_clk) {
+    clk.alloc(16, h.stream);
+    CB2_CUDA(cudaMemsetAsync(clk.get(), 0, 16 * sizeof(long long), h.stream));
+    p.dbg_clk = clk.get();
+  }
 
   CUtensorMap tm_x  = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
                                   static_cast<uint64_t>(d) * sizeof(float), KBLOCK, TILE_M,
@@ -712,6 +768,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   }
   EventPair ev{};
   if (h.timing) ev = h.begin_event();
+  const long long grid_dbg = pair ? h.sm_count / 2 : h.sm_count;
   if (pair) {
     // one CTA pair per TPC; grid must be even (cluster dims 2x1x1 are compiled into the kernel)
     const int64_t pair_tiles = (p.m_tiles + 1) / 2;
@@ -723,6 +780,14 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   }
   CB2_CHECK_LAUNCH();
   if (h.timing) h.end_event(ev, true);
+  if (want_clk) {
+    long long hc[16];
+    CB2_CUDA(cudaMemcpyAsync(hc, clk.get(), sizeof(hc), cudaMemcpyDeviceToHost, h.stream));
+    CB2_CUDA(cudaStreamSynchronize(h.stream));
+    std::printf("[cuml_b200 clk] tiles/CTA %lld | producer wait %lld / %lld | converter wait %lld / %lld | mma wait acc %lld a %lld b %lld / %lld | "
+                "epilogue wait %lld / %lld (cycles, CTA 0)\n",
+                static_cast<long long>((p.m_tiles + grid_dbg - 1) / grid_dbg), hc[0], hc[1], hc[2], hc[3], hc[4], hc[5], hc[6], hc[7], hc[8], hc[9]);
+  }
 }
 
 }  // namespace cb2

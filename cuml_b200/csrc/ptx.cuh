@@ -99,6 +99,18 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const void* tmap,
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // CacheHintSm90::EVICT_FIRST
 constexpr uint64_t kEvictLast  = 0x14F0000000000000ull;  // CacheHintSm90::EVICT_LAST
 
+// one lane of a fully converged warp (the idiom the compiler recognises for single-thread tcgen05 issue)
+__device__ __forceinline__ bool elect_one()
+{
+  uint32_t pred;
+  asm volatile(
+    "{\n\t.reg .pred P;\n\t"
+    "elect.sync _|P, 0xffffffff;\n\t"
+    "selp.u32 %0, 1, 0, P;\n\t}"
+    : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- tcgen05
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols)
 {
