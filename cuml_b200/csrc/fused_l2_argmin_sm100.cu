@@ -41,7 +41,8 @@ constexpr int KBLOCK_BYTES = TILE_M * 128;    // one K-block of an A tile: 16 KB
 constexpr int NUM_THREADS  = 512;             // 16 warps: producers, MMA issuer, 4 converter, 8 epilogue
 constexpr int MAX_STAGES   = 4;
 constexpr int MAX_A_SLOTS  = 8;
-constexpr int MAX_ACC      = 8;   // TMEM accumulator stages (512 columns / BN, at most 8)
+constexpr int MAX_ACC      = 8;
+constexpr int MAX_RAW      = 12;  // raw X K-block slots (16 KB each) of the A-in-TMEM variant   // TMEM accumulator stages (512 columns / BN, at most 8)
 constexpr int A_SLOT_BYTES = 2 * KBLOCK_BYTES;  // hi then lo
 
 struct FusedParams {
@@ -55,6 +56,8 @@ struct FusedParams {
   int b_stages;   // 2..4
   int b_resident; // all k_tiles*kb centroid blocks fit the B stages: load once, never release
   int n_acc;      // TMEM accumulator stages: min(MAX_ACC, 512 / bn)
+  int raw_slots;  // A-in-TMEM variant: raw X ring depth; a_slots then counts 64-column TMEM operand slots
+  int a_col0;     // A-in-TMEM variant: first TMEM column of the operand slots (= n_acc * bn)
   uint32_t tmem_cols;
   const float* cnh;  // [k_pad] 1/2 ||c||^2, +inf for padding
   int32_t* labels;
@@ -67,6 +70,7 @@ struct Barriers {
   uint64_t a_raw_full[MAX_A_SLOTS], a_ready[MAX_A_SLOTS], a_empty[MAX_A_SLOTS];
   uint64_t b_full[MAX_STAGES], b_empty[MAX_STAGES];
   uint64_t acc_full[MAX_ACC], acc_empty[MAX_ACC];
+  uint64_t raw_full[MAX_RAW], raw_empty[MAX_RAW];   // A-in-TMEM variant: raw X ring in shared memory
   uint32_t tmem_base;
 };
 
@@ -581,6 +585,251 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   if (warp == 1) ptx::tmem_dealloc_2cta(tmem_base, p.tmem_cols);
 }
 
+// =================================================================================================
+// A-in-TMEM variant (the fast one).  Measured on B200 (tools/micro/mma_rate.cu): a kind::tf32 MMA with
+// both operands in shared memory costs 43 + N/2 cycles (171 at N = 256 -> 861 TFLOP/s), with the A
+// operand in tensor memory it runs at the N/2 floor (64 cycles at N = 128 -> 1149 TFLOP/s).  So the
+// converter warps write the hi / lo split of each X K-block straight into TMEM (tcgen05.st, thread = row)
+// instead of shared memory; the raw X tiles ride a deep 16 KB-per-slot ring; BN <= 128 leaves TMEM room
+// for the operand slots:  columns [0, n_acc*BN) accumulators | a_slots x (hi 32 | lo 32) operand columns.
+// PAIR = true runs it as a CTA pair (cta_group::2): M = 256, each CTA holds BN/2 centroid rows.
+template <bool PAIR>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+fused_l2_argmin_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
+                          const __grid_constant__ CUtensorMap tm_lo, const FusedParams p)
+{
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t raw_base = ptx::smem_u32(smem_dyn);
+  const uint32_t base     = (raw_base + 1023u) & ~1023u;
+  uint8_t* gbase          = smem_dyn + (base - raw_base);
+
+  const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const bool leader       = cta_rank == 0;
+  const int64_t unit      = PAIR ? (blockIdx.x >> 1) : blockIdx.x;       // CTA or CTA pair
+  const int64_t n_units   = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const int rows_unit     = PAIR ? 2 * TILE_M : TILE_M;
+  const int64_t tiles     = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;      // tiles of rows_unit rows
+  const int my_bn         = PAIR ? p.bn / 2 : p.bn;                       // centroid rows held by this CTA
+
+  const uint32_t b_half_bytes  = static_cast<uint32_t>(my_bn) * 128u;
+  const uint32_t b_stage_bytes = 2u * b_half_bytes;                      // hi then lo
+  const uint32_t x_base  = base;                                         // raw ring
+  const uint32_t b_base  = x_base + p.raw_slots * KBLOCK_BYTES;
+  const uint32_t cn_off  = p.raw_slots * KBLOCK_BYTES + p.b_stages * b_stage_bytes;
+  float* cn_s            = reinterpret_cast<float*>(gbase + cn_off);     // [2][bn]
+  float* mrg_v           = cn_s + 2 * p.bn;
+  int* mrg_i             = reinterpret_cast<int*>(mrg_v + TILE_M);
+  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 2u * TILE_M * 4u);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  const uint32_t conv_arrivals = PAIR ? 8u : 4u;    // converter warps that feed one MMA
+  const uint32_t epi_arrivals  = PAIR ? 16u : 8u;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_RAW; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->raw_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->raw_empty[s]), 4);     // the CTA's own 4 converter warps
+    }
+    for (int s = 0; s < MAX_A_SLOTS; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->a_ready[s]), conv_arrivals);
+      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), 1);
+    }
+    for (int s = 0; s < MAX_ACC; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), epi_arrivals);
+    }
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->b_empty[s]), 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_x);
+    ptx::prefetch_tmap(&tm_hi);
+    ptx::prefetch_tmap(&tm_lo);
+  }
+  if (warp == 1) {
+    if (PAIR) {
+      ptx::tmem_alloc_2cta(ptx::smem_u32(&bars->tmem_base), p.tmem_cols);
+      ptx::tmem_relinquish_2cta();
+    } else {
+      ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), p.tmem_cols);
+      ptx::tmem_relinquish();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (PAIR) ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== raw X producer (own 128 rows) =====================
+    uint32_t cnt = 0;
+    for (int64_t t = unit; t < tiles; t += n_units) {
+      const int32_t row0 = static_cast<int32_t>(t * rows_unit + cta_rank * TILE_M);
+      for (int kbi = 0; kbi < p.kb; ++kbi, ++cnt) {
+        const uint32_t rs = cnt % p.raw_slots, rp = (cnt / p.raw_slots) & 1u;
+        ptx::mbar_wait(ptx::smem_u32(&bars->raw_empty[rs]), rp ^ 1u);
+        if (ptx::elect_one()) {
+          const uint32_t full = ptx::smem_u32(&bars->raw_full[rs]);
+          ptx::mbar_arrive_expect_tx(full, KBLOCK_BYTES);
+          ptx::tma_load_2d_hint(x_base + rs * KBLOCK_BYTES, &tm_x, kbi * KBLOCK, row0, full, ptx::kEvictFirst);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== centroid producer =====================
+    uint32_t b_cnt = 0;
+    for (int64_t t = unit; t < tiles; t += n_units) {
+      if (p.b_resident && t != unit) break;
+      for (int nt = 0; nt < p.k_tiles; ++nt) {
+        for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
+          const uint32_t sb = b_cnt % p.b_stages, pb = (b_cnt / p.b_stages) & 1u;
+          ptx::mbar_wait(ptx::smem_u32(&bars->b_empty[sb]), pb ^ 1u);
+          if (ptx::elect_one()) {
+            const uint32_t full_local = ptx::smem_u32(&bars->b_full[sb]);
+            const uint32_t dst        = b_base + sb * b_stage_bytes;
+            const int32_t crow        = nt * p.bn + static_cast<int32_t>(cta_rank) * my_bn;
+            if (PAIR) {
+              const uint32_t full_leader = ptx::mapa(full_local, 0);
+              if (leader) ptx::mbar_arrive_expect_tx(full_local, 2u * b_stage_bytes);  // bytes of BOTH CTAs
+              ptx::tma_load_2d_2cta(dst, &tm_hi, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+              ptx::tma_load_2d_2cta(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+            } else {
+              ptx::mbar_arrive_expect_tx(full_local, b_stage_bytes);
+              ptx::tma_load_2d_hint(dst, &tm_hi, kbi * KBLOCK, crow, full_local, ptx::kEvictLast);
+              ptx::tma_load_2d_hint(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, crow, full_local, ptx::kEvictLast);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== converter: raw row (shared) -> hi | lo operand columns (tensor memory) =========
+    const int quarter = warp & 3;
+    const int row     = quarter * 32 + lane;                       // row of the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    uint32_t cnt = 0;
+    for (int64_t t = unit; t < tiles; t += n_units) {
+      for (int kbi = 0; kbi < p.kb; ++kbi, ++cnt) {
+        const uint32_t rs = cnt % p.raw_slots, rp = (cnt / p.raw_slots) & 1u;
+        const uint32_t as = cnt % p.a_slots, ap = (cnt / p.a_slots) & 1u;
+        ptx::mbar_wait(ptx::smem_u32(&bars->raw_full[rs]), rp);
+        const uint4* src = reinterpret_cast<const uint4*>(gbase + rs * KBLOCK_BYTES + row * 128);
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const uint4 v = src[c ^ (row & 7)];                        // 128B swizzle: chunk ^= row & 7
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t h = w4[e] & 0xffffe000u;
+            hi[c * 4 + e]    = h;
+            lo[c * 4 + e]    = __float_as_uint(__uint_as_float(w4[e]) - __uint_as_float(h));
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->raw_empty[rs]));   // raw slot may be refilled
+        ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[as]), ap ^ 1u);             // MMAs that read this slot retired
+        ptx::tc_fence_after();
+        const uint32_t acol = tmem_base + lane_addr + p.a_col0 + as * 64;
+        ptx::tmem_st_32x32(acol, hi);
+        ptx::tmem_st_32x32(acol + 32, lo);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->a_ready[as]), 0));
+          else ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready[as]));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    if (leader) {
+      const uint32_t idesc = ptx::umma_idesc_tf32(PAIR ? 2 * TILE_M : TILE_M, p.bn);
+      uint32_t a_cnt0 = 0, b_cnt = 0, acc_cnt = 0;
+      for (int64_t t = unit; t < tiles; t += n_units, a_cnt0 += p.kb) {
+        for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
+          const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
+          ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * p.bn;
+          for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
+            const uint32_t a_cnt = a_cnt0 + kbi;
+            const uint32_t as = a_cnt % p.a_slots, ap = (a_cnt / p.a_slots) & 1u;
+            if (nt == 0) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[as]), ap);
+            uint32_t sb = b_cnt % p.b_stages;
+            const uint32_t pb = (b_cnt / p.b_stages) & 1u;
+            if (p.b_resident) {
+              sb = nt * p.kb + kbi;
+              if (t == unit) ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), 0u);
+            } else {
+              ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), pb);
+            }
+            ptx::tc_fence_after();
+            const uint32_t a_hi  = tmem_base + p.a_col0 + as * 64;
+            const uint32_t a_lo  = a_hi + 32;
+            const uint64_t db_hi = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes);
+            const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
+            const int nks = min(4, (p.d - kbi * KBLOCK + 7) / 8);
+            if (ptx::elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                if (ks >= nks) break;
+                const uint64_t adv = static_cast<uint64_t>(ks * 2);   // B: 8 tf32 = 32 bytes = 2 x 16B units
+                const uint32_t ak  = static_cast<uint32_t>(ks * 8);   // A: 8 TMEM columns per K = 8 step
+                const uint32_t first = (kbi | ks) != 0 ? 1u : 0u;
+                if (PAIR) {
+                  ptx::mma_tf32_ts_2cta(d_tmem, a_lo + ak, db_hi + adv, idesc, first);
+                  ptx::mma_tf32_ts_2cta(d_tmem, a_hi + ak, db_lo + adv, idesc, 1u);
+                  ptx::mma_tf32_ts_2cta(d_tmem, a_hi + ak, db_hi + adv, idesc, 1u);
+                } else {
+                  ptx::mma_tf32_ts(d_tmem, a_lo + ak, db_hi + adv, idesc, first);
+                  ptx::mma_tf32_ts(d_tmem, a_hi + ak, db_lo + adv, idesc, 1u);
+                  ptx::mma_tf32_ts(d_tmem, a_hi + ak, db_hi + adv, idesc, 1u);
+                }
+              }
+              if (PAIR) {
+                if (!p.b_resident) ptx::mma_commit_2cta(ptx::smem_u32(&bars->b_empty[sb]), 3);
+                if (nt == p.k_tiles - 1) ptx::mma_commit_2cta(ptx::smem_u32(&bars->a_empty[as]), 3);
+              } else {
+                if (!p.b_resident) ptx::mma_commit(ptx::smem_u32(&bars->b_empty[sb]));
+                if (nt == p.k_tiles - 1) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[as]));
+              }
+            }
+            __syncwarp();
+          }
+          if (ptx::elect_one()) {
+            if (PAIR) ptx::mma_commit_2cta(ptx::smem_u32(&bars->acc_full[acc]), 3);
+            else ptx::mma_commit(ptx::smem_u32(&bars->acc_full[acc]));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 8) {
+    // ===================== epilogue =====================
+    const int64_t n_mine = (tiles > unit) ? (tiles - unit + n_units - 1) / n_units : 0;
+    epilogue_role<PAIR>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, unit * rows_unit + cta_rank * TILE_M,
+                        n_units * rows_unit, n_mine);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (PAIR) ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  if (warp == 1) {
+    if (PAIR) ptx::tmem_dealloc_2cta(tmem_base, p.tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 // hi/lo split + half norms of the centroids into padded operand buffers
 __global__ void prepare_centroids_kernel(const float* __restrict__ C, int k, int d, int k_pad, int d_pad,
                                          float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ cnh)
@@ -683,6 +932,59 @@ bool use_2cta(const Handle& h, int d, int k)
   return plan_tiles_2cta(d, k, h.smem_optin).bn > 0;
 }
 
+// Plan for the A-in-TMEM kernel: BN <= 128, operand slots in TMEM, raw X ring + centroid stages in smem.
+struct TsPlan {
+  int kb = 0, bn = 0, a_slots = 0, raw_slots = 0, b_stages = 0, b_resident = 0, n_acc = 0, pair = 0;
+  size_t smem = 0;
+};
+
+TsPlan plan_ts(const Handle& h, int d, int k)
+{
+  TsPlan t;
+  t.kb = static_cast<int>(ceil_div(d, KBLOCK));
+  int bn = 128;
+  if (k <= 32) bn = 32;
+  else if (k <= 64) bn = 64;
+  const int k_tiles = static_cast<int>(ceil_div(k, bn));
+  {
+    const char* e = std::getenv("CUML_B200_2CTA");
+    const bool want = e ? (std::atoi(e) != 0) : true;
+    t.pair = (want && bn == 128 && (h.sm_count % 2) == 0) ? 1 : 0;
+  }
+  // tensor memory: accumulators first, then 64-column operand slots (need all K-blocks of a row tile when
+  // there are several centroid tiles)
+  const int a_min = (k_tiles > 1) ? t.kb : 1;
+  int n_acc       = std::min(MAX_ACC, std::max(2, 256 / bn));
+  while (n_acc > 2 && (512 - n_acc * bn) / 64 < std::max(a_min, 2)) --n_acc;
+  int a_slots = std::min(MAX_A_SLOTS, (512 - n_acc * bn) / 64);
+  if (a_slots < a_min) return t;   // bn stays 0: not available
+  const size_t stage = static_cast<size_t>(t.pair ? bn / 2 : bn) * 128 * 2;
+  auto bytes = [&](int raw_, int bs_) {
+    return static_cast<size_t>(raw_) * KBLOCK_BYTES + static_cast<size_t>(bs_) * stage + 2 * bn * sizeof(float) +
+           2 * TILE_M * 4 + sizeof(Barriers) + 1024;
+  };
+  int b_stages = 3, resident = 0;
+  if (k_tiles * t.kb <= MAX_STAGES && bytes(4, k_tiles * t.kb) <= h.smem_optin) {
+    b_stages = k_tiles * t.kb;
+    resident = 1;
+  }
+  if (bytes(2, b_stages) > h.smem_optin) return t;
+  if (!resident) b_stages = MAX_STAGES;   // deep centroid ring: stages are small (<= 32 KB)
+  while (b_stages > 2 && bytes(4, b_stages) > h.smem_optin) --b_stages;
+  int raw = 2;
+  while (raw < MAX_RAW && bytes(raw + 1, b_stages) <= h.smem_optin) ++raw;
+  t.bn = bn; t.a_slots = a_slots; t.raw_slots = raw; t.b_stages = b_stages; t.b_resident = resident; t.n_acc = n_acc;
+  t.smem = bytes(raw, b_stages);
+  return t;
+}
+
+bool use_ts(const Handle& h, int d, int k)
+{
+  const char* e = std::getenv("CUML_B200_TS");
+  if (e && std::atoi(e) == 0) return false;
+  return plan_ts(h, d, k).bn > 0;
+}
+
 }  // namespace
 
 bool tc_supported(int64_t d, int k)
@@ -692,8 +994,14 @@ bool tc_supported(int64_t d, int k)
 
 void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out)
 {
-  const bool pair = use_2cta(h, d, k);
+  const bool ts   = use_ts(h, d, k);
+  const bool pair = !ts && use_2cta(h, d, k);
   TilePlan t = pair ? plan_tiles_2cta(d, k, h.smem_optin) : plan_tiles(d, k, h.smem_optin);
+  if (ts) {
+    const TsPlan tp = plan_ts(h, d, k);
+    t.bn = tp.bn;
+    t.kb = tp.kb;
+  }
   CB2_EXPECTS(t.bn > 0, "tcgen05 k-means tile plan does not fit shared memory");
   const int d_pad = t.kb * KBLOCK;
   const int k_pad = static_cast<int>(ceil_div(k, t.bn)) * t.bn;
@@ -716,6 +1024,50 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   if (n == 0) return;
   CB2_EXPECTS(h.cc_major == 10, "the tcgen05 k-means engine needs an sm_100-class GPU (B200)");
   CB2_EXPECTS(reinterpret_cast<uintptr_t>(X) % 16 == 0, "X must be 16-byte aligned for TMA");
+  if (use_ts(h, d, k)) {
+    const TsPlan tp = plan_ts(h, d, k);
+    CB2_EXPECTS(tp.bn == cen.block_n, "centroid operand buffers were prepared for a different tile plan");
+    FusedParams p{};
+    p.n = n; p.m_tiles = ceil_div(n, TILE_M); p.k_tiles = cen.k_pad / tp.bn; p.d = d; p.kb = tp.kb; p.bn = tp.bn;
+    p.a_slots = tp.a_slots; p.raw_slots = tp.raw_slots; p.b_stages = tp.b_stages; p.b_resident = tp.b_resident;
+    p.n_acc = tp.n_acc; p.a_col0 = tp.n_acc * tp.bn; p.tmem_cols = 512;
+    p.cnh = cen.cnh.get(); p.labels = labels; p.dbg_dots = dbg_dots;
+    CUtensorMap tm_x = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
+                                   static_cast<uint64_t>(d) * sizeof(float), KBLOCK, TILE_M,
+                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    const uint32_t rows_box = tp.pair ? tp.bn / 2 : tp.bn;
+    CUtensorMap tm_hi = make_map_2d(cen.hi.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * sizeof(float),
+                                    KBLOCK, rows_box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    CUtensorMap tm_lo = make_map_2d(cen.lo.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * sizeof(float),
+                                    KBLOCK, rows_box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    static bool ts_attr = false;
+    if (!ts_attr) {
+      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(h.smem_optin)));
+      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(h.smem_optin)));
+      ts_attr = true;
+    }
+    EventPair ev{};
+    if (h.timing) ev = h.begin_event();
+    if (tp.pair) {
+      const int64_t pair_tiles = (p.m_tiles + 1) / 2;
+      const unsigned grid = 2u * static_cast<unsigned>(std::min<int64_t>(pair_tiles, h.sm_count / 2));
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = tp.smem; cfg.stream = h.stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      CB2_CUDA(cudaLaunchKernelEx(&cfg, fused_l2_argmin_ts_kernel<true>, tm_x, tm_hi, tm_lo, p));
+    } else {
+      const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
+      fused_l2_argmin_ts_kernel<false><<<grid, NUM_THREADS, tp.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+    }
+    CB2_CHECK_LAUNCH();
+    if (h.timing) h.end_event(ev, true);
+    return;
+  }
   const bool pair = use_2cta(h, d, k);
   TilePlan t = pair ? plan_tiles_2cta(d, k, h.smem_optin) : plan_tiles(d, k, h.smem_optin);
   CB2_EXPECTS(t.bn == cen.block_n, "centroid operand buffers were prepared for a different tile plan");
