@@ -38,7 +38,8 @@ namespace {
 constexpr int TILE_M       = 128;
 constexpr int KBLOCK       = 32;              // fp32 elements per 128-byte swizzle row
 constexpr int KBLOCK_BYTES = TILE_M * 128;    // one K-block of an A tile: 16 KB
-constexpr int NUM_THREADS  = 512;             // 16 warps: producers, MMA issuer, 4 converter, 8 epilogue
+constexpr int NUM_THREADS  = 768;             // 24 warps: producers, MMA issuer, 4 converter, 16 epilogue
+constexpr int EPI_THREADS  = 512;             // 16 epilogue warps: 4 TMEM lane quarters x 4 column parts
 constexpr int MAX_STAGES   = 4;
 constexpr int MAX_A_SLOTS  = 8;
 constexpr int MAX_ACC      = 8;
@@ -74,27 +75,28 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
-// ===================== epilogue role (shared by the single-CTA and the CTA-pair kernels) ============
-// 8 warps: warp e handles TMEM lanes [32*(e&3), +32) (its rows) and the column half (e>>2) of every
-// accumulator tile; thread = row.  Per row: four independent running (min, argmin) chains, merged with
-// the first-minimum rule; the two column halves are merged through shared memory.
+// ===================== epilogue role (shared by all kernel variants) ===================================
+// 16 warps: warp e handles TMEM lanes [32*(e&3), +32) (its rows) and column part (e>>2) of every
+// accumulator tile (BN/4 columns, at least one 32-column chunk); thread = row.  Per row: four independent
+// running (min, argmin) chains, merged with the first-minimum rule; the column parts are merged through
+// shared memory.  The argmin is instruction-issue bound (4 instructions per distance), hence many warps.
 template <bool PAIR>
 __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* bars, float* cn_s, float* mrg_v,
                                               int* mrg_i, uint32_t tmem_base, int64_t first_row, int64_t row_stride,
                                               int64_t n_tiles_cta)
 {
-  const int et      = threadIdx.x - 256;      // 0..255
-  const int ew      = et >> 5;                // epilogue warp 0..7
+  const int et      = threadIdx.x - 256;      // 0..511
+  const int ew      = et >> 5;                // epilogue warp 0..15
   const int lane    = et & 31;
   const int quarter = ew & 3;                 // TMEM lane quarter this warp may access
-  const int half    = ew >> 2;                // column half of the accumulator tile
+  const int part    = ew >> 2;                // column part of the accumulator tile
   const int rit     = quarter * 32 + lane;    // row within the 128-row tile
   const float inf   = __int_as_float(0x7f800000);
-  const int cbeg    = (p.bn >= 64) ? half * (p.bn / 2) : 0;
-  const int cend    = (p.bn >= 64) ? cbeg + p.bn / 2 : (half == 0 ? p.bn : 0);
+  const int nparts  = min(4, p.bn / 32);      // parts that own at least one 32-column chunk
+  const int pcols   = p.bn / nparts;
+  const int cbeg    = part * pcols;
+  const int cend    = (part < nparts) ? cbeg + pcols : cbeg;
   uint32_t acc_cnt  = 0;
-  long long ewait = 0;
-  const long long estart = clock64();
   // 1/2||c||^2 of the next centroid tile is fetched one tile ahead (registers), so its global-load
   // latency never sits on the epilogue's critical path
   float pre = 0.f;
@@ -102,7 +104,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
   fetch_cn(0);
   if (p.k_tiles == 1) {  // single centroid tile: stage the half norms once
     if (et < p.bn) cn_s[et] = pre;
-    ptx::named_bar_sync(1, 256);
+    ptx::named_bar_sync(1, EPI_THREADS);
   }
   for (int64_t t = 0; t < n_tiles_cta; ++t) {
     float b0 = inf, b1 = inf, b2 = inf, b3 = inf;
@@ -113,13 +115,9 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
       if (p.k_tiles > 1) {
         if (et < p.bn) cn[et] = pre;
         fetch_cn(nt + 1 == p.k_tiles ? 0 : nt + 1);
-        ptx::named_bar_sync(1, 256);
+        ptx::named_bar_sync(1, EPI_THREADS);
       }
-      {
-        const long long t__ = clock64();
-        ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[acc]), pacc);
-        ewait += clock64() - t__;
-      }
+      ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[acc]), pacc);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.bn;
       const int jbase      = nt * p.bn;
@@ -162,22 +160,24 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
     if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
     if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
     if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
-    // merge the two column halves through shared memory
-    if (half == 1) {
-      mrg_v[rit] = b0;
-      mrg_i[rit] = i0;
+    // merge the column parts through shared memory
+    if (part > 0) {
+      mrg_v[(part - 1) * TILE_M + rit] = b0;
+      mrg_i[(part - 1) * TILE_M + rit] = i0;
     }
-    ptx::named_bar_sync(2, 256);
-    if (half == 0) {
-      const float ov = mrg_v[rit];
-      const int oi   = mrg_i[rit];
-      if (ov < b0 || (ov == b0 && oi < i0)) { b0 = ov; i0 = oi; }
+    ptx::named_bar_sync(2, EPI_THREADS);
+    if (part == 0) {
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float ov = mrg_v[q * TILE_M + rit];
+        const int oi   = mrg_i[q * TILE_M + rit];
+        if (ov < b0 || (ov == b0 && oi < i0)) { b0 = ov; i0 = oi; }
+      }
       const int64_t row = first_row + t * row_stride + rit;
       if (row < p.n) p.labels[row] = i0;
     }
-    ptx::named_bar_sync(3, 256);  // mrg_* may be overwritten by the next tile
+    ptx::named_bar_sync(3, EPI_THREADS);  // mrg_* may be overwritten by the next tile
   }
-  if (p.dbg_clk && blockIdx.x == 0 && et == 0) { p.dbg_clk[8] = ewait; p.dbg_clk[9] = clock64() - estart; }
 }
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -197,8 +197,8 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
   const uint32_t cn_off  = p.a_slots * A_SLOT_BYTES + p.b_stages * b_stage_bytes;
   float* cn_s            = reinterpret_cast<float*>(gbase + cn_off);               // [2][bn]
   float* mrg_v           = cn_s + 2 * p.bn;                                         // [128] epilogue half merge
-  int* mrg_i             = reinterpret_cast<int*>(mrg_v + TILE_M);                  // [128]
-  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 2u * TILE_M * 4u);
+  int* mrg_i             = reinterpret_cast<int*>(mrg_v + 3 * TILE_M);              // [3][128]
+  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 6u * TILE_M * 4u);
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -211,7 +211,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     }
     for (int s = 0; s < MAX_ACC; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 8);    // one arrive per epilogue warp
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 16);   // one arrive per epilogue warp
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);
@@ -413,8 +413,8 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   const uint32_t cn_off  = p.a_slots * A_SLOT_BYTES + p.b_stages * b_stage_bytes;
   float* cn_s            = reinterpret_cast<float*>(gbase + cn_off);    // [2][bn]
   float* mrg_v           = cn_s + 2 * p.bn;                              // [128] epilogue half merge
-  int* mrg_i             = reinterpret_cast<int*>(mrg_v + TILE_M);       // [128]
-  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 2u * TILE_M * 4u);
+  int* mrg_i             = reinterpret_cast<int*>(mrg_v + 3 * TILE_M);   // [3][128]
+  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 6u * TILE_M * 4u);
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -427,7 +427,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     }
     for (int s = 0; s < MAX_ACC; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 16);  // 8 epilogue warps x 2 CTAs (leader's copy)
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 32);  // 16 epilogue warps x 2 CTAs (leader's copy)
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);      // leader's copy: expect_tx covers both CTAs
@@ -618,13 +618,13 @@ fused_l2_argmin_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
   const uint32_t cn_off  = p.raw_slots * KBLOCK_BYTES + p.b_stages * b_stage_bytes;
   float* cn_s            = reinterpret_cast<float*>(gbase + cn_off);     // [2][bn]
   float* mrg_v           = cn_s + 2 * p.bn;
-  int* mrg_i             = reinterpret_cast<int*>(mrg_v + TILE_M);
-  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 2u * TILE_M * 4u);
+  int* mrg_i             = reinterpret_cast<int*>(mrg_v + 3 * TILE_M);
+  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 6u * TILE_M * 4u);
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   const uint32_t conv_arrivals = PAIR ? 8u : 4u;    // converter warps that feed one MMA
-  const uint32_t epi_arrivals  = PAIR ? 16u : 8u;
+  const uint32_t epi_arrivals  = PAIR ? 32u : 16u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_RAW; ++s) {
@@ -866,7 +866,7 @@ TilePlan plan_tiles(int d, int k, size_t smem_limit)
   else if (k <= 128) bn0 = 128;
   auto bytes = [&](int bn_, int as_, int bs_) {
     return static_cast<size_t>(as_) * A_SLOT_BYTES + static_cast<size_t>(bs_) * 2 * bn_ * 128 +
-           2 * bn_ * sizeof(float) + 2 * TILE_M * 4 + sizeof(Barriers) + 1024;
+           2 * bn_ * sizeof(float) + 6 * TILE_M * 4 + sizeof(Barriers) + 1024;
   };
   t.bn = 0;
   for (int bn = bn0; bn >= 32 && t.bn == 0; bn /= 2) {
@@ -901,7 +901,7 @@ TilePlan plan_tiles_2cta(int d, int k, size_t smem_limit)
   const int bn = 256;
   auto bytes = [&](int as_, int bs_) {
     return static_cast<size_t>(as_) * A_SLOT_BYTES + static_cast<size_t>(bs_) * bn * 128 + 2 * bn * sizeof(float) +
-           2 * TILE_M * 4 + sizeof(Barriers) + 1024;
+           6 * TILE_M * 4 + sizeof(Barriers) + 1024;
   };
   const int k_tiles = static_cast<int>(ceil_div(k, bn));
   const int a_min   = (k_tiles > 1) ? t.kb : std::min(t.kb, 2);
@@ -961,7 +961,7 @@ TsPlan plan_ts(const Handle& h, int d, int k)
   const size_t stage = static_cast<size_t>(t.pair ? bn / 2 : bn) * 128 * 2;
   auto bytes = [&](int raw_, int bs_) {
     return static_cast<size_t>(raw_) * KBLOCK_BYTES + static_cast<size_t>(bs_) * stage + 2 * bn * sizeof(float) +
-           2 * TILE_M * 4 + sizeof(Barriers) + 1024;
+           6 * TILE_M * 4 + sizeof(Barriers) + 1024;
   };
   int b_stages = 3, resident = 0;
   if (k_tiles * t.kb <= MAX_STAGES && bytes(4, k_tiles * t.kb) <= h.smem_optin) {

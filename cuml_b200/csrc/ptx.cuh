@@ -214,7 +214,9 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank)
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr)
 {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  // default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive: what crosses the CTA pair
+  // here is tensor-memory / async-proxy state ordered by the tcgen05 fences, so no GPU-scope membar
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc_2cta(uint32_t dst_smem, uint32_t cols)
