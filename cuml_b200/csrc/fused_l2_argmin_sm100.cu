@@ -980,8 +980,11 @@ TsPlan plan_ts(const Handle& h, int d, int k)
 
 bool use_ts(const Handle& h, int d, int k)
 {
+  // Experimental: the MMA itself is 33 % faster with A in tensor memory (tools/micro/mma_rate.cu), but the
+  // whole kernel is then bound by the argmin epilogue (BN <= 128 doubles its per-tile hand-offs) and
+  // measures slower than the shared-memory CTA-pair kernel (profiles/).  Opt-in with CUML_B200_TS=1.
   const char* e = std::getenv("CUML_B200_TS");
-  if (e && std::atoi(e) == 0) return false;
+  if (!e || std::atoi(e) == 0) return false;
   return plan_ts(h, d, k).bn > 0;
 }
 

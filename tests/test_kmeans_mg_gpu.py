@@ -28,7 +28,9 @@ def _worker(rank, world, port, q, init_kind):
     lo, hi = shard_bounds(n, rank, world)
     h = comms_from_torch_distributed()
     init = blobs.parity_init(centres) if init_kind == "array" else init_kind
-    km = KMeansMG(handle=h, n_clusters=k, init=init, max_iter=10, tol=0.0, random_state=5, n_init=1)
+    km = KMeansMG(handle=h, n_clusters=k, init=init, max_iter=10 if init_kind == "array" else 50,
+                  tol=0.0 if init_kind == "array" else 1e-6, random_state=5,
+                  n_init=1 if init_kind == "array" else 5)
     # two ragged local partitions per rank
     mid = lo + (hi - lo) // 3
     km.fit([X[lo:mid], X[mid:hi]])
