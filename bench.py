@@ -33,6 +33,9 @@ WORKLOADS = {
     "C3": (100_000_000, 64, 256, "KMeans fit n=100M d=64 k=256 fp32 row-sharded"),
     "C5": (200_000_000, 16, 64, "KMeans fit n=200M d=16 k=64 fp32 row-sharded"),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant (fused) kernel at the full
+# workload, from the committed `ncu --set full` captures (profiles/r01_ncu_full_c3.txt)
+TRAFFIC_NCU = {"C3": 25.601282e9 + 0.346264e9}
 METRIC = "kmeans_lloyd_iters_per_sec"
 UNIT = "Lloyd iter/s"
 
@@ -274,10 +277,31 @@ def run_ours(args):
         fused_ms = f_ms.value / max(1, f_n.value)
         update_ms = u_ms.value / max(1, u_n.value)
         flop = 2.0 * n_local * k * d
-        achieved = flop / (fused_ms * 1e-3) / 1e12 if fused_ms > 0 else None
+        fused_bytes = 4.0 * n_local * d + 4.0 * n_local            # X read once + labels written
+        tf_achieved = flop / (fused_ms * 1e-3) / 1e12 if fused_ms > 0 else None
+        gb_achieved = fused_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else None
         # fp32-equivalent tensor roofline: TF32 runs at half the bf16 rate and 3xTF32 issues 3 MMAs per
         # product => peak(algorithmic 2nkd) = bf16_sustained / 2 / 3  
-        peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0
+        tf_peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0
+        # which roofline binds the fused kernel: time at the tensor peak vs time at the HBM peak
+        tensor_bound = (flop / (tf_peak * 1e12)) >= (fused_bytes / (peaks["hbm_gbs"] * 1e9))
+        if tensor_bound:
+            roof = {"bound": "tensor", "achieved": tf_achieved, "peak": tf_peak, "unit": "TFLOP/s",
+                    "frac": (tf_achieved / tf_peak) if tf_achieved else None}
+        else:
+            roof = {"bound": "hbm", "achieved": gb_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": (gb_achieved / peaks["hbm_gbs"]) if gb_achieved else None}
+        roof.update({
+            "traffic": TRAFFIC_NCU.get(args.workload) if world == 1 and not args.n else None,
+            "kernel": "fused_l2_argmin (tcgen05 3xTF32 distance+argmin)", "kernel_ms": fused_ms,
+            "algorithmic_flops_per_launch": flop, "algorithmic_bytes_per_launch": fused_bytes,
+            "algorithmic_tflops": tf_achieved, "issued_tf32_tflops": (3 * tf_achieved) if tf_achieved else None,
+            "hbm_gbs_fused": gb_achieved,
+            "peak_note": f"{peaks['source']}: tensor peak = bf16_tflops_sustained/2 (tf32 rate) /3 (3xTF32); "
+                         f"hbm peak = hbm_gbs (copy)",
+            "update_kernel_ms": update_ms,
+            "update_kernel_hbm_gbs": 4.0 * n_local * (d + 1) / (update_ms * 1e-3) / 1e9 if update_ms > 0 else None,
+            "hbm_peak_gbs": peaks["hbm_gbs"], "tensor_peak_tflops": tf_peak})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -290,15 +314,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "clocks": clocks,
             "e2e": e2e,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "kernel": "fused_l2_argmin_kernel", "kernel_ms": fused_ms,
-                         "algorithmic_flops_per_launch": flop, "issued_tf32_tflops": (3 * achieved) if achieved else None,
-                         "peak_note": f"{peaks['source']} bf16_tflops_sustained/2 (tf32) /3 (3xTF32)",
-                         "hbm_gbs_fused": 4.0 * n_local * d / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else None,
-                         "update_kernel_ms": update_ms,
-                         "update_kernel_hbm_gbs": 4.0 * n_local * (d + 1) / (update_ms * 1e-3) / 1e9 if update_ms > 0 else None,
-                         "hbm_peak_gbs": peaks["hbm_gbs"]},
+            "roofline": roof,
         }
         if world == 1 and not args.no_cpu:
             rate, cores, sample = cpu_reference_rate(n, d, k)
