@@ -46,6 +46,27 @@ constexpr int MAX_ACC      = 8;
 constexpr int MAX_RAW      = 12;  // raw X K-block slots (16 KB each) of the A-in-TMEM variant   // TMEM accumulator stages (512 columns / BN, at most 8)
 constexpr int A_SLOT_BYTES = 2 * KBLOCK_BYTES;  // hi then lo
 
+// (slot, phase) of an mbarrier ring, advanced without integer division (a runtime '%' or '/' costs ~100
+// dependent cycles on the GPU, and every role used to pay several per tile)
+struct Ring {
+  uint32_t slot = 0, phase = 0;
+  __device__ __forceinline__ void advance(uint32_t n)
+  {
+    if (++slot == n) {
+      slot = 0;
+      phase ^= 1u;
+    }
+  }
+  __device__ __forceinline__ void advance_by(uint32_t steps, uint32_t n)
+  {
+    slot += steps;
+    while (slot >= n) {
+      slot -= n;
+      phase ^= 1u;
+    }
+  }
+};
+
 struct FusedParams {
   int64_t n;
   int64_t m_tiles;
@@ -97,6 +118,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
   const int cbeg    = part * pcols;
   const int cend    = (part < nparts) ? cbeg + pcols : cbeg;
   uint32_t acc_cnt  = 0;
+  Ring racc;
   // 1/2||c||^2 of the next centroid tile is fetched one tile ahead (registers), so its global-load
   // latency never sits on the epilogue's critical path
   float pre = 0.f;
@@ -110,7 +132,8 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
     float b0 = inf, b1 = inf, b2 = inf, b3 = inf;
     int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
     for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
-      const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
+      const uint32_t acc = racc.slot, pacc = racc.phase;
+      racc.advance(p.n_acc);
       float* cn = cn_s + ((p.k_tiles == 1) ? 0 : (acc_cnt & 1u) * p.bn);
       if (p.k_tiles > 1) {
         if (et < p.bn) cn[et] = pre;
@@ -237,11 +260,13 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     // ===================== A producer: raw X K-blocks into the slot ring =====================
     {
       uint32_t a_cnt = 0;
+      Ring ra;
       long long wcyc = 0;
       const long long tstart = clock64();
       for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
         for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
-          const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
+          const uint32_t sa = ra.slot, pa = ra.phase;
+          ra.advance(p.a_slots);
           CB2_TIMED_WAIT(ptx::smem_u32(&bars->a_empty[sa]), pa ^ 1u, wcyc);
           if (ptx::elect_one()) {
             const uint32_t full = ptx::smem_u32(&bars->a_raw_full[sa]);
@@ -258,11 +283,13 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     // ===================== B producer: centroid hi/lo K-blocks =====================
     {
       uint32_t b_cnt = 0;
+      Ring rb;
       for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
         if (p.b_resident && tile != blockIdx.x) break;  // resident centroids: loaded once per CTA
         for (int nt = 0; nt < p.k_tiles; ++nt) {
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
-            const uint32_t sb = b_cnt % p.b_stages, pb = (b_cnt / p.b_stages) & 1u;
+            const uint32_t sb = rb.slot, pb = rb.phase;
+            rb.advance(p.b_stages);
             ptx::mbar_wait(ptx::smem_u32(&bars->b_empty[sb]), pb ^ 1u);
             if (ptx::elect_one()) {
               const uint32_t full = ptx::smem_u32(&bars->b_full[sb]);
@@ -280,11 +307,13 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     // ===================== converter: raw -> (hi in place, lo) =====================
     const int ct = threadIdx.x - 128;  // 0..127
     uint32_t a_cnt = 0;
+      Ring ra;
     long long wcyc = 0;
     const long long tstart = clock64();
     for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
       for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
-        const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
+        const uint32_t sa = ra.slot, pa = ra.phase;
+          ra.advance(p.a_slots);
         CB2_TIMED_WAIT(ptx::smem_u32(&bars->a_raw_full[sa]), pa, wcyc);
         uint4* hi = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES);
@@ -317,21 +346,25 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     // each tcgen05.mma is a single predicated instruction); one elected lane issues.
     {
       const uint32_t idesc = ptx::umma_idesc_tf32(TILE_M, p.bn);
-      uint32_t a_cnt0 = 0, b_cnt = 0, acc_cnt = 0;
-      long long wacc = 0, wa = 0, wb = 0;
+      uint32_t b_cnt = 0, acc_cnt = 0;
+      Ring ra_tile, rb, racc;
+      long long wacc = 0, wa = 0, wb = 0, tissue = 0, tcommit = 0, tc0 = 0;
       const long long tstart = clock64();
-      for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, a_cnt0 += p.kb) {
+      for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ra_tile.advance_by(p.kb, p.a_slots)) {
         for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
-          const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
+          const uint32_t acc = racc.slot, pacc = racc.phase;
+          racc.advance(p.n_acc);
+          Ring ra = ra_tile;
           CB2_TIMED_WAIT(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u, wacc);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * p.bn;
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
-            const uint32_t a_cnt = a_cnt0 + kbi;
-            const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
+            const uint32_t sa = ra.slot, pa = ra.phase;
+            ra.advance(p.a_slots);
             if (nt == 0) CB2_TIMED_WAIT(ptx::smem_u32(&bars->a_ready[sa]), pa, wa);  // first use of this X K-block
-            uint32_t sb = b_cnt % p.b_stages;
-            const uint32_t pb = (b_cnt / p.b_stages) & 1u;
+            uint32_t sb = rb.slot;
+            const uint32_t pb = rb.phase;
+            rb.advance(p.b_stages);
             if (p.b_resident) {
               sb = nt * p.kb + kbi;
               if (tile == static_cast<int64_t>(blockIdx.x)) ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), 0u);
@@ -344,6 +377,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             const uint64_t db_hi = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes);
             const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
             const int nks = min(4, (p.d - kbi * KBLOCK + 7) / 8);  // K=8 steps that hold real columns
+            const long long ti0 = clock64();
             if (ptx::elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
@@ -354,19 +388,27 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
                 ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
                 ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
               }
+            }
+            __syncwarp();
+            const long long ti1 = clock64();
+            tissue += ti1 - ti0;
+            if (ptx::elect_one()) {
               if (!p.b_resident) ptx::mma_commit(ptx::smem_u32(&bars->b_empty[sb]));  // frees the B stage
               // last centroid tile: this X K-block is not needed again -> release its slot early so
               // the next row tile's load + hi/lo split overlaps the remaining K-blocks
               if (nt == p.k_tiles - 1) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[sa]));
             }
             __syncwarp();
+            tc0 = ti1;
           }
           if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->acc_full[acc]));  // accumulator ready
           __syncwarp();
+          tcommit += clock64() - tc0;
         }
       }
       if (p.dbg_clk && blockIdx.x == 0 && lane == 0) {
         p.dbg_clk[4] = wacc; p.dbg_clk[5] = wa; p.dbg_clk[6] = wb; p.dbg_clk[7] = clock64() - tstart;
+        p.dbg_clk[10] = tissue; p.dbg_clk[11] = tcommit;
       }
     }
   } else if (warp >= 8) {
@@ -455,10 +497,12 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     // ===================== X producer (own 128 rows) =====================
     {
       uint32_t a_cnt = 0;
+      Ring ra;
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
         const int32_t row0 = static_cast<int32_t>(pt * 2 * TILE_M + cta_rank * TILE_M);
         for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
-          const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
+          const uint32_t sa = ra.slot, pa = ra.phase;
+          ra.advance(p.a_slots);
           ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[sa]), pa ^ 1u);
           if (ptx::elect_one()) {
             const uint32_t full = ptx::smem_u32(&bars->a_raw_full[sa]);
@@ -473,11 +517,13 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     // ===================== centroid producer (own half of every block) =====================
     {
       uint32_t b_cnt = 0;
+      Ring rb;
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
         if (p.b_resident && pt != pair) break;
         for (int nt = 0; nt < p.k_tiles; ++nt) {
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
-            const uint32_t sb = b_cnt % p.b_stages, pb = (b_cnt / p.b_stages) & 1u;
+            const uint32_t sb = rb.slot, pb = rb.phase;
+            rb.advance(p.b_stages);
             ptx::mbar_wait(ptx::smem_u32(&bars->b_empty[sb]), pb ^ 1u);
             if (ptx::elect_one()) {
               const uint32_t full_local  = ptx::smem_u32(&bars->b_full[sb]);
@@ -497,9 +543,11 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     // ===================== converter =====================
     const int ct = threadIdx.x - 128;
     uint32_t a_cnt = 0;
+      Ring ra;
     for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
       for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
-        const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
+        const uint32_t sa = ra.slot, pa = ra.phase;
+          ra.advance(p.a_slots);
         ptx::mbar_wait(ptx::smem_u32(&bars->a_raw_full[sa]), pa);
         uint4* hi = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES);
@@ -527,19 +575,23 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     // ===================== MMA issuer (pair leader only; warp-uniform loop, one elected lane issues) ====
     if (leader) {
       const uint32_t idesc = ptx::umma_idesc_tf32(2 * TILE_M, p.bn);
-      uint32_t a_cnt0 = 0, b_cnt = 0, acc_cnt = 0;
-      for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs, a_cnt0 += p.kb) {
+      uint32_t b_cnt = 0, acc_cnt = 0;
+      Ring ra_tile, rb, racc;
+      for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs, ra_tile.advance_by(p.kb, p.a_slots)) {
         for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
-          const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
+          const uint32_t acc = racc.slot, pacc = racc.phase;
+          racc.advance(p.n_acc);
+          Ring ra = ra_tile;
           ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * p.bn;
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
-            const uint32_t a_cnt = a_cnt0 + kbi;
-            const uint32_t sa = a_cnt % p.a_slots, pa = (a_cnt / p.a_slots) & 1u;
+            const uint32_t sa = ra.slot, pa = ra.phase;
+            ra.advance(p.a_slots);
             if (nt == 0) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[sa]), pa);
-            uint32_t sb = b_cnt % p.b_stages;
-            const uint32_t pb = (b_cnt / p.b_stages) & 1u;
+            uint32_t sb = rb.slot;
+            const uint32_t pb = rb.phase;
+            rb.advance(p.b_stages);
             if (p.b_resident) {
               sb = nt * p.kb + kbi;
               if (pt == pair) ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), 0u);
@@ -668,10 +720,12 @@ fused_l2_argmin_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
   if (warp == 0) {
     // ===================== raw X producer (own 128 rows) =====================
     uint32_t cnt = 0;
+    Ring rr;
     for (int64_t t = unit; t < tiles; t += n_units) {
       const int32_t row0 = static_cast<int32_t>(t * rows_unit + cta_rank * TILE_M);
       for (int kbi = 0; kbi < p.kb; ++kbi, ++cnt) {
-        const uint32_t rs = cnt % p.raw_slots, rp = (cnt / p.raw_slots) & 1u;
+        const uint32_t rs = rr.slot, rp = rr.phase;
+        rr.advance(p.raw_slots);
         ptx::mbar_wait(ptx::smem_u32(&bars->raw_empty[rs]), rp ^ 1u);
         if (ptx::elect_one()) {
           const uint32_t full = ptx::smem_u32(&bars->raw_full[rs]);
@@ -684,11 +738,13 @@ fused_l2_argmin_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
   } else if (warp == 2) {
     // ===================== centroid producer =====================
     uint32_t b_cnt = 0;
+    Ring rb;
     for (int64_t t = unit; t < tiles; t += n_units) {
       if (p.b_resident && t != unit) break;
       for (int nt = 0; nt < p.k_tiles; ++nt) {
         for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
-          const uint32_t sb = b_cnt % p.b_stages, pb = (b_cnt / p.b_stages) & 1u;
+          const uint32_t sb = rb.slot, pb = rb.phase;
+            rb.advance(p.b_stages);
           ptx::mbar_wait(ptx::smem_u32(&bars->b_empty[sb]), pb ^ 1u);
           if (ptx::elect_one()) {
             const uint32_t full_local = ptx::smem_u32(&bars->b_full[sb]);
@@ -715,10 +771,13 @@ fused_l2_argmin_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
     const int row     = quarter * 32 + lane;                       // row of the tile == TMEM lane
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t cnt = 0;
+    Ring rr, ra;
     for (int64_t t = unit; t < tiles; t += n_units) {
       for (int kbi = 0; kbi < p.kb; ++kbi, ++cnt) {
-        const uint32_t rs = cnt % p.raw_slots, rp = (cnt / p.raw_slots) & 1u;
-        const uint32_t as = cnt % p.a_slots, ap = (cnt / p.a_slots) & 1u;
+        const uint32_t rs = rr.slot, rp = rr.phase;
+        rr.advance(p.raw_slots);
+        const uint32_t as = ra.slot, ap = ra.phase;
+        ra.advance(p.a_slots);
         ptx::mbar_wait(ptx::smem_u32(&bars->raw_full[rs]), rp);
         const uint4* src = reinterpret_cast<const uint4*>(gbase + rs * KBLOCK_BYTES + row * 128);
         uint32_t hi[32], lo[32];
@@ -753,19 +812,23 @@ fused_l2_argmin_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
     // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
     if (leader) {
       const uint32_t idesc = ptx::umma_idesc_tf32(PAIR ? 2 * TILE_M : TILE_M, p.bn);
-      uint32_t a_cnt0 = 0, b_cnt = 0, acc_cnt = 0;
-      for (int64_t t = unit; t < tiles; t += n_units, a_cnt0 += p.kb) {
+      uint32_t b_cnt = 0, acc_cnt = 0;
+      Ring ra_tile, rb, racc;
+      for (int64_t t = unit; t < tiles; t += n_units, ra_tile.advance_by(p.kb, p.a_slots)) {
         for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
-          const uint32_t acc = acc_cnt % p.n_acc, pacc = (acc_cnt / p.n_acc) & 1u;
+          const uint32_t acc = racc.slot, pacc = racc.phase;
+          racc.advance(p.n_acc);
+          Ring ra = ra_tile;
           ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
           ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * p.bn;
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
-            const uint32_t a_cnt = a_cnt0 + kbi;
-            const uint32_t as = a_cnt % p.a_slots, ap = (a_cnt / p.a_slots) & 1u;
+            const uint32_t as = ra.slot, ap = ra.phase;
+            ra.advance(p.a_slots);
             if (nt == 0) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[as]), ap);
-            uint32_t sb = b_cnt % p.b_stages;
-            const uint32_t pb = (b_cnt / p.b_stages) & 1u;
+            uint32_t sb = rb.slot;
+            const uint32_t pb = rb.phase;
+            rb.advance(p.b_stages);
             if (p.b_resident) {
               sb = nt * p.kb + kbi;
               if (t == unit) ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), 0u);
@@ -1140,8 +1203,8 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     CB2_CUDA(cudaMemcpyAsync(hc, clk.get(), sizeof(hc), cudaMemcpyDeviceToHost, h.stream));
     CB2_CUDA(cudaStreamSynchronize(h.stream));
     std::printf("[cuml_b200 clk] tiles/CTA %lld | producer wait %lld / %lld | converter wait %lld / %lld | mma wait acc %lld a %lld b %lld / %lld | "
-                "epilogue wait %lld / %lld (cycles, CTA 0)\n",
-                static_cast<long long>((p.m_tiles + grid_dbg - 1) / grid_dbg), hc[0], hc[1], hc[2], hc[3], hc[4], hc[5], hc[6], hc[7], hc[8], hc[9]);
+                "epilogue wait %lld / %lld | mma issue %lld commit %lld (cycles, CTA 0)\n",
+                static_cast<long long>((p.m_tiles + grid_dbg - 1) / grid_dbg), hc[0], hc[1], hc[2], hc[3], hc[4], hc[5], hc[6], hc[7], hc[8], hc[9], hc[10], hc[11]);
   }
 }
 
