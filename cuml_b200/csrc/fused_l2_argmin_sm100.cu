@@ -30,9 +30,13 @@ namespace {
 // timed mbarrier wait: accumulates the cycles spent waiting (role-level profiling, CTA 0 only)
 #define CB2_TIMED_WAIT(bar, parity, acc)            \
   do {                                              \
-    const long long t__ = clock64();                \
-    ptx::mbar_wait((bar), (parity));                \
-    (acc) += clock64() - t__;                       \
+    if (p.dbg_clk) {                                \
+      const long long t__ = clock64();              \
+      ptx::mbar_wait((bar), (parity));              \
+      (acc) += clock64() - t__;                     \
+    } else {                                        \
+      ptx::mbar_wait((bar), (parity));              \
+    }                                               \
   } while (0)
 
 constexpr int TILE_M       = 128;
@@ -78,6 +82,8 @@ struct FusedParams {
   int b_stages;   // 2..4
   int b_resident; // all k_tiles*kb centroid blocks fit the B stages: load once, never release
   int n_acc;      // TMEM accumulator stages: min(MAX_ACC, 512 / bn)
+  int pack;       // 1, or 2: two consecutive X rows share one operand row; centroids are block-diagonal
+  int k_sub;      // pack == 2: accumulator columns per packed group (bn == 2 * k_sub)
   int raw_slots;  // A-in-TMEM variant: raw X ring depth; a_slots then counts 64-column TMEM operand slots
   int a_col0;     // A-in-TMEM variant: first TMEM column of the operand slots (= n_acc * bn)
   uint32_t tmem_cols;
@@ -117,6 +123,11 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
   const int pcols   = p.bn / nparts;
   const int cbeg    = part * pcols;
   const int cend    = (part < nparts) ? cbeg + pcols : cbeg;
+  // row packing: the accumulator columns [g*k_sub, (g+1)*k_sub) belong to data row pack*r + g
+  const int ppg     = max(1, nparts / p.pack);                       // column parts per packed group
+  const int grp     = (p.pack > 1 && part < nparts) ? part / ppg : 0;
+  const int col0    = grp * p.k_sub;                                 // first accumulator column of my group
+  const bool lead   = (part < nparts) && (part % ppg == 0);          // merges its group's parts, stores labels
   uint32_t acc_cnt  = 0;
   Ring racc;
   // 1/2||c||^2 of the next centroid tile is fetched one tile ahead (registers), so its global-load
@@ -158,7 +169,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
           }
         }
         const float4* cn4 = reinterpret_cast<const float4*>(cn + c0);
-        const int jb      = jbase + c0;
+        const int jb      = jbase + c0 - col0;
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4) {
           const float4 c4 = cn4[q4];
@@ -183,20 +194,19 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
     if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
     if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
     if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
-    // merge the column parts through shared memory
-    if (part > 0) {
+    // merge the column parts of each group through shared memory
+    if (part < nparts && !lead) {
       mrg_v[(part - 1) * TILE_M + rit] = b0;
       mrg_i[(part - 1) * TILE_M + rit] = i0;
     }
     ptx::named_bar_sync(2, EPI_THREADS);
-    if (part == 0) {
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const float ov = mrg_v[q * TILE_M + rit];
-        const int oi   = mrg_i[q * TILE_M + rit];
+    if (lead) {
+      for (int q = 1; q < ppg; ++q) {
+        const float ov = mrg_v[(part + q - 1) * TILE_M + rit];
+        const int oi   = mrg_i[(part + q - 1) * TILE_M + rit];
         if (ov < b0 || (ov == b0 && oi < i0)) { b0 = ov; i0 = oi; }
       }
-      const int64_t row = first_row + t * row_stride + rit;
+      const int64_t row = (first_row + t * row_stride + rit) * p.pack + grp;
       if (row < p.n) p.labels[row] = i0;
     }
     ptx::named_bar_sync(3, EPI_THREADS);  // mrg_* may be overwritten by the next tile
@@ -356,7 +366,6 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
           racc.advance(p.n_acc);
           Ring ra = ra_tile;
           CB2_TIMED_WAIT(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u, wacc);
-          ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * p.bn;
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sa = ra.slot, pa = ra.phase;
@@ -377,7 +386,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             const uint64_t db_hi = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes);
             const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
             const int nks = min(4, (p.d - kbi * KBLOCK + 7) / 8);  // K=8 steps that hold real columns
-            const long long ti0 = clock64();
+            const long long ti0 = p.dbg_clk ? clock64() : 0;
             if (ptx::elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
@@ -390,7 +399,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
               }
             }
             __syncwarp();
-            const long long ti1 = clock64();
+            const long long ti1 = p.dbg_clk ? clock64() : 0;
             tissue += ti1 - ti0;
             if (ptx::elect_one()) {
               if (!p.b_resident) ptx::mma_commit(ptx::smem_u32(&bars->b_empty[sb]));  // frees the B stage
@@ -403,7 +412,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
           }
           if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->acc_full[acc]));  // accumulator ready
           __syncwarp();
-          tcommit += clock64() - tc0;
+          if (p.dbg_clk) tcommit += clock64() - tc0;
         }
       }
       if (p.dbg_clk && blockIdx.x == 0 && lane == 0) {
@@ -583,7 +592,6 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
           racc.advance(p.n_acc);
           Ring ra = ra_tile;
           ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
-          ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * p.bn;
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sa = ra.slot, pa = ra.phase;
@@ -820,7 +828,6 @@ fused_l2_argmin_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
           racc.advance(p.n_acc);
           Ring ra = ra_tile;
           ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
-          ptx::tc_fence_after();
           const uint32_t d_tmem = tmem_base + acc * p.bn;
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t as = ra.slot, ap = ra.phase;
@@ -911,6 +918,39 @@ __global__ void prepare_centroids_kernel(const float* __restrict__ C, int k, int
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   if (lane == 0) cnh[j] = (j < k) ? static_cast<float>(0.5 * s) : __int_as_float(0x7f800000);
+}
+
+// Row-packed operands for n_features <= 16: two consecutive rows of X are read as ONE 128-byte operand
+// row [x_2r | x_2r+1] (X is simply viewed as [n/2, 2d]), and the centroid operand becomes block-diagonal:
+// B'[g*k_sub + j] = c_j placed at columns [g*d, g*d + d).  One 128-row MMA tile then covers 256 data rows with a
+// fully used K-block (no out-of-bounds half), halving the per-row cost of the tile hand-offs that bound the
+// small-d regime.  Accumulator columns [g*k_sub, (g+1)*k_sub) hold x_{2r+g} . c_j.
+__global__ void prepare_centroids_packed_kernel(const float* __restrict__ C, int k, int d, int k_sub,
+                                                float* __restrict__ hi, float* __restrict__ lo,
+                                                float* __restrict__ cnh)
+{
+  const int jj   = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;   // row of B' in [0, 2*k_sub)
+  const int lane = threadIdx.x % 32;
+  if (jj >= 2 * k_sub) return;
+  const int g = jj / k_sub, j = jj % k_sub;
+  const int c = lane - g * d;                                          // feature index held by this column
+  const float v = (j < k && c >= 0 && c < d) ? C[static_cast<int64_t>(j) * d + c] : 0.0f;
+  const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+  hi[static_cast<int64_t>(jj) * KBLOCK + lane] = h;
+  lo[static_cast<int64_t>(jj) * KBLOCK + lane] = v - h;
+  double s = static_cast<double>(v) * static_cast<double>(v);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) cnh[jj] = (j < k) ? static_cast<float>(0.5 * s) : __int_as_float(0x7f800000);
+}
+
+// packing applies to short rows with few clusters (both halves of the block-diagonal operand fit N <= 256)
+int pack_k_sub(int d, int k)
+{
+  const char* e = std::getenv("CUML_B200_PACK");
+  if (e && std::atoi(e) == 0) return 0;
+  if (d > 16 || d % 4 != 0 || k > 128) return 0;
+  return k <= 32 ? 32 : (k <= 64 ? 64 : 128);
 }
 
 struct TilePlan {
@@ -1060,6 +1100,25 @@ bool tc_supported(int64_t d, int k)
 
 void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out)
 {
+  if (const int k_sub = pack_k_sub(d, k)) {
+    const int k_pad = 2 * k_sub;
+    if (out.k_pad != k_pad || out.d_pad != KBLOCK || !out.hi.get()) {
+      out.hi.alloc(static_cast<size_t>(k_pad) * KBLOCK, h.stream);
+      out.lo.alloc(static_cast<size_t>(k_pad) * KBLOCK, h.stream);
+      out.cnh.alloc(k_pad, h.stream);
+      out.k_pad = k_pad;
+      out.d_pad = KBLOCK;
+    }
+    out.block_n = k_pad;
+    out.pack    = 2;
+    out.k_sub   = k_sub;
+    prepare_centroids_packed_kernel<<<static_cast<unsigned>(ceil_div(k_pad, 8)), 256, 0, h.stream>>>(
+      C, k, d, k_sub, out.hi.get(), out.lo.get(), out.cnh.get());
+    CB2_CHECK_LAUNCH();
+    return;
+  }
+  out.pack  = 1;
+  out.k_sub = 0;
   const bool ts   = use_ts(h, d, k);
   const bool pair = !ts && use_2cta(h, d, k);
   TilePlan t = pair ? plan_tiles_2cta(d, k, h.smem_optin) : plan_tiles(d, k, h.smem_optin);
@@ -1084,19 +1143,84 @@ void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out)
   CB2_CHECK_LAUNCH();
 }
 
+// label of ONE row against the packed operand buffers (the odd last row of a row-packed launch)
+__global__ void assign_tail_row_kernel(const float* __restrict__ x, int d, int k, const float* __restrict__ hi,
+                                       const float* __restrict__ lo, int32_t* __restrict__ label)
+{
+  // one warp; lane j, j+32, ... scans centroids; exact (x-c)^2 in fp32 with c = hi + lo
+  float best = __int_as_float(0x7f800000);
+  int bidx   = 0x7fffffff;
+  for (int j = threadIdx.x; j < k; j += 32) {
+    float s = 0.f;
+    for (int c = 0; c < d; ++c) {
+      const float cv = hi[j * KBLOCK + c] + lo[j * KBLOCK + c];
+      const float df = x[c] - cv;
+      s += df * df;
+    }
+    if (s < best) { best = s; bidx = j; }
+  }
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oi   = __shfl_xor_sync(0xffffffffu, bidx, off);
+    if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+  }
+  if (threadIdx.x == 0) *label = bidx;
+}
+
 void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen, int32_t* labels,
                float* dbg_dots)
 {
   if (n == 0) return;
   CB2_EXPECTS(h.cc_major == 10, "the tcgen05 k-means engine needs an sm_100-class GPU (B200)");
   CB2_EXPECTS(reinterpret_cast<uintptr_t>(X) % 16 == 0, "X must be 16-byte aligned for TMA");
+  if (cen.pack == 2) {
+    // two rows per operand row: X viewed as [n/2, 2d]
+    const int64_t n2 = n / 2;
+    if (n2 > 0) {
+      TilePlan t = plan_tiles(2 * d, cen.k_pad, h.smem_optin);
+      CB2_EXPECTS(t.bn == cen.k_pad && t.kb == 1, "row-packed plan mismatch");
+      FusedParams p{};
+      p.n = 2 * n2; p.m_tiles = ceil_div(n2, TILE_M); p.k_tiles = 1; p.d = 2 * d; p.kb = 1; p.bn = t.bn;
+      p.a_slots = t.a_slots; p.b_stages = t.b_stages; p.b_resident = t.b_resident;
+      p.n_acc = std::min(MAX_ACC, 512 / t.bn); p.pack = 2; p.k_sub = cen.k_sub;
+      uint32_t cols = 32;
+      while (cols < static_cast<uint32_t>(p.n_acc * t.bn)) cols <<= 1;
+      p.tmem_cols = cols;
+      p.cnh = cen.cnh.get(); p.labels = labels; p.dbg_dots = nullptr;
+      CUtensorMap tm_x  = make_map_2d(X, static_cast<uint64_t>(2 * d), static_cast<uint64_t>(n2),
+                                      static_cast<uint64_t>(2 * d) * sizeof(float), KBLOCK, TILE_M,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+      CUtensorMap tm_hi = make_map_2d(cen.hi.get(), KBLOCK, cen.k_pad, KBLOCK * sizeof(float), KBLOCK, t.bn,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+      CUtensorMap tm_lo = make_map_2d(cen.lo.get(), KBLOCK, cen.k_pad, KBLOCK * sizeof(float), KBLOCK, t.bn,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+      static bool pk_attr = false;
+      if (!pk_attr) {
+        CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(h.smem_optin)));
+        pk_attr = true;
+      }
+      EventPair ev{};
+      if (h.timing) ev = h.begin_event();
+      const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
+      fused_l2_argmin_kernel<<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+      CB2_CHECK_LAUNCH();
+      if (h.timing) h.end_event(ev, true);
+    }
+    if (n & 1) {
+      assign_tail_row_kernel<<<1, 32, 0, h.stream>>>(X + (n - 1) * d, d, k, cen.hi.get(), cen.lo.get(), labels + (n - 1));
+      CB2_CHECK_LAUNCH();
+    }
+    return;
+  }
   if (use_ts(h, d, k)) {
     const TsPlan tp = plan_ts(h, d, k);
     CB2_EXPECTS(tp.bn == cen.block_n, "centroid operand buffers were prepared for a different tile plan");
     FusedParams p{};
     p.n = n; p.m_tiles = ceil_div(n, TILE_M); p.k_tiles = cen.k_pad / tp.bn; p.d = d; p.kb = tp.kb; p.bn = tp.bn;
     p.a_slots = tp.a_slots; p.raw_slots = tp.raw_slots; p.b_stages = tp.b_stages; p.b_resident = tp.b_resident;
-    p.n_acc = tp.n_acc; p.a_col0 = tp.n_acc * tp.bn; p.tmem_cols = 512;
+    p.n_acc = tp.n_acc; p.a_col0 = tp.n_acc * tp.bn; p.tmem_cols = 512; p.pack = 1; p.k_sub = 0;
     p.cnh = cen.cnh.get(); p.labels = labels; p.dbg_dots = dbg_dots;
     CUtensorMap tm_x = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
                                    static_cast<uint64_t>(d) * sizeof(float), KBLOCK, TILE_M,
@@ -1148,6 +1272,8 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   p.a_slots   = t.a_slots;
   p.b_stages  = t.b_stages;
   p.b_resident = t.b_resident;
+  p.pack       = 1;
+  p.k_sub      = 0;
   p.n_acc = std::min(MAX_ACC, 512 / t.bn);
   uint32_t cols = 32;
   while (cols < static_cast<uint32_t>(p.n_acc * t.bn)) cols <<= 1;

@@ -23,6 +23,8 @@ bool tc_supported(int64_t d, int k);
 struct TcCentroids {           // per-iteration operand buffers (hi/lo split + half norms)
   DevBuf<float> hi, lo, cnh;
   int k_pad = 0, d_pad = 0, block_n = 0;
+  int pack = 1;   // rows of X packed side by side into one 128-byte operand row (2 when n_features <= 16)
+  int k_sub = 0;  // centroid rows per packed group (k padded to 32/64/128) when pack == 2
 };
 void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out);
 void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen,
