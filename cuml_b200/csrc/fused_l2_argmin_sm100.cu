@@ -82,6 +82,7 @@ struct FusedParams {
   int b_stages;   // 2..4
   int b_resident; // all k_tiles*kb centroid blocks fit the B stages: load once, never release
   int n_acc;      // TMEM accumulator stages: min(MAX_ACC, 512 / bn)
+  int a_stream;   // n_features > 128: X K-blocks are not kept across centroid tiles but re-streamed per tile
   int pack;       // 1, or 2: two consecutive X rows share one operand row; centroids are block-diagonal
   int k_sub;      // pack == 2: accumulator columns per packed group (bn == 2 * k_sub)
   int raw_slots;  // A-in-TMEM variant: raw X ring depth; a_slots then counts 64-column TMEM operand slots
@@ -273,7 +274,9 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
       Ring ra;
       long long wcyc = 0;
       const long long tstart = clock64();
+      const int a_reps = p.a_stream ? p.k_tiles : 1;   // streamed mode reloads the row tile per centroid tile
       for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+        for (int rep = 0; rep < a_reps; ++rep)
         for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
           const uint32_t sa = ra.slot, pa = ra.phase;
           ra.advance(p.a_slots);
@@ -320,10 +323,12 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
       Ring ra;
     long long wcyc = 0;
     const long long tstart = clock64();
+    const int a_reps = p.a_stream ? p.k_tiles : 1;
     for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      for (int rep = 0; rep < a_reps; ++rep)
       for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
         const uint32_t sa = ra.slot, pa = ra.phase;
-          ra.advance(p.a_slots);
+        ra.advance(p.a_slots);
         CB2_TIMED_WAIT(ptx::smem_u32(&bars->a_raw_full[sa]), pa, wcyc);
         uint4* hi = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES);
@@ -357,20 +362,20 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     {
       const uint32_t idesc = ptx::umma_idesc_tf32(TILE_M, p.bn);
       uint32_t b_cnt = 0, acc_cnt = 0;
-      Ring ra_tile, rb, racc;
+      Ring ra_tile, ra_run, rb, racc;
       long long wacc = 0, wa = 0, wb = 0, tissue = 0, tcommit = 0, tc0 = 0;
       const long long tstart = clock64();
       for (int64_t tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ra_tile.advance_by(p.kb, p.a_slots)) {
         for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
           const uint32_t acc = racc.slot, pacc = racc.phase;
           racc.advance(p.n_acc);
-          Ring ra = ra_tile;
+          Ring ra = p.a_stream ? ra_run : ra_tile;
           CB2_TIMED_WAIT(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u, wacc);
           const uint32_t d_tmem = tmem_base + acc * p.bn;
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sa = ra.slot, pa = ra.phase;
             ra.advance(p.a_slots);
-            if (nt == 0) CB2_TIMED_WAIT(ptx::smem_u32(&bars->a_ready[sa]), pa, wa);  // first use of this X K-block
+            if (nt == 0 || p.a_stream) CB2_TIMED_WAIT(ptx::smem_u32(&bars->a_ready[sa]), pa, wa);  // first use
             uint32_t sb = rb.slot;
             const uint32_t pb = rb.phase;
             rb.advance(p.b_stages);
@@ -405,11 +410,12 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
               if (!p.b_resident) ptx::mma_commit(ptx::smem_u32(&bars->b_empty[sb]));  // frees the B stage
               // last centroid tile: this X K-block is not needed again -> release its slot early so
               // the next row tile's load + hi/lo split overlaps the remaining K-blocks
-              if (nt == p.k_tiles - 1) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[sa]));
+              if (nt == p.k_tiles - 1 || p.a_stream) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[sa]));
             }
             __syncwarp();
             tc0 = ti1;
           }
+          ra_run = ra;
           if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->acc_full[acc]));  // accumulator ready
           __syncwarp();
           if (p.dbg_clk) tcommit += clock64() - tc0;
@@ -507,8 +513,10 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     {
       uint32_t a_cnt = 0;
       Ring ra;
+      const int a_reps = p.a_stream ? p.k_tiles : 1;
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
         const int32_t row0 = static_cast<int32_t>(pt * 2 * TILE_M + cta_rank * TILE_M);
+        for (int rep = 0; rep < a_reps; ++rep)
         for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
           const uint32_t sa = ra.slot, pa = ra.phase;
           ra.advance(p.a_slots);
@@ -553,10 +561,12 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     const int ct = threadIdx.x - 128;
     uint32_t a_cnt = 0;
       Ring ra;
+    const int a_reps = p.a_stream ? p.k_tiles : 1;
     for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
+      for (int rep = 0; rep < a_reps; ++rep)
       for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
         const uint32_t sa = ra.slot, pa = ra.phase;
-          ra.advance(p.a_slots);
+        ra.advance(p.a_slots);
         ptx::mbar_wait(ptx::smem_u32(&bars->a_raw_full[sa]), pa);
         uint4* hi = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES);
@@ -585,18 +595,18 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     if (leader) {
       const uint32_t idesc = ptx::umma_idesc_tf32(2 * TILE_M, p.bn);
       uint32_t b_cnt = 0, acc_cnt = 0;
-      Ring ra_tile, rb, racc;
+      Ring ra_tile, ra_run, rb, racc;
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs, ra_tile.advance_by(p.kb, p.a_slots)) {
         for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
           const uint32_t acc = racc.slot, pacc = racc.phase;
           racc.advance(p.n_acc);
-          Ring ra = ra_tile;
+          Ring ra = p.a_stream ? ra_run : ra_tile;
           ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
           const uint32_t d_tmem = tmem_base + acc * p.bn;
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sa = ra.slot, pa = ra.phase;
             ra.advance(p.a_slots);
-            if (nt == 0) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[sa]), pa);
+            if (nt == 0 || p.a_stream) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[sa]), pa);
             uint32_t sb = rb.slot;
             const uint32_t pb = rb.phase;
             rb.advance(p.b_stages);
@@ -622,10 +632,11 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
                 ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
               }
               if (!p.b_resident) ptx::mma_commit_2cta(ptx::smem_u32(&bars->b_empty[sb]), 3);
-              if (nt == p.k_tiles - 1) ptx::mma_commit_2cta(ptx::smem_u32(&bars->a_empty[sa]), 3);
+              if (nt == p.k_tiles - 1 || p.a_stream) ptx::mma_commit_2cta(ptx::smem_u32(&bars->a_empty[sa]), 3);
             }
             __syncwarp();
           }
+          ra_run = ra;
           if (ptx::elect_one()) ptx::mma_commit_2cta(ptx::smem_u32(&bars->acc_full[acc]), 3);
           __syncwarp();
         }
@@ -954,7 +965,7 @@ int pack_k_sub(int d, int k)
 }
 
 struct TilePlan {
-  int kb, bn, a_slots, b_stages, b_resident;
+  int kb, bn, a_slots, b_stages, b_resident, a_stream;
   size_t smem;
 };
 
@@ -974,7 +985,8 @@ TilePlan plan_tiles(int d, int k, size_t smem_limit)
   t.bn = 0;
   for (int bn = bn0; bn >= 32 && t.bn == 0; bn /= 2) {
     const int k_tiles = static_cast<int>(ceil_div(k, bn));
-    const int a_min   = (k_tiles > 1) ? t.kb : std::min(t.kb, 2);  // all K-blocks stay resident across N tiles
+    t.a_stream        = (k_tiles > 1 && t.kb > 4) ? 1 : 0;        // wide rows: re-stream X per centroid tile
+    const int a_min   = (k_tiles > 1 && !t.a_stream) ? t.kb : std::min(t.kb, 2);  // resident across N tiles
     // at least 3 B stages when a stage is short (N <= 128), 2 otherwise
     const int b_min = (bn <= 128) ? 3 : 2;
     if (bytes(bn, std::max(a_min, 2), b_min) > smem_limit) continue;
@@ -1007,8 +1019,9 @@ TilePlan plan_tiles_2cta(int d, int k, size_t smem_limit)
            6 * TILE_M * 4 + sizeof(Barriers) + 1024;
   };
   const int k_tiles = static_cast<int>(ceil_div(k, bn));
-  const int a_min   = (k_tiles > 1) ? t.kb : std::min(t.kb, 2);
-  int b_stages      = 2;
+  t.a_stream        = (k_tiles > 1 && t.kb > 4) ? 1 : 0;
+  const int a_min   = (k_tiles > 1 && !t.a_stream) ? t.kb : std::min(t.kb, 2);
+  int b_stages      = t.a_stream ? 3 : 2;
   int resident      = 0;
   if (k_tiles * t.kb <= MAX_STAGES && bytes(std::max(a_min, 2), k_tiles * t.kb) <= smem_limit) {
     b_stages = k_tiles * t.kb;
@@ -1095,7 +1108,7 @@ bool use_ts(const Handle& h, int d, int k)
 
 bool tc_supported(int64_t d, int k)
 {
-  return d >= 4 && d % 4 == 0 && d <= 128 && k >= 1 && k <= (1 << 20);
+  return d >= 4 && d % 4 == 0 && d <= 1024 && k >= 1 && k <= (1 << 20);
 }
 
 void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out)
@@ -1272,6 +1285,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   p.a_slots   = t.a_slots;
   p.b_stages  = t.b_stages;
   p.b_resident = t.b_resident;
+  p.a_stream   = t.a_stream;
   p.pack       = 1;
   p.k_sub      = 0;
   p.n_acc = std::min(MAX_ACC, 512 / t.bn);

@@ -48,7 +48,7 @@ class LloydSolver {
     bool tc_ok = std::is_same<T, float>::value && tc_supported(d, k) && h.cc_major == 10 && aligned;
     if (engine == ENGINE_TC) {
       CB2_EXPECTS(tc_ok, "tcgen05 engine requested but unsupported for this problem (needs fp32, sm_100, "
-                         "n_features % 4 == 0, n_features <= 128, 16-byte aligned X)");
+                         "n_features % 4 == 0, n_features <= 1024, 16-byte aligned X)");
     }
     use_tc_ = (engine == ENGINE_SIMT) ? false : tc_ok;
     // label storage: every partition starts on a 16-byte boundary and the tail is padded so the

@@ -41,7 +41,8 @@ def _step(env, X, C0, k, engine, w=None):
 
 
 SHAPES = [(2000, 8, 5), (5000, 32, 16), (3001, 20, 3), (4000, 64, 40), (1500, 7, 9), (20000, 128, 300),
-          (129, 4, 2), (128, 32, 1), (10000, 16, 64), (7000, 96, 130), (9000, 100, 257)]
+          (129, 4, 2), (128, 32, 1), (10000, 16, 64), (7000, 96, 130), (9000, 100, 257),
+          (3000, 160, 300), (2500, 256, 520), (2001, 12, 100), (4001, 16, 33)]
 
 
 @pytest.mark.parametrize("n,d,k", SHAPES)
