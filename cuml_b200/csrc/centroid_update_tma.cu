@@ -283,6 +283,7 @@ struct UpdParams6 {
   int64_t tiles_total;
   int64_t tiles_per_block;
   int d, k, tr, nb, nstage;
+  int dbg_skip;   // profiling knob (env CUML_B200_UPD_SKIP): consumers acknowledge stages without touching them
   const int32_t* labels;
   const float* w;
   float* partial_S;
@@ -369,7 +370,7 @@ accumulate_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams
       const int64_t left = p.n - row0;
       const int valid    = left < p.tr ? static_cast<int>(left) : p.tr;
       for (int r0 = 0; r0 < p.tr; r0 += 4) {
-        if (r0 >= valid) break;
+        if (r0 >= valid || p.dbg_skip) break;
         // labels of the 4 rows of this batch (one broadcast 16-byte read); rows past the end get -1
         int4 lb4;
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
@@ -525,8 +526,13 @@ static TmaUpdatePlan plan_tma_update(const Handle& h, int d, int k)
         const int cons_sm       = per_sm * nb * cons_per_sub;
         const double inflight   = static_cast<double>(per_sm) * nstage * tile_bytes;       // bytes per SM
         // consumers below 8 per SM are the limiter; beyond ~12 extra warps do not help
-        const double score = std::min(inflight, 160.0 * 1024) * std::min(cons_sm, 12) / 12.0 +
-                             (tile_bytes >= 8192 ? 1.0 : 0.0);
+        // the ring alone reaches ~6.6 TB/s with >= 64 KB in flight per SM (measured with the consumers
+        // disabled); the kernel itself is bound by shared-memory wavefronts at ~3.5 TB/s whatever the split,
+        // so the score only has to avoid starving either side (A/B on C3 and C5: profiles/README.md)
+        static const double cap_kb = std::getenv("CUML_B200_UPD_INFLIGHT_KB") ? std::atof(std::getenv("CUML_B200_UPD_INFLIGHT_KB")) : 96.0;
+        static const int cons_cap  = std::getenv("CUML_B200_UPD_CONS_CAP") ? std::atoi(std::getenv("CUML_B200_UPD_CONS_CAP")) : 16;
+        const double score = std::min(inflight, cap_kb * 1024) * std::min(cons_sm, cons_cap) / cons_cap +
+                             (tile_bytes >= 8192 ? 1.0 : 0.0) + 1e-6 * inflight;
         if (score > best_score) {
           best_score       = score;
           best.ds          = ds;
@@ -557,9 +563,12 @@ struct RowsPlan {
 static RowsPlan plan_rows_update(const Handle& h, int d, int k)
 {
   RowsPlan best;
+  int mode = 0;   // 0 = off (default: measured slower than the vectorised kernel), 1 = when >= 5 consumer warps
+                  // per SM fit, 2 = always (profiling)
   {
     const char* e = std::getenv("CUML_B200_UPDATE_ROWS");
-    if (e && std::atoi(e) == 0) return best;
+    if (e) mode = std::atoi(e);
+    if (mode == 0) return best;
   }
   if (d % 4 != 0) return best;
   const int ds = d >= 32 ? 32 : d;
@@ -597,7 +606,7 @@ static RowsPlan plan_rows_update(const Handle& h, int d, int k)
       }
     }
   }
-  if (best.ds && best.ctas_per_sm * best.nb < 5) best.ds = 0;   // too few consumer warps: use the vectorised kernel
+  if (mode == 1 && best.ds && best.ctas_per_sm * best.nb < 5) best.ds = 0;   // too few consumer warps: vectorised kernel
   return best;
 }
 
@@ -621,6 +630,13 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
   if (const RowsPlan rp = plan_rows_update(h, d, k); rp.ds > 0) {
     UpdParams6 q{};
     q.n = n; q.d = d; q.k = k; q.tr = rp.tr; q.nb = rp.nb; q.nstage = rp.nstage;
+    {
+      const char* e = std::getenv("CUML_B200_UPD_SKIP");
+      q.dbg_skip    = e ? std::atoi(e) : 0;
+      if (std::getenv("CUML_B200_UPD_PLAN"))
+        std::printf("[cuml_b200 update plan] ds %d nb %d tr %d nstage %d slices %d ctas/sm %d smem %zu\n", rp.ds, rp.nb, rp.tr,
+                    rp.nstage, rp.slices, rp.ctas_per_sm, rp.smem);
+    }
     q.tiles_total = ceil_div(n, rp.tr);
     int64_t rb = std::max<int64_t>(1, static_cast<int64_t>(h.sm_count) * rp.ctas_per_sm / rp.slices);
     rb         = std::min<int64_t>(rb, q.tiles_total);
@@ -654,6 +670,9 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
   }
   TmaUpdatePlan pl = plan_tma_update(h, d, k);
   CB2_EXPECTS(pl.ds > 0, "no shared-memory plan for the TMA centroid update");
+  if (std::getenv("CUML_B200_UPD_PLAN"))
+    std::printf("[cuml_b200 update plan v5] ds %d nb %d tr %d nstage %d slices %d ctas/sm %d warps %d smem %zu\n", pl.ds, pl.nb,
+                pl.tr, pl.nstage, pl.slices, pl.ctas_per_sm, pl.warps, pl.smem);
   UpdParams p{};
   p.n           = n;
   p.d           = d;
