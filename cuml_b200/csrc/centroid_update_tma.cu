@@ -81,6 +81,25 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity)
   }
 }
 
+// wait that lets the hardware park the warp (suspend-time hint) instead of burning issue slots on polling
+__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity)
+{
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(20000u)
+      : "memory");
+    if (!ok && ++spins > (1u << 22)) {
+      printf("cuml_b200: update-kernel mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  } while (!ok);
+}
+
 // NC = 16-byte chunks per sub-slice row: 8 (128B-swizzled, ds >= 32), 4 (64B), 2 (32B) or 1 (dense).
 // Warp roles: 0 = TMA producer, 1..na = analysts (round-robin over tiles), then the consumers.  Lane = row: one warp instruction
 // covers 32 consecutive rows.  The analyst computes, once per 32-row group, each row's rank among
@@ -213,17 +232,26 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
       const int64_t row0 = t * p.tr;
       const int64_t left = p.n - row0;
       const int valid    = left < p.tr ? static_cast<int>(left) : p.tr;
-#pragma unroll 2
+      // software pipeline: the loads of the next 32-row group are issued before the read-modify-write rounds
+      // of the current one, so their shared-memory latency overlaps the dependent table updates
+      int lb_n = 0, meta_n = 0;
+      float4 x0_n = make_float4(0.f, 0.f, 0.f, 0.f), x1_n = x0_n;
+      auto fetch = [&](int r) {
+        lb_n   = (r < valid) ? lds32(ls + r * 4) : 0;
+        meta_n = lds32(ms + r * 4);
+        const uint32_t xa = xs + static_cast<uint32_t>(r) * ROWB + ((j0 ^ ((static_cast<uint32_t>(r) >> SH) & MSK)) << 4);
+        x0_n = lds128(xa);
+        if (CPL == 2) x1_n = lds128(xa ^ 16u);
+      };
+      fetch(lane);
       for (int r = lane; r < p.tr; r += 32) {
         const bool ok    = r < valid;
-        const int lb     = ok ? lds32(ls + r * 4) : 0;
-        const int meta   = lds32(ms + r * 4);
+        const int lb     = lb_n;
+        const int meta   = meta_n;
+        float4 x0 = x0_n, x1 = x1_n;
+        if (r + 32 < p.tr) fetch(r + 32);
         const int rank   = meta & 0xff;
         const int maxr   = meta >> 8;                       // warp-uniform
-        const uint32_t xa = xs + static_cast<uint32_t>(r) * ROWB + ((j0 ^ ((static_cast<uint32_t>(r) >> SH) & MSK)) << 4);
-        float4 x0 = lds128(xa);
-        float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (CPL == 2) x1 = lds128(xa ^ 16u);
         if (HAS_W) {
           const float wv = ok ? __ldg(p.w + row0 + r) : 0.0f;
           x0.x *= wv; x0.y *= wv; x0.z *= wv; x0.w *= wv;
@@ -451,6 +479,358 @@ accumulate_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams
   }
 }
 
+// ---- v7: label-class ownership ----------------------------------------------------------------------
+// One [k x DS] fp32 table per CTA (DS = 32*VEC columns), NCONS consumer warps.  Consumer w exclusively owns
+// the table rows of the clusters with (label % NCONS) == w, so no two warps ever touch the same cell and no
+// atomics or rank bookkeeping are needed.  Per 32-row group every consumer reads the 32 labels (lane = row),
+// ballots the rows of its class and then walks its rows one by one with lane = column: the X row segment,
+// the table row read and the table row write are each ONE contiguous, conflict-free shared-memory access
+// (the vectorised variant above pays ~3x the wavefronts for its 32 random table rows per instruction).
+// Consecutive rows of one consumer that share a label are ordered by program order of the same lanes.
+template <int VEC>
+struct VecIO;
+template <>
+struct VecIO<1> {
+  float v[1];
+  __device__ __forceinline__ void load(uint32_t a) { asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(a)); }
+  __device__ __forceinline__ void store(uint32_t a) const { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v[0]) : "memory"); }
+};
+template <>
+struct VecIO<2> {
+  float v[2];
+  __device__ __forceinline__ void load(uint32_t a) { asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1]) : "r"(a)); }
+  __device__ __forceinline__ void store(uint32_t a) const { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v[0]), "f"(v[1]) : "memory"); }
+};
+template <>
+struct VecIO<4> {
+  float v[4];
+  __device__ __forceinline__ void load(uint32_t a)
+  {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(a));
+  }
+  __device__ __forceinline__ void store(uint32_t a) const
+  {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+  }
+};
+
+struct UpdParams7 {
+  int64_t n;
+  int64_t tiles_total;
+  int64_t tiles_per_block;
+  int d, k, tr, nstage, ncons;   // ncons: power of two
+  int nl;                        // depth of the label / row-list ring (>= nstage)
+  int dbg_skip;
+  const int32_t* labels;
+  const float* w;
+  const uint8_t* cls_map;        // [k] label -> class (balanced by last iteration's cluster sizes), or null
+  float* partial_S;
+  float* partial_W;
+};
+
+constexpr int OWN_CONS  = 16;   // consumer warps = label classes
+constexpr int OWN_NA    = 2;    // analyst warps (alternate tiles)
+constexpr int OWN_MAXCH = 8;    // 32-row groups per tile (tile rows <= 256)
+
+__device__ __forceinline__ uint2 lds64u(uint32_t addr)
+{
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
+constexpr int OWN_MAXNL = 8;    // label ring depth
+
+// class map for the next launch: clusters sorted by size (descending), dealt to the 16 classes in serpentine
+// order, so every consumer warp gets about the same number of rows whatever the cluster-size skew
+__global__ void __launch_bounds__(1024)
+balance_classes_kernel(const double* __restrict__ W, int k, uint8_t* __restrict__ cls_map)
+{
+  extern __shared__ float bc_w[];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const float v = static_cast<float>(W[j]);
+    bc_w[j]       = (v == v && v >= 0.f && v < 3.0e38f) ? v : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const float me = bc_w[j];
+    int rank = 0;
+    for (int i = 0; i < k; ++i) {
+      const float o = bc_w[i];
+      rank += (o > me || (o == me && i < j)) ? 1 : 0;
+    }
+    const int q = rank / OWN_CONS, m = rank % OWN_CONS;
+    cls_map[j]  = static_cast<uint8_t>((q & 1) ? (OWN_CONS - 1 - m) : m);
+  }
+}
+
+// Warp roles: 0 = X producer; 1 = label producer; 2..3 = analysts; 4..19 = consumers.
+//   Two rings: X tiles (nstage deep, 32..64 KB each) and labels + row lists (nl deep, ~2 KB each).  The
+//   label ring runs ahead of the X ring, so the analysts' latency never sits on an X stage's turn-around.
+//   analyst  : counting sort of a tile's rows by label class, once per tile: 4 ballots (one per class bit)
+//              give lane j < 16 the row mask of class j; the rows land in `perm` (row << 16 | label), class
+//              after class, in row order, with the class offsets next to it.  Also keeps the per-cluster
+//              row counts of unweighted fits (integer shared-memory reductions).
+//   consumer : owns the table rows of its class.  Walks its perm segment with lane = column: per row one
+//              contiguous table read, add, write; the X segment of the next row and the next list entries are
+//              already in flight.  Two rows per loop iteration (register rotation without moves).
+template <int VEC, bool HAS_W>
+__global__ void __launch_bounds__((2 + OWN_NA + OWN_CONS) * 32)
+accumulate_owner_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams7 p)
+{
+  constexpr int DS        = 32 * VEC;
+  constexpr uint32_t ROWB = DS * 4;
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t raw  = ptx::smem_u32(smem_dyn);
+  const uint32_t base = (raw + 127u) & ~127u;
+  uint8_t* g          = smem_dyn + (base - raw);
+  // X stages | label stages (labels | perm | wperm | class offsets) | table | wtab | class map | barriers
+  const uint32_t x_bytes    = static_cast<uint32_t>(p.tr) * ROWB;
+  const uint32_t lab_bytes  = static_cast<uint32_t>(p.tr) * 4u;
+  const uint32_t perm_bytes = lab_bytes + 128u;     // read up to 3 entries past a segment
+  const uint32_t l_bytes    = lab_bytes + 2u * perm_bytes + 128u;
+  const uint32_t lbase      = base + p.nstage * x_bytes;
+  const uint32_t tab_off    = p.nstage * x_bytes + p.nl * l_bytes;
+  const uint32_t tab_u32    = base + tab_off;
+  float* tab       = reinterpret_cast<float*>(g + tab_off);
+  float* wtab      = tab + static_cast<size_t>(p.k) * DS;
+  uint8_t* smap    = reinterpret_cast<uint8_t*>(wtab + ((p.k + 3) & ~3));
+  uint64_t* bars   = reinterpret_cast<uint64_t*>(smap + ((p.k + 15) & ~15));
+  const uint32_t bars_u32 = ptx::smem_u32(bars);
+  const uint32_t wtab_u32 = ptx::smem_u32(wtab);
+  const uint32_t smap_u32 = ptx::smem_u32(smap);
+  const uint32_t B_FULLX = 0, B_EMPTYX = MAX_NSTAGE * 8, B_FULLL = 2 * MAX_NSTAGE * 8,
+                 B_READYL = B_FULLL + OWN_MAXNL * 8, B_EMPTYL = B_READYL + OWN_MAXNL * 8;
+
+  const int warp  = threadIdx.x / 32;
+  const int lane  = threadIdx.x % 32;
+  const int slice = blockIdx.y;
+  const int cs    = slice * DS;
+  const bool counts = (slice == 0);
+
+  for (int i = threadIdx.x; i < p.k * DS; i += blockDim.x) tab[i] = 0.0f;
+  for (int i = threadIdx.x; i < p.k; i += blockDim.x) wtab[i] = 0.0f;   // (int 0 == float 0)
+  for (int i = threadIdx.x; i < p.k; i += blockDim.x) smap[i] = p.cls_map ? p.cls_map[i] : static_cast<uint8_t>(i & (OWN_CONS - 1));
+  for (uint32_t i = threadIdx.x; i < p.nl * l_bytes / 4u; i += blockDim.x)   // list slots past a segment are read
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(lbase + i * 4u), "r"(0u) : "memory");   // (never used): keep in range
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_NSTAGE; ++s) {
+      ptx::mbar_init(bars_u32 + B_FULLX + s * 8, 1);
+      ptx::mbar_init(bars_u32 + B_EMPTYX + s * 8, OWN_CONS);
+    }
+    for (int s = 0; s < OWN_MAXNL; ++s) {
+      ptx::mbar_init(bars_u32 + B_FULLL + s * 8, 1);
+      ptx::mbar_init(bars_u32 + B_READYL + s * 8, 1);
+      ptx::mbar_init(bars_u32 + B_EMPTYL + s * 8, OWN_CONS);
+    }
+    ptx::fence_barrier_init();
+    ptx::prefetch_tmap(&tm_x);
+  }
+  __syncthreads();
+
+  const int64_t t_begin = static_cast<int64_t>(blockIdx.x) * p.tiles_per_block;
+  const int64_t t_end   = min(p.tiles_total, t_begin + p.tiles_per_block);
+  const bool prof       = (p.dbg_skip & 2) != 0;   // role-level cycle accounting (CUML_B200_UPD_SKIP=2)
+
+  if (warp == 0) {
+    // ---------------- X producer ----------------
+    uint32_t s = 0, ph = 0;
+    for (int64_t t = t_begin; t < t_end; ++t) {
+      mbar_wait_park(bars_u32 + B_EMPTYX + s * 8, ph ^ 1u);
+      if (ptx::elect_one()) {
+        const uint32_t full = bars_u32 + B_FULLX + s * 8;
+        ptx::mbar_arrive_expect_tx(full, x_bytes);
+        ptx::tma_load_2d_hint(base + s * x_bytes, &tm_x, cs, static_cast<int32_t>(t * p.tr), full, ptx::kEvictFirst);
+      }
+      __syncwarp();
+      if (++s == static_cast<uint32_t>(p.nstage)) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ---------------- label producer ----------------
+    uint32_t s = 0, ph = 0;
+    for (int64_t t = t_begin; t < t_end; ++t) {
+      mbar_wait_park(bars_u32 + B_EMPTYL + s * 8, ph ^ 1u);
+      if (ptx::elect_one()) {
+        const uint32_t full = bars_u32 + B_FULLL + s * 8;
+        ptx::mbar_arrive_expect_tx(full, lab_bytes);
+        bulk_load_1d(lbase + s * l_bytes, p.labels + t * p.tr, lab_bytes, full);
+      }
+      __syncwarp();
+      if (++s == static_cast<uint32_t>(p.nl)) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp < 2 + OWN_NA) {
+    // ---------------- analysts ----------------
+    const int aw      = warp - 2;
+    const uint32_t lt = (1u << lane) - 1u;
+    // lane j < 16 selects class j: bit b of a row's class must equal bit b of j
+    const uint32_t nj0 = (lane & 1) ? 0u : 0xffffffffu, nj1 = (lane & 2) ? 0u : 0xffffffffu;
+    const uint32_t nj2 = (lane & 4) ? 0u : 0xffffffffu, nj3 = (lane & 8) ? 0u : 0xffffffffu;
+    const uint32_t lane_lt16 = lane < OWN_CONS ? 0xffffffffu : 0u;
+    uint32_t s = 0, ph = 0;
+    int turn = 0;
+    long long c_wait = 0;
+    const long long c_start = clock64();
+    for (int64_t t = t_begin; t < t_end; ++t) {
+      if (turn == aw) {
+        const long long c0 = prof ? clock64() : 0;
+        mbar_wait_park(bars_u32 + B_FULLL + s * 8, ph);
+        if (prof) c_wait += clock64() - c0;
+        const uint32_t ls   = lbase + s * l_bytes;
+        const uint32_t perm = ls + lab_bytes;
+        const uint32_t wprm = perm + perm_bytes;
+        const uint32_t offs = wprm + perm_bytes;
+        const int64_t row0  = t * p.tr;
+        const int64_t left  = p.n - row0;
+        const int valid     = left < p.tr ? static_cast<int>(left) : p.tr;
+        int lbv[OWN_MAXCH], clv[OWN_MAXCH];
+        float wv[OWN_MAXCH];
+        uint32_t keep[OWN_MAXCH];   // lane j < 16: rows of class j in group c
+#pragma unroll
+        for (int c = 0; c < OWN_MAXCH; ++c) {
+          lbv[c] = (c * 32 < p.tr) ? lds32(ls + (c * 32 + lane) * 4) : 0;
+          if (HAS_W) wv[c] = (c * 32 + lane < valid) ? __ldg(p.w + row0 + c * 32 + lane) : 0.0f;
+        }
+#pragma unroll
+        for (int c = 0; c < OWN_MAXCH; ++c) {
+          clv[c] = 0;
+          if (c * 32 < p.tr && c * 32 + lane < valid)   // labels past the end of the data are not labels
+            asm volatile("ld.shared.u8 %0, [%1];" : "=r"(clv[c]) : "r"(smap_u32 + static_cast<uint32_t>(lbv[c])));
+        }
+        int tot = 0;
+#pragma unroll
+        for (int c = 0; c < OWN_MAXCH; ++c) {
+          keep[c] = 0;
+          if (c * 32 < p.tr) {
+            // 4 ballots (one per class bit) + the valid mask give lane j < 16 the row mask of class j
+            const bool ok     = (c * 32 + lane < valid) && !(p.dbg_skip & 1);
+            const uint32_t vm = __ballot_sync(0xffffffffu, ok);
+            const uint32_t b0 = __ballot_sync(0xffffffffu, (clv[c] & 1) != 0);
+            const uint32_t b1 = __ballot_sync(0xffffffffu, (clv[c] & 2) != 0);
+            const uint32_t b2 = __ballot_sync(0xffffffffu, (clv[c] & 4) != 0);
+            const uint32_t b3 = __ballot_sync(0xffffffffu, (clv[c] & 8) != 0);
+            keep[c] = vm & (b0 ^ nj0) & (b1 ^ nj1) & (b2 ^ nj2) & (b3 ^ nj3) & lane_lt16;
+            tot += __popc(keep[c]);
+            if (!HAS_W && counts && ok)
+              asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(wtab_u32 + static_cast<uint32_t>(lbv[c]) * 4u), "r"(1) : "memory");
+          }
+        }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += v;
+        }
+        int run = incl - tot;   // lane j: first slot of class j; lane 16: number of queued rows
+        if (lane <= OWN_CONS) asm volatile("st.shared.b32 [%0], %1;" ::"r"(offs + lane * 4u), "r"(run) : "memory");
+#pragma unroll
+        for (int c = 0; c < OWN_MAXCH; ++c) {
+          if (c * 32 < p.tr) {
+            const bool ok      = (c * 32 + lane < valid) && !(p.dbg_skip & 1);
+            const int cls      = clv[c] & (OWN_CONS - 1);
+            const uint32_t mym = __shfl_sync(0xffffffffu, keep[c], cls);
+            const int cbase    = __shfl_sync(0xffffffffu, run, cls);
+            if (ok) {
+              const uint32_t pos = static_cast<uint32_t>(cbase + __popc(mym & lt));
+              asm volatile("st.shared.b32 [%0], %1;" ::"r"(perm + pos * 4u),
+                           "r"((static_cast<uint32_t>(c * 32 + lane) << 16) | static_cast<uint32_t>(lbv[c])) : "memory");
+              if (HAS_W) asm volatile("st.shared.f32 [%0], %1;" ::"r"(wprm + pos * 4u), "f"(wv[c]) : "memory");
+            }
+            run += __popc(keep[c]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bars_u32 + B_READYL + s * 8);
+      }
+      if (++turn == OWN_NA) turn = 0;
+      if (++s == static_cast<uint32_t>(p.nl)) { s = 0; ph ^= 1u; }
+    }
+    if (prof && blockIdx.x == 1 && blockIdx.y == 0 && lane == 0)
+      printf("[upd v9 prof] analyst %d total %lld wait %lld\n", aw, clock64() - c_start, c_wait);
+  } else {
+    // ---------------- consumers ----------------
+    const int cw          = warp - 2 - OWN_NA;
+    const uint32_t coff   = static_cast<uint32_t>(lane) * (VEC * 4u);
+    const uint32_t tab_me = tab_u32 + coff;
+    uint32_t s = 0, ph = 0, sl = 0, phl = 0;
+    long long c_wait = 0, c_rows = 0;
+    const long long c_start = clock64();
+    for (int64_t t = t_begin; t < t_end; ++t) {
+      const long long c0 = prof ? clock64() : 0;
+      mbar_wait_park(bars_u32 + B_READYL + sl * 8, phl);
+      mbar_wait_park(bars_u32 + B_FULLX + s * 8, ph);
+      if (prof) c_wait += clock64() - c0;
+      const uint32_t xs   = base + s * x_bytes + coff;
+      const uint32_t perm = lbase + sl * l_bytes + lab_bytes;
+      const uint32_t wprm = perm + perm_bytes;
+      const uint32_t offs = wprm + perm_bytes;
+      const uint2 oo = lds64u(offs + (cw & ~1) * 4);
+      int j          = (cw & 1) ? static_cast<int>(oo.y) : static_cast<int>(oo.x);
+      const int o1   = (cw & 1) ? lds32(offs + cw * 4 + 4) : static_cast<int>(oo.y);
+      c_rows += o1 - j;
+      VecIO<VEC> x0, x1, tv;
+      // apply one row: table row of label (e & 0xffff) += w * x
+      auto apply = [&](uint32_t e, const VecIO<VEC>& x, float w, auto&& between) {
+        const uint32_t l  = e & 0xffffu;
+        const uint32_t ta = tab_me + l * ROWB;
+        tv.load(ta);
+        float cur = 0.0f;
+        if (HAS_W && counts) cur = __int_as_float(lds32(wtab_u32 + l * 4u));
+        between();
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) tv.v[q] = HAS_W ? fmaf(x.v[q], w, tv.v[q]) : tv.v[q] + x.v[q];
+        tv.store(ta);
+        if (HAS_W && counts)   // every lane writes the same value to the same word: no divergence, no atomics
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(wtab_u32 + l * 4u), "f"(cur + w) : "memory");
+      };
+      if (j < o1 && (j & 1)) {   // odd head so that the pair loop reads aligned entry pairs
+        const uint32_t e = static_cast<uint32_t>(lds32(perm + j * 4));
+        float w = 1.0f;
+        if (HAS_W) w = __int_as_float(lds32(wprm + j * 4));
+        x0.load(xs + (e >> 16) * ROWB);
+        apply(e, x0, w, [] {});
+        ++j;
+      }
+      if (j < o1) {
+        uint2 e = lds64u(perm + j * 4);
+        uint2 w = make_uint2(0x3f800000u, 0x3f800000u);
+        if (HAS_W) w = lds64u(wprm + j * 4);
+        x0.load(xs + (e.x >> 16) * ROWB);
+        for (; j < o1; j += 2) {
+          const uint2 en = lds64u(perm + j * 4 + 8);     // entries j+2, j+3 (past the end: stale, in range)
+          uint2 wn       = w;
+          if (HAS_W) wn = lds64u(wprm + j * 4 + 8);
+          apply(e.x, x0, __uint_as_float(w.x), [&] { x1.load(xs + (e.y >> 16) * ROWB); });
+          if (j + 1 < o1) apply(e.y, x1, __uint_as_float(w.y), [&] { x0.load(xs + (en.x >> 16) * ROWB); });
+          e = en;
+          w = wn;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(bars_u32 + B_EMPTYX + s * 8);
+        ptx::mbar_arrive(bars_u32 + B_EMPTYL + sl * 8);
+      }
+      if (++s == static_cast<uint32_t>(p.nstage)) { s = 0; ph ^= 1u; }
+      if (++sl == static_cast<uint32_t>(p.nl)) { sl = 0; phl ^= 1u; }
+    }
+    if (prof && blockIdx.x == 1 && blockIdx.y == 0 && lane == 0)
+      printf("[upd v9 prof] consumer %d tiles %lld rows %lld total %lld wait %lld\n", cw,
+             static_cast<long long>(t_end - t_begin), c_rows, clock64() - c_start, c_wait);
+  }
+  __syncthreads();
+  float* outS     = p.partial_S + static_cast<size_t>(blockIdx.x) * p.k * p.d;
+  const int wcols = min(DS, p.d - cs);
+  for (int i = threadIdx.x; i < p.k * DS; i += blockDim.x) {
+    const int j = i / DS, c = i % DS;
+    if (c < wcols) outS[static_cast<size_t>(j) * p.d + cs + c] = tab[i];
+  }
+  if (slice == 0) {
+    float* outW = p.partial_W + static_cast<size_t>(blockIdx.x) * p.k;
+    for (int i = threadIdx.x; i < p.k; i += blockDim.x)
+      outW[i] = HAS_W ? wtab[i] : static_cast<float>(reinterpret_cast<const int*>(wtab)[i]);
+  }
+}
+
 // packed[e] (+)= sum_b partial[b][e]: fixed order, fp64.  32 elements x 8 partial-lanes per block.
 __global__ void __launch_bounds__(256)
 reduce_partials_f32_kernel(const float* __restrict__ partial_S, const float* __restrict__ partial_W, int row_blocks,
@@ -610,6 +990,64 @@ static RowsPlan plan_rows_update(const Handle& h, int d, int k)
   return best;
 }
 
+struct OwnerPlan {
+  int vec = 0, tr = 0, nstage = 0, slices = 0, ncons = 16, nl = 0;
+  size_t smem = 0;
+};
+
+// label-class kernel: needs n_features >= 32 and the [k x 32*VEC] table plus >= 64 KB of ring in one SM
+static OwnerPlan plan_owner_update(const Handle& h, int d, int k)
+{
+  OwnerPlan best;
+  int mode = 1;
+  if (const char* e = std::getenv("CUML_B200_UPDATE_OWNER")) mode = std::atoi(e);
+  if (mode == 0 || d < 32 || d % 4 != 0 || k < 16) return best;
+  int force_vec = 0, force_tr = 0, force_nl = 0, force_ns = 0;
+  if (const char* e = std::getenv("CUML_B200_OWNER_VEC")) force_vec = std::atoi(e);
+  if (const char* e = std::getenv("CUML_B200_OWNER_TR")) force_tr = std::atoi(e);
+  if (const char* e = std::getenv("CUML_B200_OWNER_NL")) force_nl = std::atoi(e);
+  if (const char* e = std::getenv("CUML_B200_OWNER_NS")) force_ns = std::atoi(e);
+  const size_t budget = h.smem_optin - 512;
+  double best_score   = -1.0;
+  for (int vec = 4; vec >= 1; vec >>= 1) {
+    if (force_vec && vec != force_vec) continue;
+    const int ds = 32 * vec;
+    if (vec > 1 && ds > d) continue;   // do not read padding columns
+    const size_t table = (static_cast<size_t>(k) * ds + ((k + 3) & ~3)) * 4 + ((k + 15) & ~15) + (2 * MAX_NSTAGE + 3 * OWN_MAXNL) * 8 + 256;
+    if (table + 2 * 8192 > budget) continue;
+    const int slices = static_cast<int>(ceil_div(d, ds));
+    for (int tr = 64; tr <= 256; tr += 32) {
+      if (force_tr && tr != force_tr) continue;
+      const size_t stage = static_cast<size_t>(tr) * ds * 4;
+      for (int nl = OWN_MAXNL; nl >= 4; --nl) {
+        if (force_nl && nl != force_nl) continue;
+        const size_t lists = nl * (static_cast<size_t>(tr) * 12 + 384);   // label ring
+        if (table + lists + 2 * stage > budget) continue;
+        int nstage = static_cast<int>(std::min<size_t>(MAX_NSTAGE, (budget - table - lists) / stage));
+        nstage     = std::min(nstage, nl - 1);
+        if (force_ns) nstage = std::min(nstage, force_ns);
+        if (nstage < 2) continue;
+        const double inflight = static_cast<double>(nstage) * tr * ds * 4;
+        // measured on C3 / C2 (profiles/README.md): large tiles amortise the consumers' per-tile barrier
+        // round trips; two 64 KB stages beat four 32 KB ones once the analysts run ahead on the label ring
+        const double score = std::min(inflight, 64.0 * 1024) * (1.0 + 0.25 * vec) + 96.0 * tr + 16.0 * nl +
+                             (d % ds == 0 ? 4096.0 : 0.0);
+        if (score > best_score) {
+          best_score  = score;
+          best.vec    = vec;
+          best.tr     = tr;
+          best.nstage = nstage;
+          best.slices = slices;
+          best.smem   = table + lists + nstage * stage + 128;
+          best.nl     = nl;
+        }
+      }
+    }
+  }
+  best.ncons = OWN_CONS;
+  return best;
+}
+
 bool tma_update_supported(const Handle& h, int d, int k)
 {
   if (h.cc_major < 9 || d % 4 != 0) return false;
@@ -618,13 +1056,66 @@ bool tma_update_supported(const Handle& h, int d, int k)
 }
 
 // sums + weights of one partition into packed[0 .. k*d+k) (the inertia cell is left untouched)
+// label -> consumer-class map from the cluster weights of the previous iteration (work balance only: the sums do
+// not depend on it).  Returns null when the label-class kernel is not the one planned for (d, k).
+const uint8_t* tma_update_balance(Handle& h, const double* W, int d, int k, DevBuf<uint8_t>& map)
+{
+  if (plan_owner_update(h, d, k).vec == 0) return nullptr;
+  if (map.n < static_cast<size_t>(k)) map.alloc(k, h.stream);
+  balance_classes_kernel<<<1, 1024, static_cast<size_t>(k) * sizeof(float), h.stream>>>(W, k, map.get());
+  CB2_CHECK_LAUNCH();
+  return map.get();
+}
+
 void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const int32_t* labels_padded, const float* w,
                            int k, DevBuf<float>& partial_S, DevBuf<float>& partial_W, double* packed,
-                           bool accumulate_into)
+                           bool accumulate_into, const uint8_t* cls_map)
 {
   const int64_t total = static_cast<int64_t>(k) * d + k;
   if (n == 0) {
     if (!accumulate_into) CB2_CUDA(cudaMemsetAsync(packed, 0, total * sizeof(double), h.stream));
+    return;
+  }
+  if (const OwnerPlan op = plan_owner_update(h, d, k); op.vec > 0) {
+    UpdParams7 q{};
+    q.n = n; q.d = d; q.k = k; q.tr = op.tr; q.nstage = op.nstage; q.ncons = op.ncons; q.nl = op.nl;
+    q.cls_map = cls_map;
+    {
+      const char* e = std::getenv("CUML_B200_UPD_SKIP");
+      q.dbg_skip    = e ? std::atoi(e) : 0;
+      if (std::getenv("CUML_B200_UPD_PLAN"))
+        std::printf("[cuml_b200 update plan owner] vec %d tr %d nstage %d nl %d slices %d smem %zu\n", op.vec, op.tr,
+                    op.nstage, op.nl, op.slices, op.smem);
+    }
+    q.tiles_total = ceil_div(n, op.tr);
+    int64_t rb = std::max<int64_t>(1, static_cast<int64_t>(h.sm_count) / op.slices);
+    rb         = std::min<int64_t>(rb, q.tiles_total);
+    rb         = std::min<int64_t>(rb, std::max<int64_t>(1, n / (16 * static_cast<int64_t>(k)) + 1));
+    q.tiles_per_block = ceil_div(q.tiles_total, rb);
+    rb                = ceil_div(q.tiles_total, q.tiles_per_block);
+    if (partial_S.n < static_cast<size_t>(rb) * k * d) partial_S.alloc(static_cast<size_t>(rb) * k * d, h.stream);
+    if (partial_W.n < static_cast<size_t>(rb) * k) partial_W.alloc(static_cast<size_t>(rb) * k, h.stream);
+    q.labels = labels_padded; q.w = w; q.partial_S = partial_S.get(); q.partial_W = partial_W.get();
+    CUtensorMap tm = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
+                                 static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(32 * op.vec),
+                                 static_cast<uint32_t>(op.tr), CU_TENSOR_MAP_SWIZZLE_NONE,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    dim3 grid(static_cast<unsigned>(rb), static_cast<unsigned>(op.slices));
+    const unsigned threads = (2 + OWN_NA + OWN_CONS) * 32;
+    auto launch = [&](auto kern) {
+      CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
+      kern<<<grid, threads, op.smem, h.stream>>>(tm, q);
+    };
+    const bool hw = w != nullptr;
+    switch (op.vec) {
+      case 4: hw ? launch(accumulate_owner_kernel<4, true>) : launch(accumulate_owner_kernel<4, false>); break;
+      case 2: hw ? launch(accumulate_owner_kernel<2, true>) : launch(accumulate_owner_kernel<2, false>); break;
+      default: hw ? launch(accumulate_owner_kernel<1, true>) : launch(accumulate_owner_kernel<1, false>); break;
+    }
+    CB2_CHECK_LAUNCH();
+    reduce_partials_f32_kernel<<<static_cast<unsigned>(ceil_div(total, 32)), 256, 0, h.stream>>>(
+      partial_S.get(), partial_W.get(), static_cast<int>(rb), k, d, packed, accumulate_into ? 1 : 0);
+    CB2_CHECK_LAUNCH();
     return;
   }
   if (const RowsPlan rp = plan_rows_update(h, d, k); rp.ds > 0) {

@@ -57,7 +57,8 @@ void compute_inertia(Handle& h, const T* X, int64_t n, int d, const int32_t* lab
 bool tma_update_supported(const Handle& h, int d, int k);
 void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const int32_t* labels_padded, const float* w,
                            int k, DevBuf<float>& partial_S, DevBuf<float>& partial_W, double* packed,
-                           bool accumulate_into);
+                           bool accumulate_into, const uint8_t* cls_map = nullptr);
+const uint8_t* tma_update_balance(Handle& h, const double* W, int d, int k, DevBuf<uint8_t>& map);
 // C_new = S/W (W>0) else C_old; shift2 = sum (C_new-C_old)^2 (deterministic, one block)
 template <typename T>
 void finalize_centroids(Handle& h, const double* packed, T* C, int k, int d, double* shift2_out);

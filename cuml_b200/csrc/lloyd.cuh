@@ -121,9 +121,14 @@ class LloydSolver {
     bool need_separate_inertia = with_inertia;
     if (use_tma_update_) {
       if constexpr (std::is_same<T, float>::value) {
+        // consumer classes balanced by the cluster weights the previous accumulate left in packed
+        const uint8_t* cls_map = nullptr;
+        if (have_weights_ && !parts_.empty())
+          cls_map = tma_update_balance(h_, packed_.get() + static_cast<size_t>(k_) * d_, d_, k_, cls_map_);
         for (size_t i = 0; i < parts_.size(); ++i)
           tma_update_accumulate(h_, parts_[i].X, parts_[i].n, d_, labels(i), parts_[i].w, k_, tma_S_, tma_W_,
-                                packed_.get(), i != 0);
+                                packed_.get(), i != 0, cls_map);
+        have_weights_ = true;
       }
       if (!with_inertia) CB2_CUDA(cudaMemsetAsync(inertia_cell, 0, sizeof(double), h_.stream));
     } else {
@@ -192,6 +197,8 @@ class LloydSolver {
   bool use_tma_update_ = false;
   std::vector<int64_t> label_off_;
   DevBuf<float> tma_S_, tma_W_;
+  DevBuf<uint8_t> cls_map_;
+  bool have_weights_ = false;
   DevBuf<int32_t> labels_;
   DevBuf<T> cnorm_;
   DevBuf<double> packed_;
