@@ -97,6 +97,7 @@ struct DevBuf {
   T* p           = nullptr;
   size_t n       = 0;
   cudaStream_t s = nullptr;
+  bool direct    = false;   // cudaMalloc / cudaFree instead of the stream-ordered pool
   DevBuf() = default;
   DevBuf(size_t n_, cudaStream_t s_) { alloc(n_, s_); }
   void alloc(size_t n_, cudaStream_t s_)
@@ -104,11 +105,24 @@ struct DevBuf {
     release();
     n = n_;
     s = s_;
-    if (n) { CB2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), n * sizeof(T), s)); }
+    // Staging-sized buffers bypass the stream-ordered pool: growing and trimming the pool by tens of GB costs
+    // hundreds of milliseconds per fit (measured: tools/e2e_probe.py), a plain cudaMalloc a few.
+    direct = n * sizeof(T) >= (size_t(1) << 30);
+    if (n) {
+      if (direct) CB2_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), n * sizeof(T)));
+      else CB2_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&p), n * sizeof(T), s));
+    }
   }
   void release()
   {
-    if (p) cudaFreeAsync(p, s);
+    if (p) {
+      if (direct) {
+        cudaStreamSynchronize(s);   // work queued on the owning stream may still use the buffer
+        cudaFree(p);
+      } else {
+        cudaFreeAsync(p, s);
+      }
+    }
     p = nullptr;
     n = 0;
   }
@@ -120,7 +134,7 @@ struct DevBuf {
   {
     if (this != &o) {
       release();
-      p = o.p; n = o.n; s = o.s;
+      p = o.p; n = o.n; s = o.s; direct = o.direct;
       o.p = nullptr; o.n = 0;
     }
     return *this;

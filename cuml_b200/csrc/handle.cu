@@ -162,6 +162,19 @@ Handle* make_handle(void* stream, void* comm, int rank, int n_ranks)
   h->comm    = comm;
   h->rank    = rank;
   h->n_ranks = n_ranks < 1 ? 1 : n_ranks;
+  {
+    // keep up to 2 GB of freed work buffers (labels, partial tables) cached in the stream-ordered pool between
+    // calls instead of returning them to the driver at every synchronisation
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess && pool) {
+      uint64_t thr = 0;
+      if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr) == cudaSuccess && thr < (uint64_t(1) << 31)) {
+        thr = uint64_t(1) << 31;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+      }
+    }
+    cudaGetLastError();
+  }
   CB2_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->pinned), 64 * sizeof(double)));
   return h.release();
 }

@@ -5,6 +5,7 @@
 // overload (kmeans_fit.cu:23-99,237-318), predict (kmeans_predict.cu:19-135) and transform
 // (kmeans_transform.cu:18-78).  Everything below those shims -- which in the reference is the
 // un-vendored cuVS -- is this library's own CUDA code.
+#include <chrono>
 #include <limits>
 
 #include "lloyd.cuh"
@@ -131,8 +132,18 @@ void fit_parts_impl(Handle& h, const cuml_b200_kmeans_params_t& params, const T*
   const int k  = params.n_clusters;
   const int di = static_cast<int>(d);
 
+  // CUML_B200_TRACE=1: host-timed phases (adds stream synchronisations; measurement aid only)
+  static const bool trace = std::getenv("CUML_B200_TRACE") != nullptr;
+  auto tnow = [&] {
+    if (trace) cudaStreamSynchronize(h.stream);
+    return std::chrono::steady_clock::now();
+  };
+  auto tms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+  const auto t_0 = tnow();
   Staged<T> st;
   stage_parts<T>(h, X_parts, n_parts_rows, n_parts, d, w_parts, st);
+  const auto t_1 = tnow();
+  if (trace) std::printf("[cuml_b200 trace] stage_parts %.1f ms\n", tms(t_0, t_1));
   int64_t n_local = 0;
   for (auto& p : st.parts) n_local += p.n;
   const int64_t n_global = allreduce_i64_host(h, n_local);
@@ -176,10 +187,16 @@ void fit_parts_impl(Handle& h, const cuml_b200_kmeans_params_t& params, const T*
     } else {
       init_scalable<T>(sctx, params, C);
     }
+    const auto t_2 = tnow();
     const int64_t iters = solver.run(C, params.max_iter, params.tol);
+    const auto t_3 = tnow();
     // final E-step + cost with the final centroids
     solver.assign(C);
     const double inertia = solver.inertia(C) * wscale;
+    const auto t_4 = tnow();
+    if (trace)
+      std::printf("[cuml_b200 trace] setup+init %.1f ms, %lld Lloyd iterations %.1f ms, final assign+inertia %.1f ms\n",
+                  tms(t_1, t_2), static_cast<long long>(iters), tms(t_2, t_3), tms(t_3, t_4));
     if (inertia < best_inertia || run == 0) {
       best_inertia = inertia;
       best_iter    = iters;

@@ -76,17 +76,45 @@ def test_regime2_step_matches_oracle(env, engine):
     assert agree >= 0.9999 and bad == 0
 
 
-def test_weighted_step(env):
+@pytest.mark.parametrize("n,d,k", [(6000, 24, 11), (5000, 64, 40), (4001, 32, 16), (3000, 160, 300), (7000, 96, 130)])
+def test_weighted_step(env, n, d, k):
     from oracle import blobs, lloyd
-    X, centres, _ = blobs.make_blobs(6000, 24, 11)
+    X, centres, _ = blobs.make_blobs(n, d, k)
     init = blobs.parity_init(centres)
-    w = np.random.default_rng(5).uniform(0.25, 4.0, 6000).astype(np.float32)
-    lab, packed, C_new, _ = _step(env, X, init, 11, 0, w=w)
+    w = np.random.default_rng(5).uniform(0.25, 4.0, n).astype(np.float32)
+    lab, packed, C_new, _ = _step(env, X, init, k, 0, w=w)
     _, S, W, C_o, inertia, _ = lloyd.lloyd_step(X, init, w)
-    k, d = 11, 24
     assert np.abs(packed[:k * d].reshape(k, d) - S).max() / np.abs(S).max() < 1e-5
     assert np.abs(packed[k * d:k * d + k] - W).max() / W.max() < 1e-5
     assert abs(packed[-1] - inertia) / inertia < 1e-6
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_skewed_cluster_sizes_two_steps(env, weighted):
+    # 90 % of the rows in one cluster, the rest spread thin: long same-label runs and empty classes in the
+    # M-step; the second step runs with the size-balanced class map of the first
+    from oracle import lloyd
+    rng = np.random.default_rng(11)
+    n, d, k = 20000, 64, 24
+    centres = (rng.standard_normal((k, d)) * 10).astype(np.float32)
+    which = np.where(rng.random(n) < 0.9, 3, rng.integers(0, k, n))
+    X = (centres[which] + rng.standard_normal((n, d)).astype(np.float32)).astype(np.float32)
+    w = rng.uniform(0.5, 2.0, n).astype(np.float32) if weighted else None
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    Xd = torch.from_numpy(X).cuda()
+    Cd = torch.from_numpy(centres.copy()).cuda()
+    wd = torch.from_numpy(w).cuda() if weighted else None
+    packed = torch.zeros(k * d + k + 1, dtype=torch.float64, device="cuda")
+    C_o = centres.astype(np.float64)
+    for _ in range(2):
+        _lib.check(lib.cuml_b200_kmeans_lloyd_step_f32(h.ptr, Xd.data_ptr(), n, d, wd.data_ptr() if weighted else None,
+                                                       k, Cd.data_ptr(), None, packed.data_ptr(), None, 0))
+        h.sync()
+        _, S, W, C_o, _, _ = lloyd.lloyd_step(X, C_o.astype(np.float32), w)
+        got = packed.cpu().numpy()
+        assert np.abs(got[:k * d].reshape(k, d) - S).max() / np.abs(S).max() < 1e-5
+        assert np.abs(got[k * d:k * d + k] - W).max() / W.max() < 1e-5
+        assert np.abs(Cd.cpu().numpy() - C_o).max() / np.abs(C_o).max() < 1e-5
 
 
 def test_tensor_core_dot_accuracy(env):
