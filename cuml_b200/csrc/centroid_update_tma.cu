@@ -81,25 +81,6 @@ __device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity)
   }
 }
 
-// wait that lets the hardware park the warp (suspend-time hint) instead of burning issue slots on polling
-__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity)
-{
-  uint32_t ok = 0, spins = 0;
-  do {
-    asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(20000u)
-      : "memory");
-    if (!ok && ++spins > (1u << 22)) {
-      printf("cuml_b200: update-kernel mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
-    }
-  } while (!ok);
-}
-
 // NC = 16-byte chunks per sub-slice row: 8 (128B-swizzled, ds >= 32), 4 (64B), 2 (32B) or 1 (dense).
 // Warp roles: 0 = TMA producer, 1..na = analysts (round-robin over tiles), then the consumers.  Lane = row: one warp instruction
 // covers 32 consecutive rows.  The analyst computes, once per 32-row group, each row's rank among
@@ -636,7 +617,7 @@ accumulate_owner_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParam
     // ---------------- X producer ----------------
     uint32_t s = 0, ph = 0;
     for (int64_t t = t_begin; t < t_end; ++t) {
-      mbar_wait_park(bars_u32 + B_EMPTYX + s * 8, ph ^ 1u);
+      ptx::mbar_wait_park(bars_u32 + B_EMPTYX + s * 8, ph ^ 1u);
       if (ptx::elect_one()) {
         const uint32_t full = bars_u32 + B_FULLX + s * 8;
         ptx::mbar_arrive_expect_tx(full, x_bytes);
@@ -649,7 +630,7 @@ accumulate_owner_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParam
     // ---------------- label producer ----------------
     uint32_t s = 0, ph = 0;
     for (int64_t t = t_begin; t < t_end; ++t) {
-      mbar_wait_park(bars_u32 + B_EMPTYL + s * 8, ph ^ 1u);
+      ptx::mbar_wait_park(bars_u32 + B_EMPTYL + s * 8, ph ^ 1u);
       if (ptx::elect_one()) {
         const uint32_t full = bars_u32 + B_FULLL + s * 8;
         ptx::mbar_arrive_expect_tx(full, lab_bytes);
@@ -673,7 +654,7 @@ accumulate_owner_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParam
     for (int64_t t = t_begin; t < t_end; ++t) {
       if (turn == aw) {
         const long long c0 = prof ? clock64() : 0;
-        mbar_wait_park(bars_u32 + B_FULLL + s * 8, ph);
+        ptx::mbar_wait_park(bars_u32 + B_FULLL + s * 8, ph);
         if (prof) c_wait += clock64() - c0;
         const uint32_t ls   = lbase + s * l_bytes;
         const uint32_t perm = ls + lab_bytes;
@@ -756,8 +737,8 @@ accumulate_owner_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParam
     const long long c_start = clock64();
     for (int64_t t = t_begin; t < t_end; ++t) {
       const long long c0 = prof ? clock64() : 0;
-      mbar_wait_park(bars_u32 + B_READYL + sl * 8, phl);
-      mbar_wait_park(bars_u32 + B_FULLX + s * 8, ph);
+      ptx::mbar_wait_park(bars_u32 + B_READYL + sl * 8, phl);
+      ptx::mbar_wait_park(bars_u32 + B_FULLX + s * 8, ph);
       if (prof) c_wait += clock64() - c0;
       const uint32_t xs   = base + s * x_bytes + coff;
       const uint32_t perm = lbase + sl * l_bytes + lab_bytes;

@@ -17,6 +17,8 @@
 //                            (min, argmin) per row in registers, coalesced label store
 // Pipelines are mbarrier rings: A raw->ready->empty, B full/empty, and two TMEM accumulators
 // (full/empty) so the argmin of N-tile t overlaps the MMAs of N-tile t+1.
+#include <cuda_bf16.h>
+
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -32,10 +34,10 @@ namespace {
   do {                                              \
     if (p.dbg_clk) {                                \
       const long long t__ = clock64();              \
-      ptx::mbar_wait((bar), (parity));              \
+      ptx::mbar_wait_park((bar), (parity));         \
       (acc) += clock64() - t__;                     \
     } else {                                        \
-      ptx::mbar_wait((bar), (parity));              \
+      ptx::mbar_wait_park((bar), (parity));         \
     }                                               \
   } while (0)
 
@@ -43,6 +45,7 @@ constexpr int TILE_M       = 128;
 constexpr int KBLOCK       = 32;              // fp32 elements per 128-byte swizzle row
 constexpr int KBLOCK_BYTES = TILE_M * 128;    // one K-block of an A tile: 16 KB
 constexpr int NUM_THREADS  = 768;             // 24 warps: producers, MMA issuer, 4 converter, 16 epilogue
+constexpr int PAIR_THREADS = 896;             // CTA-pair kernel: 4 more converter warps (24..27)
 constexpr int EPI_THREADS  = 512;             // 16 epilogue warps: 4 TMEM lane quarters x 4 column parts
 constexpr int MAX_STAGES   = 4;
 constexpr int MAX_A_SLOTS  = 8;
@@ -93,6 +96,7 @@ struct FusedParams {
   float* dbg_dots;   // optional [n, k_pad] dump of the x.c accumulators (tests only)
   long long* dbg_clk; // optional [16]: per-role (wait cycles, total cycles) of CTA 0 (env CUML_B200_DBG_CLK)
   int dbg_skip;      // profiling knob (env CUML_B200_DBG_SKIP): 1 = no hi/lo split, 2 = no MMA, 4 = no argmin
+  int l2_ahead;      // CTA-pair kernel: row tiles prefetched into L2 ahead of the shared-memory ring
 };
 
 struct Barriers {
@@ -152,7 +156,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
         fetch_cn(nt + 1 == p.k_tiles ? 0 : nt + 1);
         ptx::named_bar_sync(1, EPI_THREADS);
       }
-      ptx::mbar_wait(ptx::smem_u32(&bars->acc_full[acc]), pacc);
+      ptx::mbar_wait_park(ptx::smem_u32(&bars->acc_full[acc]), pacc);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.bn;
       const int jbase      = nt * p.bn;
@@ -423,7 +427,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
       }
       if (p.dbg_clk && blockIdx.x == 0 && lane == 0) {
         p.dbg_clk[4] = wacc; p.dbg_clk[5] = wa; p.dbg_clk[6] = wb; p.dbg_clk[7] = clock64() - tstart;
-        p.dbg_clk[10] = tissue; p.dbg_clk[11] = tcommit;
+        (void)tissue; (void)tcommit;
       }
     }
   } else if (warp >= 8) {
@@ -448,9 +452,16 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
 // (the limiter of the single-CTA kernel at d=64, k=256).  Same pipelines as above; barriers that gate
 // the MMA issuer live in the leader and are arrived on remotely, barriers released by MMA completion
 // are signalled in both CTAs with a multicast tcgen05.commit.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+// BF16C: the two correction terms x_lo.c_hi and x_hi.c_lo are computed with bf16 operands (kind::f16, K = 16:
+// half the MMA instructions of a tf32 term).  hi is then the round-to-nearest tf32 of x, so |lo| <= 2^-12 |x|, and
+// rounding lo and hi to bf16 perturbs each correction by <= 2^-9 relative: ~2^-20 |x||c| per product -- the size of
+// the lo.lo term every 3xTF32 scheme drops.  Operand slot layout per 32-feature K-block:
+//   [0, 16 KB) hi tf32, 128B swizzle | [16 KB, 24 KB) hi bf16, 64B swizzle | [24 KB, 32 KB) lo bf16, 64B swizzle
+template <bool BF16C>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
-                            const __grid_constant__ CUtensorMap tm_lo, const FusedParams p)
+                            const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_lb,
+                            const FusedParams p)
 {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t raw_base = ptx::smem_u32(smem_dyn);
@@ -479,7 +490,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_A_SLOTS; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->a_raw_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->a_ready[s]), 8);     // 4 converter warps x 2 CTAs (leader's copy is used)
+      ptx::mbar_init(ptx::smem_u32(&bars->a_ready[s]), 16);    // 8 converter warps x 2 CTAs (leader's copy is used)
       ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), 1);
     }
     for (int s = 0; s < MAX_ACC; ++s) {
@@ -516,11 +527,21 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
       const int a_reps = p.a_stream ? p.k_tiles : 1;
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
         const int32_t row0 = static_cast<int32_t>(pt * 2 * TILE_M + cta_rank * TILE_M);
+        // L2 prefetch of the row tile p.l2_ahead rounds ahead: the shared-memory ring only holds ~2 row tiles, too
+        // few to cover the ~1.5 us HBM latency; with the tile already in L2 the ring turns around in time
+        if (p.l2_ahead > 0) {
+          const int64_t pf = pt + static_cast<int64_t>(p.l2_ahead) * n_pairs;
+          if (pf < pair_tiles && ptx::elect_one()) {
+            const int32_t prow = static_cast<int32_t>(pf * 2 * TILE_M + cta_rank * TILE_M);
+            for (int kbi = 0; kbi < p.kb; ++kbi) ptx::tma_prefetch_l2_2d(&tm_x, kbi * KBLOCK, prow);
+          }
+          __syncwarp();
+        }
         for (int rep = 0; rep < a_reps; ++rep)
         for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
           const uint32_t sa = ra.slot, pa = ra.phase;
           ra.advance(p.a_slots);
-          ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[sa]), pa ^ 1u);
+          ptx::mbar_wait_park(ptx::smem_u32(&bars->a_empty[sa]), pa ^ 1u);
           if (ptx::elect_one()) {
             const uint32_t full = ptx::smem_u32(&bars->a_raw_full[sa]);
             ptx::mbar_arrive_expect_tx(full, KBLOCK_BYTES);
@@ -541,7 +562,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sb = rb.slot, pb = rb.phase;
             rb.advance(p.b_stages);
-            ptx::mbar_wait(ptx::smem_u32(&bars->b_empty[sb]), pb ^ 1u);
+            ptx::mbar_wait_park(ptx::smem_u32(&bars->b_empty[sb]), pb ^ 1u);
             if (ptx::elect_one()) {
               const uint32_t full_local  = ptx::smem_u32(&bars->b_full[sb]);
               const uint32_t full_leader = ptx::mapa(full_local, 0);
@@ -549,16 +570,22 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
               const uint32_t dst = b_base + sb * b_stage_bytes;
               const int32_t crow = nt * p.bn + static_cast<int32_t>(cta_rank) * half_n;
               ptx::tma_load_2d_2cta(dst, &tm_hi, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
-              ptx::tma_load_2d_2cta(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+              if (BF16C) {   // tm_lo = bf16 hi, tm_lb = bf16 lo: two half-size tiles
+                ptx::tma_load_2d_2cta(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+                ptx::tma_load_2d_2cta(dst + b_half_bytes + b_half_bytes / 2, &tm_lb, kbi * KBLOCK, crow, full_leader,
+                                      ptx::kEvictLast);
+              } else {
+                ptx::tma_load_2d_2cta(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+              }
             }
             __syncwarp();
           }
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== converter =====================
-    const int ct = threadIdx.x - 128;
+  } else if ((warp >= 4 && warp < 8) || warp >= 24) {
+    // ===================== converter (8 warps: 4..7 and 24..27) =====================
+    const int ct = warp >= 24 ? threadIdx.x - 768 + 128 : threadIdx.x - 128;   // 0..255
     uint32_t a_cnt = 0;
       Ring ra;
     const int a_reps = p.a_stream ? p.k_tiles : 1;
@@ -567,25 +594,53 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
       for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
         const uint32_t sa = ra.slot, pa = ra.phase;
         ra.advance(p.a_slots);
-        ptx::mbar_wait(ptx::smem_u32(&bars->a_raw_full[sa]), pa);
+        ptx::mbar_wait_park(ptx::smem_u32(&bars->a_raw_full[sa]), pa);
         uint4* hi = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES);
-        const int live_chunks = 2 * min(4, (p.d - kbi * KBLOCK + 7) / 8);
+        const int rem_f       = p.d - kbi * KBLOCK;
+        const int live_chunks = BF16C ? 4 * min(2, (rem_f + 15) / 16) : 2 * min(4, (rem_f + 7) / 8);
+        uint8_t* hb = gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES;                    // bf16 hi tile (8 KB)
+        uint8_t* lb = hb + KBLOCK_BYTES / 2;                                       // bf16 lo tile (8 KB)
+        constexpr int CPT = KBLOCK_BYTES / 16 / 256;   // 16-byte chunks per thread
+        // all loads first: the chunks are independent, one shared-memory latency instead of CPT
+        uint4 v[CPT];
 #pragma unroll
-        for (int i = 0; i < KBLOCK_BYTES / 16 / 128; ++i) {
-          const int e = ct + i * 128;
-          if (((e & 7) ^ ((e >> 3) & 7)) >= live_chunks) continue;
-          uint4 v = hi[e];
+        for (int i = 0; i < CPT; ++i) v[i] = hi[ct + i * 256];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) {
+          const int e  = ct + i * 256;
+          const int lc = (e & 7) ^ ((e >> 3) & 7);     // logical 16-byte chunk: features [4 lc, 4 lc + 4)
+          if (lc >= live_chunks) continue;
           uint4 h, l;
-          h.x = v.x & 0xffffe000u; h.y = v.y & 0xffffe000u; h.z = v.z & 0xffffe000u; h.w = v.w & 0xffffe000u;
-          l.x = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(h.x));
-          l.y = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(h.y));
-          l.z = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(h.z));
-          l.w = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(h.w));
+          if (BF16C) {   // round to nearest tf32
+            h.x = (v[i].x + 0x0fffu + ((v[i].x >> 13) & 1u)) & 0xffffe000u;
+            h.y = (v[i].y + 0x0fffu + ((v[i].y >> 13) & 1u)) & 0xffffe000u;
+            h.z = (v[i].z + 0x0fffu + ((v[i].z >> 13) & 1u)) & 0xffffe000u;
+            h.w = (v[i].w + 0x0fffu + ((v[i].w >> 13) & 1u)) & 0xffffe000u;
+          } else {
+            h.x = v[i].x & 0xffffe000u; h.y = v[i].y & 0xffffe000u; h.z = v[i].z & 0xffffe000u; h.w = v[i].w & 0xffffe000u;
+          }
+          l.x = __float_as_uint(__uint_as_float(v[i].x) - __uint_as_float(h.x));
+          l.y = __float_as_uint(__uint_as_float(v[i].y) - __uint_as_float(h.y));
+          l.z = __float_as_uint(__uint_as_float(v[i].z) - __uint_as_float(h.z));
+          l.w = __float_as_uint(__uint_as_float(v[i].w) - __uint_as_float(h.w));
           hi[e] = h;
-          lo[e] = l;
+          if (BF16C) {
+            // 4 features -> 8 bytes of the 64-byte bf16 row; 64B swizzle: 16-byte chunk ^= (row / 2) % 4
+            const int row      = e >> 3;
+            const uint32_t off = static_cast<uint32_t>(row) * 64u + ((static_cast<uint32_t>(lc >> 1) ^ ((row >> 1) & 3u)) << 4) +
+                                 (static_cast<uint32_t>(lc & 1) << 3);
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(__uint_as_float(h.x), __uint_as_float(h.y));
+            const __nv_bfloat162 h23 = __floats2bfloat162_rn(__uint_as_float(h.z), __uint_as_float(h.w));
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(__uint_as_float(l.x), __uint_as_float(l.y));
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(__uint_as_float(l.z), __uint_as_float(l.w));
+            *reinterpret_cast<uint2*>(hb + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            *reinterpret_cast<uint2*>(lb + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+          } else {
+            lo[e] = l;
+          }
         }
-        ptx::fence_proxy_async_all();   // generic-proxy writes -> visible to the pair's tensor cores
+        ptx::fence_proxy_async_smem();  // generic-proxy writes to this CTA's operand tiles -> async proxy (pair MMA)
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->a_ready[sa]), 0));
       }
@@ -593,7 +648,9 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   } else if (warp == 1) {
     // ===================== MMA issuer (pair leader only; warp-uniform loop, one elected lane issues) ====
     if (leader) {
-      const uint32_t idesc = ptx::umma_idesc_tf32(2 * TILE_M, p.bn);
+      const uint32_t idesc   = ptx::umma_idesc_tf32(2 * TILE_M, p.bn);
+      const uint32_t idesc16 = ptx::umma_idesc_bf16(2 * TILE_M, p.bn);
+      (void)idesc16;
       uint32_t b_cnt = 0, acc_cnt = 0;
       Ring ra_tile, ra_run, rb, racc;
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs, ra_tile.advance_by(p.kb, p.a_slots)) {
@@ -601,20 +658,20 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
           const uint32_t acc = racc.slot, pacc = racc.phase;
           racc.advance(p.n_acc);
           Ring ra = p.a_stream ? ra_run : ra_tile;
-          ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
+          ptx::mbar_wait_park(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
           const uint32_t d_tmem = tmem_base + acc * p.bn;
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sa = ra.slot, pa = ra.phase;
             ra.advance(p.a_slots);
-            if (nt == 0 || p.a_stream) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[sa]), pa);
+            if (nt == 0 || p.a_stream) ptx::mbar_wait_park(ptx::smem_u32(&bars->a_ready[sa]), pa);
             uint32_t sb = rb.slot;
             const uint32_t pb = rb.phase;
             rb.advance(p.b_stages);
             if (p.b_resident) {
               sb = nt * p.kb + kbi;
-              if (pt == pair) ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), 0u);
+              if (pt == pair) ptx::mbar_wait_park(ptx::smem_u32(&bars->b_full[sb]), 0u);
             } else {
-              ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), pb);
+              ptx::mbar_wait_park(ptx::smem_u32(&bars->b_full[sb]), pb);
             }
             ptx::tc_fence_after();
             const uint64_t da_hi = ptx::umma_desc_sw128(a_base + sa * A_SLOT_BYTES);
@@ -623,13 +680,35 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
             const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
             const int nks = min(4, (p.d - kbi * KBLOCK + 7) / 8);
             if (ptx::elect_one()) {
+              if (BF16C) {
+                // corrections first (bf16, K = 16), then the tf32 main term
+                const uint32_t a_hb = a_base + sa * A_SLOT_BYTES + KBLOCK_BYTES;
+                const uint32_t b_hb = b_base + sb * b_stage_bytes + b_half_bytes;
+                const uint64_t da_hb = ptx::umma_desc_sw64(a_hb), da_lb = ptx::umma_desc_sw64(a_hb + KBLOCK_BYTES / 2);
+                const uint64_t db_hb = ptx::umma_desc_sw64(b_hb), db_lb = ptx::umma_desc_sw64(b_hb + b_half_bytes / 2);
+                const int nk16 = (nks + 1) / 2;
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (ks >= nks) break;
-                const uint64_t adv = static_cast<uint64_t>(ks * 2);
-                ptx::mma_tf32_ss_2cta(d_tmem, da_lo + adv, db_hi + adv, idesc, (kbi | ks) != 0 ? 1u : 0u);
-                ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
-                ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+                for (int ks = 0; ks < 2; ++ks) {
+                  if (ks >= nk16 || (p.dbg_skip & 8)) break;
+                  const uint64_t adv = static_cast<uint64_t>(ks * 2);
+                  ptx::mma_f16_ss_2cta(d_tmem, da_lb + adv, db_hb + adv, idesc16, (kbi | ks) != 0 ? 1u : 0u);
+                  ptx::mma_f16_ss_2cta(d_tmem, da_hb + adv, db_lb + adv, idesc16, 1u);
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks >= nks || (p.dbg_skip & 16)) break;
+                  const uint64_t adv = static_cast<uint64_t>(ks * 2);
+                  ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+                }
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks >= nks) break;
+                  const uint64_t adv = static_cast<uint64_t>(ks * 2);
+                  ptx::mma_tf32_ss_2cta(d_tmem, da_lo + adv, db_hi + adv, idesc, (kbi | ks) != 0 ? 1u : 0u);
+                  ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+                  ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+                }
               }
               if (!p.b_resident) ptx::mma_commit_2cta(ptx::smem_u32(&bars->b_empty[sb]), 3);
               if (nt == p.k_tiles - 1 || p.a_stream) ptx::mma_commit_2cta(ptx::smem_u32(&bars->a_empty[sa]), 3);
@@ -642,7 +721,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
         }
       }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 24) {
     // ===================== epilogue (own 128 rows of the pair tile) =====================
     const int64_t n_mine = (pair_tiles > pair) ? (pair_tiles - pair + n_pairs - 1) / n_pairs : 0;
     epilogue_role<true>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, pair * 2 * TILE_M + cta_rank * TILE_M,
@@ -913,7 +992,8 @@ fused_l2_argmin_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
 
 // hi/lo split + half norms of the centroids into padded operand buffers
 __global__ void prepare_centroids_kernel(const float* __restrict__ C, int k, int d, int k_pad, int d_pad,
-                                         float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ cnh)
+                                         float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ cnh,
+                                         __nv_bfloat16* __restrict__ hb, __nv_bfloat16* __restrict__ lb)
 {
   const int j    = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -921,9 +1001,14 @@ __global__ void prepare_centroids_kernel(const float* __restrict__ C, int k, int
   double s = 0.0;
   for (int c = lane; c < d_pad; c += 32) {
     float v = (j < k && c < d) ? C[static_cast<int64_t>(j) * d + c] : 0.0f;
-    float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+    const uint32_t u = __float_as_uint(v);
+    float h = __uint_as_float(hb ? ((u + 0x0fffu + ((u >> 13) & 1u)) & 0xffffe000u) : (u & 0xffffe000u));
     hi[static_cast<int64_t>(j) * d_pad + c] = h;
     lo[static_cast<int64_t>(j) * d_pad + c] = v - h;
+    if (hb) {
+      hb[static_cast<int64_t>(j) * d_pad + c] = __float2bfloat16_rn(h);
+      lb[static_cast<int64_t>(j) * d_pad + c] = __float2bfloat16_rn(v - h);
+    }
     s += static_cast<double>(v) * static_cast<double>(v);
   }
 #pragma unroll
@@ -1048,6 +1133,13 @@ bool use_2cta(const Handle& h, int d, int k)
   return plan_tiles_2cta(d, k, h.smem_optin).bn > 0;
 }
 
+// bf16 correction terms in the CTA-pair kernel (default on; CUML_B200_BF16C=0 restores pure 3xTF32)
+bool use_bf16_corrections()
+{
+  const char* e = std::getenv("CUML_B200_BF16C");
+  return e ? std::atoi(e) != 0 : true;
+}
+
 // Plan for the A-in-TMEM kernel: BN <= 128, operand slots in TMEM, raw X ring + centroid stages in smem.
 struct TsPlan {
   int kb = 0, bn = 0, a_slots = 0, raw_slots = 0, b_stages = 0, b_resident = 0, n_acc = 0, pair = 0;
@@ -1151,8 +1243,15 @@ void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out)
     out.d_pad = d_pad;
   }
   out.block_n = t.bn;
+  out.bf16c   = (pair && use_bf16_corrections()) ? 1 : 0;
+  if (out.bf16c && out.hb.n < static_cast<size_t>(k_pad) * d_pad) {
+    out.hb.alloc(static_cast<size_t>(k_pad) * d_pad, h.stream);
+    out.lb.alloc(static_cast<size_t>(k_pad) * d_pad, h.stream);
+  }
   prepare_centroids_kernel<<<static_cast<unsigned>(ceil_div(k_pad, 8)), 256, 0, h.stream>>>(
-    C, k, d, k_pad, d_pad, out.hi.get(), out.lo.get(), out.cnh.get());
+    C, k, d, k_pad, d_pad, out.hi.get(), out.lo.get(), out.cnh.get(),
+    out.bf16c ? reinterpret_cast<__nv_bfloat16*>(out.hb.get()) : nullptr,
+    out.bf16c ? reinterpret_cast<__nv_bfloat16*>(out.lb.get()) : nullptr);
   CB2_CHECK_LAUNCH();
 }
 
@@ -1298,6 +1397,8 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   {
     const char* e = std::getenv("CUML_B200_DBG_SKIP");
     p.dbg_skip    = e ? std::atoi(e) : 0;
+    const char* a = std::getenv("CUML_B200_L2_AHEAD");
+    p.l2_ahead    = a ? std::atoi(a) : 3;
   }
   DevBuf<long long> clk;
   const bool want_clk = std::getenv("CUML_B200_DBG_CLK") != nullptr;
@@ -1320,7 +1421,9 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   if (!attr_set) {
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
-    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(h.smem_optin)));
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
     attr_set = true;
   }
@@ -1331,7 +1434,17 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     // one CTA pair per TPC; grid must be even (cluster dims 2x1x1 are compiled into the kernel)
     const int64_t pair_tiles = (p.m_tiles + 1) / 2;
     const unsigned grid = 2u * static_cast<unsigned>(std::min<int64_t>(pair_tiles, h.sm_count / 2));
-    fused_l2_argmin_2cta_kernel<<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+    if (cen.bf16c) {
+      CUtensorMap tm_hb = make_map_2d(cen.hb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
+                                      b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+      CUtensorMap tm_lb = make_map_2d(cen.lb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
+                                      b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+      fused_l2_argmin_2cta_kernel<true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, p);
+    } else {
+      fused_l2_argmin_2cta_kernel<false><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, p);
+    }
   } else {
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
     fused_l2_argmin_kernel<<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
@@ -1343,7 +1456,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     CB2_CUDA(cudaMemcpyAsync(hc, clk.get(), sizeof(hc), cudaMemcpyDeviceToHost, h.stream));
     CB2_CUDA(cudaStreamSynchronize(h.stream));
     std::printf("[cuml_b200 clk] tiles/CTA %lld | producer wait %lld / %lld | converter wait %lld / %lld | mma wait acc %lld a %lld b %lld / %lld | "
-                "epilogue wait %lld / %lld | mma issue %lld commit %lld (cycles, CTA 0)\n",
+                "epilogue wait %lld / %lld | epilogue hold %lld merge %lld (cycles, CTA 0)\n",
                 static_cast<long long>((p.m_tiles + grid_dbg - 1) / grid_dbg), hc[0], hc[1], hc[2], hc[3], hc[4], hc[5], hc[6], hc[7], hc[8], hc[9], hc[10], hc[11]);
   }
 }

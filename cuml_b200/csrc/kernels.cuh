@@ -22,6 +22,8 @@ void row_norms(Handle& h, const T* A, int64_t rows, int d, T* out);  // ||a_i||^
 bool tc_supported(int64_t d, int k);
 struct TcCentroids {           // per-iteration operand buffers (hi/lo split + half norms)
   DevBuf<float> hi, lo, cnh;
+  DevBuf<uint16_t> hb, lb;   // bf16 copies of hi / lo (correction terms of the CTA-pair kernel)
+  int bf16c = 0;             // hi is rounded to nearest tf32 and hb / lb are valid
   int k_pad = 0, d_pad = 0, block_n = 0;
   int pack = 1;   // rows of X packed side by side into one 128-byte operand row (2 when n_features <= 16)
   int k_sub = 0;  // centroid rows per packed group (k padded to 32/64/128) when pack == 2

@@ -56,6 +56,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
   }
 }
 
+// Wait that lets the hardware park the warp (suspend-time hint) instead of burning issue slots on polling;
+// bounded like mbar_wait (a protocol bug traps instead of hanging the GPU).
+__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity)
+{
+  uint32_t ok = 0, spins = 0;
+  do {
+    asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(20000u)
+      : "memory");
+    if (!ok && ++spins > (1u << 22)) {
+      printf("cuml_b200: mbarrier timeout (block %d,%d thread %d bar 0x%x)\n", blockIdx.x, blockIdx.y, threadIdx.x, bar);
+      __trap();
+    }
+  } while (!ok);
+}
+
 // ---------------------------------------------------------------- proxies / fences
 __device__ __forceinline__ void fence_proxy_async_smem()
 {
@@ -95,6 +115,13 @@ __device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const void* tmap,
     "[%2], %5;" ::"r"(dst),
     "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
     : "memory");
+}
+// bring a tensor tile into L2 only (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* tmap, int32_t c0, int32_t c1)
+{
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(tmap)),
+               "r"(c0), "r"(c1)
+               : "memory");
 }
 constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;  // CacheHintSm90::EVICT_FIRST
 constexpr uint64_t kEvictLast  = 0x14F0000000000000ull;  // CacheHintSm90::EVICT_LAST
@@ -243,6 +270,17 @@ __device__ __forceinline__ void mma_tf32_ss_2cta(uint32_t d_tmem, uint64_t a_des
     "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
     : "memory");
 }
+// same, 16-bit operands (kind::f16: fp16 / bf16 inputs, K = 16 per instruction), fp32 accumulate
+__device__ __forceinline__ void mma_f16_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate)
+{
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "setp.ne.b32 p, %4, 0;\n\t"
+    "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+    "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+    : "memory");
+}
 // arrive on the barrier at this offset in every CTA of `mask` once the issued MMAs have retired
 __device__ __forceinline__ void mma_commit_2cta(uint32_t bar, uint16_t mask)
 {
@@ -274,6 +312,22 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
+}
+// K-major operand tile with 64-byte rows (32 bf16), 64B swizzle: 8-row atoms of 512 bytes
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr)
+{
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+// instruction descriptor: fp32 accumulate, bf16 x bf16 (kind::f16), both operands K-major, shape M x N
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N)
+{
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 // instruction descriptor: fp32 accumulate, tf32 x tf32, both operands K-major, shape M x N
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t M, uint32_t N)

@@ -25,16 +25,17 @@ inline EncodeTiledFn encode_tiled_fn()
 }
 
 // 2-D fp32 row-major [rows, cols] tensor, box = [box_rows, box_cols]; out-of-bounds -> zeros
-inline CUtensorMap make_map_2d(const float* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
+inline CUtensorMap make_map_2d(const void* base, uint64_t cols, uint64_t rows, uint64_t row_stride_bytes,
                                uint32_t box_cols, uint32_t box_rows, CUtensorMapSwizzle swizzle,
-                               CUtensorMapL2promotion promo)
+                               CUtensorMapL2promotion promo,
+                               CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT32)
 {
   CUtensorMap m;
   cuuint64_t dims[2]    = {cols, rows};
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2]     = {box_cols, box_rows};
   cuuint32_t estr[2]    = {1, 1};
-  CUresult r = encode_tiled_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box,
+  CUresult r = encode_tiled_fn()(&m, dtype, 2, const_cast<void*>(base), dims, strides, box,
                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     throw Error(CUML_B200_CUDA_ERROR,

@@ -9,6 +9,8 @@
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ uint64_t desc_sw128(uint32_t a) {
   uint64_t d = 0; d |= (uint64_t)((a & 0x3FFFFu) >> 4); d |= (uint64_t)1 << 16; d |= (uint64_t)(1024 >> 4) << 32; d |= (uint64_t)1 << 46; d |= (uint64_t)2 << 61; return d; }
+__device__ __forceinline__ uint64_t desc_sw64(uint32_t a) {
+  uint64_t d = 0; d |= (uint64_t)((a & 0x3FFFFu) >> 4); d |= (uint64_t)1 << 16; d |= (uint64_t)(512 >> 4) << 32; d |= (uint64_t)1 << 46; d |= (uint64_t)4 << 61; return d; }
 __device__ __forceinline__ bool elect_one() { uint32_t p; asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(p)); return p != 0; }
 
 __global__ void __launch_bounds__(128, 1) k(int N, int nacc, int kind_bf16, int iters, long long* out, int ts)
@@ -25,12 +27,14 @@ __global__ void __launch_bounds__(128, 1) k(int N, int nacc, int kind_bf16, int 
   if (threadIdx.x < 32) {
     uint32_t idesc = (1u << 4) | ((kind_bf16 ? 1u : 2u) << 7) | ((kind_bf16 ? 1u : 2u) << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
     uint64_t da = desc_sw128(base), db = desc_sw128(base + 16384);
+    if (ts == 2) { da = desc_sw64(base); db = desc_sw64(base + 16384); }
     long long t0 = clock64();
     if (elect_one()) {
       for (int i = 0; i < iters; ++i) {
         uint32_t d = tm + (uint32_t)((i % nacc) * N);
         uint64_t adv = (uint64_t)((i & 3) * 2);
-        if (ts) {
+        if (ts == 2) adv = (uint64_t)((i & 1) * 2);
+        if (ts == 1) {
           // A operand from TMEM (columns 448.. hold garbage; timing only)
           uint32_t at = tm + 448 + (uint32_t)((i & 3) * 8);
           asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(at), "l"(db + adv), "r"(idesc), "r"(1u) : "memory");
@@ -62,6 +66,15 @@ int main()
     cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
     double cyc = (double)h / iters; int K = bf ? 16 : 8;
     printf("%s %4d %3d %4d %9.1f %10.1f\n", bf ? "bf16" : "tf32", N, nacc, grid, cyc, 2.0 * 128 * N * K / cyc * 1.9e9 * 148 / 1e12);
+  }
+  printf("bf16 with 64-byte swizzled operand rows (SW64)\n");
+  for (int N : {128, 256}) {
+    int iters = 4096; long long h = 0;
+    for (int rep = 0; rep < 2; ++rep) { k<<<148, 128, 50 * 1024>>>(N, 1, 1, iters, out, 2); cudaDeviceSynchronize(); }
+    cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) { printf("err %s\n", cudaGetErrorString(e)); return 1; }
+    cudaMemcpy(&h, out, 8, cudaMemcpyDeviceToHost);
+    double cyc = (double)h / iters;
+    printf("bf16-SW64 %4d %9.1f %10.1f\n", N, cyc, 2.0 * 128 * N * 16 / cyc * 1.9e9 * 148 / 1e12);
   }
   printf("TS mode (A in TMEM), tf32\n");
   for (int N : {64, 128, 256}) for (int nacc : {1}) {
