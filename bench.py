@@ -34,8 +34,8 @@ WORKLOADS = {
     "C5": (200_000_000, 16, 64, "KMeans fit n=200M d=16 k=64 fp32 row-sharded"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant (fused) kernel at the full
-# workload, from the committed `ncu --set full` captures (profiles/r01_ncu_full_c3.txt)
-TRAFFIC_NCU = {"C3": 25.601282e9 + 0.346264e9}
+# workload, from the committed `ncu --set full` captures (profiles/r01_ncu_full_c3.txt, r01_ncu_full_c2.txt)
+TRAFFIC_NCU = {"C3": 25.620909e9 + 0.402735e9, "C2": 5.127724e9 + 0.042767e9}
 METRIC = "kmeans_lloyd_iters_per_sec"
 UNIT = "Lloyd iter/s"
 
@@ -280,9 +280,13 @@ def run_ours(args):
         fused_bytes = 4.0 * n_local * d + 4.0 * n_local            # X read once + labels written
         tf_achieved = flop / (fused_ms * 1e-3) / 1e12 if fused_ms > 0 else None
         gb_achieved = fused_bytes / (fused_ms * 1e-3) / 1e9 if fused_ms > 0 else None
-        # fp32-equivalent tensor roofline: TF32 runs at half the bf16 rate and 3xTF32 issues 3 MMAs per
-        # product => peak(algorithmic 2nkd) = bf16_sustained / 2 / 3  
-        tf_peak = peaks["bf16_tflops_sustained"] / 2.0 / 3.0
+        # fp32-equivalent tensor roofline from the measured dense bf16 rate (MEASURED_PEAKS.json).  TF32 runs at half
+        # the bf16 rate.  3xTF32 issues 3 tf32 MMAs per algorithmic product: peak(2nkd) = bf16/2/3.  The CTA-pair
+        # kernel with bf16 correction terms issues 1 tf32 + 2 bf16 MMAs: time per product = 1/(bf16/2) + 2/bf16, so
+        # peak(2nkd) = bf16/4 (the denominator is larger, the fraction therefore lower, than under the 3xTF32 rule).
+        variant = int(lib.cuml_b200_kmeans_estep_variant(h.ptr, d, k))
+        mma_cost = 4.0 if variant == 3 else 6.0
+        tf_peak = peaks["bf16_tflops_sustained"] / mma_cost
         # which roofline binds the fused kernel: time at the tensor peak vs time at the HBM peak
         tensor_bound = (flop / (tf_peak * 1e12)) >= (fused_bytes / (peaks["hbm_gbs"] * 1e9))
         if tensor_bound:
@@ -291,21 +295,28 @@ def run_ours(args):
         else:
             roof = {"bound": "hbm", "achieved": gb_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": (gb_achieved / peaks["hbm_gbs"]) if gb_achieved else None}
+        variant_name = {0: "CUDA-core fp32", 1: "tcgen05 1-CTA 3xTF32", 2: "tcgen05 CTA-pair 3xTF32",
+                        3: "tcgen05 CTA-pair tf32 + 2 bf16 correction terms", 4: "tcgen05 A-in-TMEM 3xTF32"}[variant]
         roof.update({
             "traffic": TRAFFIC_NCU.get(args.workload) if world == 1 and not args.n else None,
-            "kernel": "fused_l2_argmin (tcgen05 3xTF32 distance+argmin)", "kernel_ms": fused_ms,
+            "kernel": f"fused_l2_argmin ({variant_name}: distance + argmin)", "kernel_ms": fused_ms,
             "algorithmic_flops_per_launch": flop, "algorithmic_bytes_per_launch": fused_bytes,
-            "algorithmic_tflops": tf_achieved, "issued_tf32_tflops": (3 * tf_achieved) if tf_achieved else None,
+            "algorithmic_tflops": tf_achieved,
+            "issued_mma_products_per_algorithmic": 3,
             "hbm_gbs_fused": gb_achieved,
-            "peak_note": f"{peaks['source']}: tensor peak = bf16_tflops_sustained/2 (tf32 rate) /3 (3xTF32); "
-                         f"hbm peak = hbm_gbs (copy)",
+            "peak_note": f"{peaks['source']}: tensor peak = bf16_tflops_sustained / {mma_cost:g} "
+                         f"({'1 tf32 + 2 bf16 MMAs' if variant == 3 else '3 tf32 MMAs'} per algorithmic product, "
+                         f"tf32 = bf16/2); hbm peak = hbm_gbs (copy)",
+            "update_kernel": "accumulate_owner (TMA ring, label-class ownership) + reduce_partials",
             "update_kernel_ms": update_ms,
             "update_kernel_hbm_gbs": 4.0 * n_local * (d + 1) / (update_ms * 1e-3) / 1e9 if update_ms > 0 else None,
+            "update_kernel_frac_of_hbm_peak": (4.0 * n_local * (d + 1) / (update_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
+                                              if update_ms > 0 else None,
             "hbm_peak_gbs": peaks["hbm_gbs"], "tensor_peak_tflops": tf_peak})
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32 (3xTF32 tensor-core contraction, fp32/fp64 reductions)",
+            "vs_baseline": None, "dtype": "f32 (split-precision tensor-core contraction: tf32 + bf16 corrections or 3xTF32; fp32/fp64 reductions)",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "n": n, "d": d, "k": k, "rows_per_gpu": n_local,
                        "parallelism": f"row-sharded x{world}, 1 allreduce of (k*d+k+1) f64 per iteration",

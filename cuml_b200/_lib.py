@@ -50,7 +50,7 @@ EXPORTED_SYMBOLS = [
     "cuml_b200_kmeans_transform_f32_i64", "cuml_b200_kmeans_transform_f64_i64",
     "cuml_b200_kmeans_lloyd_step_f32", "cuml_b200_kmeans_assign_f32", "cuml_b200_launch_count_reset",
     "cuml_b200_launch_count", "cuml_b200_kernel_timing_enable", "cuml_b200_kernel_timing_read",
-    "cuml_b200_kmeans_tc_supported", "cuml_b200_kmeans_debug_dots_f32",
+    "cuml_b200_kmeans_tc_supported", "cuml_b200_kmeans_debug_dots_f32", "cuml_b200_kmeans_estep_variant",
 ]
 
 
@@ -101,6 +101,7 @@ def load(build_if_missing=True):
     lib.cuml_b200_kernel_timing_enable.argtypes = [vp, C.c_int]
     lib.cuml_b200_kernel_timing_read.argtypes = [vp, P(dbl), P(i64), P(dbl), P(i64)]
     lib.cuml_b200_kmeans_tc_supported.argtypes = [i64, i32]
+    lib.cuml_b200_kmeans_estep_variant.argtypes = [vp, i64, i32]
     _LIB = lib
     return lib
 

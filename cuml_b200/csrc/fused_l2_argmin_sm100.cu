@@ -1203,6 +1203,14 @@ bool tc_supported(int64_t d, int k)
   return d >= 4 && d % 4 == 0 && d <= 1024 && k >= 1 && k <= (1 << 20);
 }
 
+int tc_variant(const Handle& h, int d, int k)
+{
+  if (pack_k_sub(d, k)) return 1;
+  if (use_ts(h, d, k)) return 4;
+  if (use_2cta(h, d, k)) return use_bf16_corrections() ? 3 : 2;
+  return 1;
+}
+
 void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out)
 {
   if (const int k_sub = pack_k_sub(d, k)) {

@@ -29,6 +29,7 @@ struct TcCentroids {           // per-iteration operand buffers (hi/lo split + h
   int k_sub = 0;  // centroid rows per packed group (k padded to 32/64/128) when pack == 2
 };
 void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out);
+int tc_variant(const Handle& h, int d, int k);   // 1 one-CTA 3xTF32, 2 pair 3xTF32, 3 pair tf32+bf16, 4 A-in-TMEM
 void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen,
                int32_t* labels, float* dbg_dots = nullptr);
 

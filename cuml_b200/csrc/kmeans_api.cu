@@ -517,4 +517,12 @@ int cuml_b200_kernel_timing_read(cuml_b200_handle_t* h, double* fused_ms, int64_
 
 int cuml_b200_kmeans_tc_supported(int64_t d, int32_t k) { return tc_supported(d, k) ? 1 : 0; }
 
+int cuml_b200_kmeans_estep_variant(cuml_b200_handle_t* h, int64_t d, int32_t k)
+{
+  if (!h || d <= 0 || d > std::numeric_limits<int>::max() || k <= 0) return 0;
+  Handle& hh = HANDLE(h);
+  if (hh.cc_major != 10 || !tc_supported(d, k)) return 0;
+  return tc_variant(hh, static_cast<int>(d), k);
+}
+
 }  // extern "C"
