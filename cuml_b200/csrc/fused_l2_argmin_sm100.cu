@@ -586,6 +586,12 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   } else if ((warp >= 4 && warp < 8) || warp >= 24) {
     // ===================== converter (8 warps: 4..7 and 24..27) =====================
     const int ct = warp >= 24 ? threadIdx.x - 768 + 128 : threadIdx.x - 128;   // 0..255
+    // this thread's chunks are ct + 256 i: 32 rows apart, so the logical chunk and the swizzle phases are fixed
+    const int conv_row       = ct >> 3;
+    const int conv_lc        = (ct & 7) ^ (conv_row & 7);     // logical 16-byte chunk: features [4 lc, 4 lc + 4)
+    const uint32_t conv_off  = static_cast<uint32_t>(conv_row) * 64u +
+                               ((static_cast<uint32_t>(conv_lc >> 1) ^ ((conv_row >> 1) & 3u)) << 4) +
+                               (static_cast<uint32_t>(conv_lc & 1) << 3);
     uint32_t a_cnt = 0;
       Ring ra;
     const int a_reps = p.a_stream ? p.k_tiles : 1;
@@ -606,38 +612,36 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
         uint4 v[CPT];
 #pragma unroll
         for (int i = 0; i < CPT; ++i) v[i] = hi[ct + i * 256];
+        if (conv_lc < live_chunks) {   // chunk ct + 256 i keeps the logical chunk and the swizzle phase of chunk ct
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) {
-          const int e  = ct + i * 256;
-          const int lc = (e & 7) ^ ((e >> 3) & 7);     // logical 16-byte chunk: features [4 lc, 4 lc + 4)
-          if (lc >= live_chunks) continue;
-          uint4 h, l;
-          if (BF16C) {   // round to nearest tf32
-            h.x = (v[i].x + 0x0fffu + ((v[i].x >> 13) & 1u)) & 0xffffe000u;
-            h.y = (v[i].y + 0x0fffu + ((v[i].y >> 13) & 1u)) & 0xffffe000u;
-            h.z = (v[i].z + 0x0fffu + ((v[i].z >> 13) & 1u)) & 0xffffe000u;
-            h.w = (v[i].w + 0x0fffu + ((v[i].w >> 13) & 1u)) & 0xffffe000u;
-          } else {
-            h.x = v[i].x & 0xffffe000u; h.y = v[i].y & 0xffffe000u; h.z = v[i].z & 0xffffe000u; h.w = v[i].w & 0xffffe000u;
-          }
-          l.x = __float_as_uint(__uint_as_float(v[i].x) - __uint_as_float(h.x));
-          l.y = __float_as_uint(__uint_as_float(v[i].y) - __uint_as_float(h.y));
-          l.z = __float_as_uint(__uint_as_float(v[i].z) - __uint_as_float(h.z));
-          l.w = __float_as_uint(__uint_as_float(v[i].w) - __uint_as_float(h.w));
-          hi[e] = h;
-          if (BF16C) {
-            // 4 features -> 8 bytes of the 64-byte bf16 row; 64B swizzle: 16-byte chunk ^= (row / 2) % 4
-            const int row      = e >> 3;
-            const uint32_t off = static_cast<uint32_t>(row) * 64u + ((static_cast<uint32_t>(lc >> 1) ^ ((row >> 1) & 3u)) << 4) +
-                                 (static_cast<uint32_t>(lc & 1) << 3);
-            const __nv_bfloat162 h01 = __floats2bfloat162_rn(__uint_as_float(h.x), __uint_as_float(h.y));
-            const __nv_bfloat162 h23 = __floats2bfloat162_rn(__uint_as_float(h.z), __uint_as_float(h.w));
-            const __nv_bfloat162 l01 = __floats2bfloat162_rn(__uint_as_float(l.x), __uint_as_float(l.y));
-            const __nv_bfloat162 l23 = __floats2bfloat162_rn(__uint_as_float(l.z), __uint_as_float(l.w));
-            *reinterpret_cast<uint2*>(hb + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
-            *reinterpret_cast<uint2*>(lb + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
-          } else {
-            lo[e] = l;
+          for (int i = 0; i < CPT; ++i) {
+            const int e = ct + i * 256;
+            uint4 h, l;
+            if (BF16C) {   // nearest tf32 (ties away from zero): |lo| <= 2^-12 |x|
+              h.x = (v[i].x + 0x1000u) & 0xffffe000u;
+              h.y = (v[i].y + 0x1000u) & 0xffffe000u;
+              h.z = (v[i].z + 0x1000u) & 0xffffe000u;
+              h.w = (v[i].w + 0x1000u) & 0xffffe000u;
+            } else {
+              h.x = v[i].x & 0xffffe000u; h.y = v[i].y & 0xffffe000u; h.z = v[i].z & 0xffffe000u; h.w = v[i].w & 0xffffe000u;
+            }
+            l.x = __float_as_uint(__uint_as_float(v[i].x) - __uint_as_float(h.x));
+            l.y = __float_as_uint(__uint_as_float(v[i].y) - __uint_as_float(h.y));
+            l.z = __float_as_uint(__uint_as_float(v[i].z) - __uint_as_float(h.z));
+            l.w = __float_as_uint(__uint_as_float(v[i].w) - __uint_as_float(h.w));
+            hi[e] = h;
+            if (BF16C) {
+              // 4 features -> 8 bytes of the 64-byte bf16 row (64B swizzle: 16-byte chunk ^= (row / 2) % 4)
+              const uint32_t off = conv_off + static_cast<uint32_t>(i) * (32u * 64u);
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(__uint_as_float(h.x), __uint_as_float(h.y));
+              const __nv_bfloat162 h23 = __floats2bfloat162_rn(__uint_as_float(h.z), __uint_as_float(h.w));
+              const __nv_bfloat162 l01 = __floats2bfloat162_rn(__uint_as_float(l.x), __uint_as_float(l.y));
+              const __nv_bfloat162 l23 = __floats2bfloat162_rn(__uint_as_float(l.z), __uint_as_float(l.w));
+              *reinterpret_cast<uint2*>(hb + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+              *reinterpret_cast<uint2*>(lb + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+            } else {
+              lo[e] = l;
+            }
           }
         }
         ptx::fence_proxy_async_smem();  // generic-proxy writes to this CTA's operand tiles -> async proxy (pair MMA)
@@ -1002,7 +1006,7 @@ __global__ void prepare_centroids_kernel(const float* __restrict__ C, int k, int
   for (int c = lane; c < d_pad; c += 32) {
     float v = (j < k && c < d) ? C[static_cast<int64_t>(j) * d + c] : 0.0f;
     const uint32_t u = __float_as_uint(v);
-    float h = __uint_as_float(hb ? ((u + 0x0fffu + ((u >> 13) & 1u)) & 0xffffe000u) : (u & 0xffffe000u));
+    float h = __uint_as_float(hb ? ((u + 0x1000u) & 0xffffe000u) : (u & 0xffffe000u));
     hi[static_cast<int64_t>(j) * d_pad + c] = h;
     lo[static_cast<int64_t>(j) * d_pad + c] = v - h;
     if (hb) {
