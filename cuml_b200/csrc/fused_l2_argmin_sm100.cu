@@ -97,6 +97,7 @@ struct FusedParams {
   long long* dbg_clk; // optional [16]: per-role (wait cycles, total cycles) of CTA 0 (env CUML_B200_DBG_CLK)
   int dbg_skip;      // profiling knob (env CUML_B200_DBG_SKIP): 1 = no hi/lo split, 2 = no MMA, 4 = no argmin
   int l2_ahead;      // CTA-pair kernel: row tiles prefetched into L2 ahead of the shared-memory ring
+  int fold;          // CTA-pair kernel: -1/2||c||^2 enters the accumulator through one extra K=8 MMA (ones x pieces)
 };
 
 struct Barriers {
@@ -104,6 +105,7 @@ struct Barriers {
   uint64_t b_full[MAX_STAGES], b_empty[MAX_STAGES];
   uint64_t acc_full[MAX_ACC], acc_empty[MAX_ACC];
   uint64_t raw_full[MAX_RAW], raw_empty[MAX_RAW];   // A-in-TMEM variant: raw X ring in shared memory
+  uint64_t cn_full;                                 // CTA-pair kernel: folded half-norm tiles have landed
   uint32_t tmem_base;
 };
 
@@ -139,8 +141,9 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
   // latency never sits on the epilogue's critical path
   float pre = 0.f;
   auto fetch_cn = [&](int nt) { pre = __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + (et < p.bn ? et : 0)); };
-  fetch_cn(0);
-  if (p.k_tiles == 1) {  // single centroid tile: stage the half norms once
+  const bool fold = PAIR && p.fold;   // accumulator already holds x.c - 1/2||c||^2: pick the maximum
+  if (!fold) fetch_cn(0);
+  if (p.k_tiles == 1 && !fold) {  // single centroid tile: stage the half norms once
     if (et < p.bn) cn_s[et] = pre;
     ptx::named_bar_sync(1, EPI_THREADS);
   }
@@ -151,7 +154,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
       const uint32_t acc = racc.slot, pacc = racc.phase;
       racc.advance(p.n_acc);
       float* cn = cn_s + ((p.k_tiles == 1) ? 0 : (acc_cnt & 1u) * p.bn);
-      if (p.k_tiles > 1) {
+      if (p.k_tiles > 1 && !fold) {
         if (et < p.bn) cn[et] = pre;
         fetch_cn(nt + 1 == p.k_tiles ? 0 : nt + 1);
         ptx::named_bar_sync(1, EPI_THREADS);
@@ -173,19 +176,34 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
             for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
           }
         }
-        const float4* cn4 = reinterpret_cast<const float4*>(cn + c0);
-        const int jb      = jbase + c0 - col0;
+        const int jb = jbase + c0 - col0;
+        if (fold) {
+          // b* hold the NEGATED score so that "smaller wins" and the chain merge below stay the same
 #pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4) {
-          const float4 c4 = cn4[q4];
-          const float v0 = c4.x - __uint_as_float(r[q4 * 4 + 0]);
-          const float v1 = c4.y - __uint_as_float(r[q4 * 4 + 1]);
-          const float v2 = c4.z - __uint_as_float(r[q4 * 4 + 2]);
-          const float v3 = c4.w - __uint_as_float(r[q4 * 4 + 3]);
-          if (v0 < b0) { b0 = v0; i0 = jb + q4 * 4 + 0; }
-          if (v1 < b1) { b1 = v1; i1 = jb + q4 * 4 + 1; }
-          if (v2 < b2) { b2 = v2; i2 = jb + q4 * 4 + 2; }
-          if (v3 < b3) { b3 = v3; i3 = jb + q4 * 4 + 3; }
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float v0 = -__uint_as_float(r[q4 * 4 + 0]);
+            const float v1 = -__uint_as_float(r[q4 * 4 + 1]);
+            const float v2 = -__uint_as_float(r[q4 * 4 + 2]);
+            const float v3 = -__uint_as_float(r[q4 * 4 + 3]);
+            if (v0 < b0) { b0 = v0; i0 = jb + q4 * 4 + 0; }
+            if (v1 < b1) { b1 = v1; i1 = jb + q4 * 4 + 1; }
+            if (v2 < b2) { b2 = v2; i2 = jb + q4 * 4 + 2; }
+            if (v3 < b3) { b3 = v3; i3 = jb + q4 * 4 + 3; }
+          }
+        } else {
+          const float4* cn4 = reinterpret_cast<const float4*>(cn + c0);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 c4 = cn4[q4];
+            const float v0 = c4.x - __uint_as_float(r[q4 * 4 + 0]);
+            const float v1 = c4.y - __uint_as_float(r[q4 * 4 + 1]);
+            const float v2 = c4.z - __uint_as_float(r[q4 * 4 + 2]);
+            const float v3 = c4.w - __uint_as_float(r[q4 * 4 + 3]);
+            if (v0 < b0) { b0 = v0; i0 = jb + q4 * 4 + 0; }
+            if (v1 < b1) { b1 = v1; i1 = jb + q4 * 4 + 1; }
+            if (v2 < b2) { b2 = v2; i2 = jb + q4 * 4 + 2; }
+            if (v3 < b3) { b3 = v3; i3 = jb + q4 * 4 + 3; }
+          }
         }
       }
       ptx::tc_fence_before();
@@ -461,7 +479,7 @@ template <bool BF16C>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                             const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_lb,
-                            const FusedParams p)
+                            const __grid_constant__ CUtensorMap tm_cn, const FusedParams p)
 {
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t raw_base = ptx::smem_u32(smem_dyn);
@@ -478,7 +496,12 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   const uint32_t b_stage_bytes = 2u * b_half_bytes;                     // hi then lo
   const uint32_t a_base  = base;
   const uint32_t b_base  = a_base + p.a_slots * A_SLOT_BYTES;
-  const uint32_t cn_off  = p.a_slots * A_SLOT_BYTES + p.b_stages * b_stage_bytes;
+  // fold tiles (p.fold): ones [128 rows x 8 tf32] then one [half_n rows x 8 tf32] tile of half-norm pieces per
+  // centroid tile, 32-byte rows, 4 KB each
+  constexpr uint32_t FOLD_TILE = TILE_M * 32u;
+  const uint32_t fold_off = p.a_slots * A_SLOT_BYTES + p.b_stages * b_stage_bytes;
+  const uint32_t fold_u32 = base + fold_off;
+  const uint32_t cn_off   = fold_off + (p.fold ? (1u + p.k_tiles) * FOLD_TILE : 0u);
   float* cn_s            = reinterpret_cast<float*>(gbase + cn_off);    // [2][bn]
   float* mrg_v           = cn_s + 2 * p.bn;                              // [128] epilogue half merge
   int* mrg_i             = reinterpret_cast<int*>(mrg_v + 3 * TILE_M);   // [3][128]
@@ -501,7 +524,13 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
       ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);      // leader's copy: expect_tx covers both CTAs
       ptx::mbar_init(ptx::smem_u32(&bars->b_empty[s]), 1);
     }
+    ptx::mbar_init(ptx::smem_u32(&bars->cn_full), 1);
     ptx::fence_barrier_init();
+  }
+  if (p.fold) {   // all-ones A tile (identical 16-byte chunks: the 32B swizzle does not matter)
+    float* ones = reinterpret_cast<float*>(gbase + fold_off);
+    for (int i = threadIdx.x; i < TILE_M * 8; i += blockDim.x) ones[i] = 1.0f;
+    ptx::fence_proxy_async_smem();
   }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_x);
@@ -556,6 +585,18 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     {
       uint32_t b_cnt = 0;
       Ring rb;
+      if (p.fold && pair < pair_tiles) {
+        // half-norm pieces of every centroid tile (this CTA's half of the rows), resident for the whole kernel
+        if (ptx::elect_one()) {
+          const uint32_t full_local  = ptx::smem_u32(&bars->cn_full);
+          const uint32_t full_leader = ptx::mapa(full_local, 0);
+          if (leader) ptx::mbar_arrive_expect_tx(full_local, 2u * p.k_tiles * FOLD_TILE);
+          for (int nt = 0; nt < p.k_tiles; ++nt)
+            ptx::tma_load_2d_2cta(fold_u32 + (1u + nt) * FOLD_TILE, &tm_cn, 0,
+                                  nt * p.bn + static_cast<int32_t>(cta_rank) * half_n, full_leader, ptx::kEvictLast);
+        }
+        __syncwarp();
+      }
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
         if (p.b_resident && pt != pair) break;
         for (int nt = 0; nt < p.k_tiles; ++nt) {
@@ -657,6 +698,8 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
       (void)idesc16;
       uint32_t b_cnt = 0, acc_cnt = 0;
       Ring ra_tile, ra_run, rb, racc;
+      if (p.fold && pair < pair_tiles) ptx::mbar_wait_park(ptx::smem_u32(&bars->cn_full), 0u);
+      const uint32_t first_acc = p.fold ? 1u : 0u;   // the fold MMA initialises the accumulator
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs, ra_tile.advance_by(p.kb, p.a_slots)) {
         for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
           const uint32_t acc = racc.slot, pacc = racc.phase;
@@ -664,6 +707,13 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
           Ring ra = p.a_stream ? ra_run : ra_tile;
           ptx::mbar_wait_park(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
           const uint32_t d_tmem = tmem_base + acc * p.bn;
+          if (p.fold) {
+            ptx::tc_fence_after();
+            if (ptx::elect_one())
+              ptx::mma_tf32_ss_2cta(d_tmem, ptx::umma_desc_sw32(fold_u32), ptx::umma_desc_sw32(fold_u32 + (1u + nt) * FOLD_TILE),
+                                    idesc, 0u);
+            __syncwarp();
+          }
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sa = ra.slot, pa = ra.phase;
             ra.advance(p.a_slots);
@@ -695,7 +745,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
                 for (int ks = 0; ks < 2; ++ks) {
                   if (ks >= nk16 || (p.dbg_skip & 8)) break;
                   const uint64_t adv = static_cast<uint64_t>(ks * 2);
-                  ptx::mma_f16_ss_2cta(d_tmem, da_lb + adv, db_hb + adv, idesc16, (kbi | ks) != 0 ? 1u : 0u);
+                  ptx::mma_f16_ss_2cta(d_tmem, da_lb + adv, db_hb + adv, idesc16, ((kbi | ks) != 0 ? 1u : 0u) | first_acc);
                   ptx::mma_f16_ss_2cta(d_tmem, da_hb + adv, db_lb + adv, idesc16, 1u);
                 }
 #pragma unroll
@@ -709,7 +759,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
                 for (int ks = 0; ks < 4; ++ks) {
                   if (ks >= nks) break;
                   const uint64_t adv = static_cast<uint64_t>(ks * 2);
-                  ptx::mma_tf32_ss_2cta(d_tmem, da_lo + adv, db_hi + adv, idesc, (kbi | ks) != 0 ? 1u : 0u);
+                  ptx::mma_tf32_ss_2cta(d_tmem, da_lo + adv, db_hi + adv, idesc, ((kbi | ks) != 0 ? 1u : 0u) | first_acc);
                   ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
                   ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
                 }
@@ -997,7 +1047,8 @@ fused_l2_argmin_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
 // hi/lo split + half norms of the centroids into padded operand buffers
 __global__ void prepare_centroids_kernel(const float* __restrict__ C, int k, int d, int k_pad, int d_pad,
                                          float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ cnh,
-                                         __nv_bfloat16* __restrict__ hb, __nv_bfloat16* __restrict__ lb)
+                                         __nv_bfloat16* __restrict__ hb, __nv_bfloat16* __restrict__ lb,
+                                         float* __restrict__ cnp)
 {
   const int j    = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -1018,6 +1069,15 @@ __global__ void prepare_centroids_kernel(const float* __restrict__ C, int k, int
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   if (lane == 0) cnh[j] = (j < k) ? static_cast<float>(0.5 * s) : __int_as_float(0x7f800000);
+  if (cnp && lane < 8) {
+    // -1/2||c||^2 as three pieces that are exact in tf32 (11 + 11 + 2 mantissa bits); padding rows can never win
+    const float m  = (j < k) ? -static_cast<float>(0.5 * s) : -3.0e38f;
+    const float p1 = __uint_as_float(__float_as_uint(m) & 0xffffe000u);
+    const float r1 = m - p1;
+    const float p2 = __uint_as_float(__float_as_uint(r1) & 0xffffe000u);
+    const float p3 = r1 - p2;
+    cnp[static_cast<int64_t>(j) * 8 + lane] = lane == 0 ? p1 : lane == 1 ? p2 : lane == 2 ? p3 : 0.0f;
+  }
 }
 
 // Row-packed operands for n_features <= 16: two consecutive rows of X are read as ONE 128-byte operand
@@ -1054,7 +1114,7 @@ int pack_k_sub(int d, int k)
 }
 
 struct TilePlan {
-  int kb, bn, a_slots, b_stages, b_resident, a_stream;
+  int kb, bn, a_slots, b_stages, b_resident, a_stream, fold;
   size_t smem;
 };
 
@@ -1098,6 +1158,13 @@ TilePlan plan_tiles(int d, int k, size_t smem_limit)
 }
 
 // CTA-pair plan: BN = 256 split across the pair (128 centroid rows per CTA), deeper X ring.
+// half norms folded into the accumulator by one extra MMA (default on; CUML_B200_FOLD=0 restores the epilogue add)
+bool use_cn_fold()
+{
+  const char* e = std::getenv("CUML_B200_FOLD");
+  return e ? std::atoi(e) != 0 : true;
+}
+
 TilePlan plan_tiles_2cta(int d, int k, size_t smem_limit)
 {
   TilePlan t{};
@@ -1108,6 +1175,8 @@ TilePlan plan_tiles_2cta(int d, int k, size_t smem_limit)
            6 * TILE_M * 4 + sizeof(Barriers) + 1024;
   };
   const int k_tiles = static_cast<int>(ceil_div(k, bn));
+  t.fold            = (use_cn_fold() && k_tiles <= 4) ? 1 : 0;
+  if (t.fold) smem_limit -= static_cast<size_t>(1 + k_tiles) * TILE_M * 32;
   t.a_stream        = (k_tiles > 1 && t.kb > 4) ? 1 : 0;
   const int a_min   = (k_tiles > 1 && !t.a_stream) ? t.kb : std::min(t.kb, 2);
   int b_stages      = t.a_stream ? 3 : 2;
@@ -1124,7 +1193,7 @@ TilePlan plan_tiles_2cta(int d, int k, size_t smem_limit)
   const int a_want = std::min(MAX_A_SLOTS, std::max(2 * t.kb, 6));
   while (t.a_slots < a_want && bytes(t.a_slots + 1, t.b_stages) <= smem_limit) ++t.a_slots;
   while (!t.b_resident && t.b_stages < MAX_STAGES && bytes(t.a_slots, t.b_stages + 1) <= smem_limit) ++t.b_stages;
-  t.smem = bytes(t.a_slots, t.b_stages);
+  t.smem = bytes(t.a_slots, t.b_stages) + (t.fold ? static_cast<size_t>(1 + k_tiles) * TILE_M * 32 : 0);
   return t;
 }
 
@@ -1260,10 +1329,12 @@ void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out)
     out.hb.alloc(static_cast<size_t>(k_pad) * d_pad, h.stream);
     out.lb.alloc(static_cast<size_t>(k_pad) * d_pad, h.stream);
   }
+  out.fold = (pair && t.fold) ? 1 : 0;
+  if (out.fold && out.cnp.n < static_cast<size_t>(k_pad) * 8) out.cnp.alloc(static_cast<size_t>(k_pad) * 8, h.stream);
   prepare_centroids_kernel<<<static_cast<unsigned>(ceil_div(k_pad, 8)), 256, 0, h.stream>>>(
     C, k, d, k_pad, d_pad, out.hi.get(), out.lo.get(), out.cnh.get(),
     out.bf16c ? reinterpret_cast<__nv_bfloat16*>(out.hb.get()) : nullptr,
-    out.bf16c ? reinterpret_cast<__nv_bfloat16*>(out.lb.get()) : nullptr);
+    out.bf16c ? reinterpret_cast<__nv_bfloat16*>(out.lb.get()) : nullptr, out.fold ? out.cnp.get() : nullptr);
   CB2_CHECK_LAUNCH();
 }
 
@@ -1444,6 +1515,12 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   const long long grid_dbg = pair ? h.sm_count / 2 : h.sm_count;
   if (pair) {
     // one CTA pair per TPC; grid must be even (cluster dims 2x1x1 are compiled into the kernel)
+    // the debug dump wants the bare x.c accumulators: no fold then (the plan keeps the space reserved)
+    p.fold = (cen.fold && t.fold && !dbg_dots) ? 1 : 0;
+    CUtensorMap tm_cn = tm_hi;
+    if (p.fold)
+      tm_cn = make_map_2d(cen.cnp.get(), 8, cen.k_pad, 8 * sizeof(float), 8, b_box_rows, CU_TENSOR_MAP_SWIZZLE_32B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     const int64_t pair_tiles = (p.m_tiles + 1) / 2;
     const unsigned grid = 2u * static_cast<unsigned>(std::min<int64_t>(pair_tiles, h.sm_count / 2));
     if (cen.bf16c) {
@@ -1453,9 +1530,9 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       CUtensorMap tm_lb = make_map_2d(cen.lb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
                                       b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-      fused_l2_argmin_2cta_kernel<true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, p);
+      fused_l2_argmin_2cta_kernel<true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
     } else {
-      fused_l2_argmin_2cta_kernel<false><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, p);
+      fused_l2_argmin_2cta_kernel<false><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     }
   } else {
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));

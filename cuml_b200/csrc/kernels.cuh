@@ -23,6 +23,8 @@ bool tc_supported(int64_t d, int k);
 struct TcCentroids {           // per-iteration operand buffers (hi/lo split + half norms)
   DevBuf<float> hi, lo, cnh;
   DevBuf<uint16_t> hb, lb;   // bf16 copies of hi / lo (correction terms of the CTA-pair kernel)
+  DevBuf<float> cnp;         // [k_pad][8]: -1/2||c||^2 as three tf32-exact pieces (folded into the MMA), zeros
+  int fold = 0;              // cnp is valid and the plan reserves the fold tiles
   int bf16c = 0;             // hi is rounded to nearest tf32 and hb / lb are valid
   int k_pad = 0, d_pad = 0, block_n = 0;
   int pack = 1;   // rows of X packed side by side into one 128-byte operand row (2 when n_features <= 16)

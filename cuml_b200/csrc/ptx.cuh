@@ -324,6 +324,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr)
   d |= static_cast<uint64_t>(4) << 61;
   return d;
 }
+// K-major operand tile with 32-byte rows (8 tf32), 32B swizzle: 8-row atoms of 256 bytes
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr)
+{
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
 // instruction descriptor: fp32 accumulate, bf16 x bf16 (kind::f16), both operands K-major, shape M x N
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N)
 {

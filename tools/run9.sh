@@ -1,4 +1,4 @@
-timeout 300 python -m pytest tests/test_kmeans_gpu.py -x -q -m gpu 2>&1 | tail -2
+timeout 300 python -m pytest tests/test_kmeans_gpu.py -x -q -m gpu 2>&1 | tail -3
 run() { env "$@" timeout 200 python bench.py --workload $W --steps 10 --warmup 3 --no-cpu --no-e2e 2>&1 | tail -1 > gpurun_out/tmp.json; python - <<PY
 import json
 try:
@@ -9,8 +9,8 @@ except Exception as e:
 PY
 }
 W=C3
-run CUML_B200_BF16C=0
-run CUML_B200_BF16C=1
+run CUML_B200_FOLD=0
+run CUML_B200_FOLD=1
 W=C2
-run CUML_B200_BF16C=0
-run CUML_B200_BF16C=1
+run CUML_B200_FOLD=0
+run CUML_B200_FOLD=1
