@@ -63,7 +63,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -72,15 +72,20 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """clocks of the samples that arrived inside [t_begin, t_end] (host clock; all samples when not given)"""
         if not self.proc:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
         time.sleep(0.15)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for (ts, ln) in self.lines
+                  if t_begin is None or (t_begin - 0.01 <= ts <= t_end + 0.03)]
+        if not inside:   # timed region shorter than one polling period: nearest samples around it
+            inside = [ln for (ts, ln) in self.lines][-3:]
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -214,22 +219,24 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()          # polling (20 ms) is already running when the timed region starts
     for _ in range(max(args.warmup, 0)):
         step()
     barrier()
     _lib.check(lib.cuml_b200_kernel_timing_enable(h.ptr, 1))
     lib.cuml_b200_launch_count_reset()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.time()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
     barrier()
+    t_end = time.time()
     ms_total = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     launches = int(lib.cuml_b200_launch_count())
     f_ms, f_n, u_ms, u_n = C.c_double(), C.c_int64(), C.c_double(), C.c_int64()
     _lib.check(lib.cuml_b200_kernel_timing_read(h.ptr, C.byref(f_ms), C.byref(f_n), C.byref(u_ms), C.byref(u_n)))
