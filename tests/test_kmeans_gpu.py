@@ -42,7 +42,10 @@ def _step(env, X, C0, k, engine, w=None):
 
 SHAPES = [(2000, 8, 5), (5000, 32, 16), (3001, 20, 3), (4000, 64, 40), (1500, 7, 9), (20000, 128, 300),
           (129, 4, 2), (128, 32, 1), (10000, 16, 64), (7000, 96, 130), (9000, 100, 257),
-          (3000, 160, 300), (2500, 256, 520), (2001, 12, 100), (4001, 16, 33)]
+          (3000, 160, 300), (2500, 256, 520), (2001, 12, 100), (4001, 16, 33),
+          # CTA-pair kernel edge cases: k just above 128 (half of the 256-wide tile is padding), more than four
+          # centroid tiles (half norms not folded into the MMA), n_features not a multiple of 16
+          (5000, 64, 129), (3000, 32, 1300), (4000, 36, 200)]
 
 
 @pytest.mark.parametrize("n,d,k", SHAPES)
