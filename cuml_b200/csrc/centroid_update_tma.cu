@@ -4,21 +4,22 @@
 // Roles replaced (cuVS side, reached from reference cpp/src/kmeans/kmeans_fit.cu:58-59,153-154):
 // reduce_rows_by_key (centroid sums) and reduce_cols_by_key (cluster weights).
 //
-// CTA = 1 producer warp + W consumer warps; a CTA works on a 32-column slice of X (128-byte row
-// segments) when n_features >= 32, on whole rows otherwise.
-//   producer : one thread streams [TR rows x DS columns] tiles of X (2-D TMA, 128B-swizzled when
-//              DS == 32) and the tile's labels (1-D bulk copy) into a 3-stage shared-memory ring;
-//              mbarrier full/empty.
-//   consumers: consumer w exclusively owns 8 columns (DS == 32: four consumers) or the whole slice
-//              (DS < 32: one consumer) of the CTA's [k x DS] fp32 table in shared memory, so no two
-//              warps ever touch the same cell.  One warp instruction covers R = 32/L rows (L lanes x
-//              float4 per row); rows in the same instruction that share a label are ordered with
-//              __match_any_sync (segmented in-warp update).  The table rows are XOR-swizzled by label
-//              like the X tile is by row, so both the tile reads and the table read-modify-writes
-//              are bank-conflict free.
-// The table is written once per CTA to a partials buffer; a second kernel sums the partials in a
-// fixed order in fp64 (deterministic, bitwise identical on every rank after the all-reduce).
-// Memory parallelism comes from the TMA ring (3 tiles in flight per CTA), not from occupancy.
+// Three kernels, chosen by tma_update_accumulate():
+//   accumulate_owner_kernel  (n_features >= 32, k >= 16, [k x 32*VEC] table fits shared memory; the default
+//                            for C2 / C3): consumer warp w owns the table rows of the clusters of class w
+//                            (16 size-balanced classes); analyst warps counting-sort each tile's rows by
+//                            class on a label ring that runs ahead of the X ring; consumers apply their rows
+//                            with lane = column (contiguous, conflict-free table read-modify-write).
+//                            HBM-bound: 5.8-5.9 TB/s at C3.
+//   accumulate_tma_kernel    (short rows / small k, e.g. C5): lane = row, consumer w owns 8 columns of the
+//                            table, rows of one instruction that share a label are ordered by ranks an
+//                            analyst warp computes with __match_any_sync; X tile and table XOR-swizzled.
+//                            Bound by shared-memory wavefronts (3.3-3.6 TB/s).
+//   accumulate_rows_kernel   (opt-in experiment, CUML_B200_UPDATE_ROWS): lane = column with per-warp column
+//                            slices; too few warps per table, kept for the A/B record.
+// Every kernel writes its table once per CTA to a partials buffer; reduce_partials_f32_kernel sums the
+// partials in a fixed order in fp64 (deterministic, bitwise identical on every rank after the all-reduce).
+// Memory parallelism comes from the TMA rings, not from occupancy (one CTA per SM).
 #include <cstdlib>
 
 #include "kernels.cuh"
