@@ -3,20 +3,24 @@
 //
 //   label_i = argmin_j ( 1/2 ||c_j||^2 - x_i . c_j )        (first minimum on ties)
 //
-// The x.c contraction runs on the 5th-gen tensor cores (tcgen05.mma kind::tf32, fp32
-// accumulators in TMEM) as 3xTF32:  x.c ~= x_lo.c_hi + x_hi.c_lo + x_hi.c_hi  with
-// hi = fp32 with the 13 low mantissa bits cleared (exactly representable in tf32) and
-// lo = x - hi (exact in fp32).  The result has ~22 mantissa bits: fp32-grade labels.
+// The x.c contraction runs on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in TMEM) in split
+// precision, hi = x rounded / truncated to tf32, lo = x - hi (exact in fp32):
+//   3xTF32          x.c ~= x_lo.c_hi + x_hi.c_lo + x_hi.c_hi, all kind::tf32          (single-CTA kernel)
+//   tf32 + 2 bf16   x_hi.c_hi as kind::tf32, the two correction terms as kind::f16 with bf16 operands (half
+//                   the MMA instructions per term); -1/2||c||^2 enters the accumulator through one extra
+//                   K = 8 MMA of a ones tile with three tf32-exact pieces               (CTA-pair kernel)
+// Both give fp32-grade labels (tests/test_kmeans_gpu.py::test_tensor_core_dot_accuracy, label-gap tests).
 //
-// One persistent CTA per SM, warp-specialised:
-//   warp 0      A producer : TMA loads of the raw X tile (128 rows x d, 128B-swizzled K-blocks)
-//   warp 2      B producer : TMA loads of centroid hi/lo K-blocks (L2-resident operand buffers)
-//   warps 4-7   converter  : split the raw X tile into hi (in place) and lo tiles in shared memory
-//   warp 1      MMA issuer : one elected thread issues tcgen05.mma, 3 per K=8 step
-//   warps 8-11  epilogue   : tcgen05.ld the 128 x BN accumulator, add 1/2||c||^2, running
-//                            (min, argmin) per row in registers, coalesced label store
-// Pipelines are mbarrier rings: A raw->ready->empty, B full/empty, and two TMEM accumulators
-// (full/empty) so the argmin of N-tile t overlaps the MMAs of N-tile t+1.
+// Persistent warp-specialised kernels, one CTA per SM:
+//   fused_l2_argmin_2cta_kernel  k > 128: two CTAs of a TPC share M = 256, N = 256 MMAs (cta_group::2), each
+//                                holds half of every centroid block; 8 converter warps, 16 epilogue warps
+//   fused_l2_argmin_kernel       k <= 128 and the row-packed small-d case
+//   fused_l2_argmin_ts_kernel    X operand in tensor memory (opt-in experiment)
+// Roles: TMA producers for X and centroid K-blocks (128B / 64B / 32B-swizzled tiles), converter warps that
+// split the raw X tile in shared memory, one MMA-issuing warp (uniform control flow, elect.sync lane), and the
+// argmin epilogue (tcgen05.ld, thread = row, four (min, argmin) chains, parts merged through shared memory).
+// Pipelines are mbarrier rings: X raw -> ready -> empty, centroids full/empty, and two or more TMEM
+// accumulators (full/empty) so the argmin of one tile overlaps the MMAs of the next.
 #include <cuda_bf16.h>
 
 #include <cstdlib>
