@@ -35,7 +35,7 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant (fused) kernel at the full
 # workload, from the committed `ncu --set full` captures (profiles/r01_ncu_full_c3.txt, r01_ncu_full_c2.txt)
-TRAFFIC_NCU = {"C3": 25.620909e9 + 0.402735e9, "C2": 5.127724e9 + 0.042767e9}
+TRAFFIC_NCU = {"C3": 25.602643e9 + 0.401213e9, "C2": 5.121371e9 + 0.042751e9}
 METRIC = "kmeans_lloyd_iters_per_sec"
 UNIT = "Lloyd iter/s"
 
