@@ -556,11 +556,15 @@ balance_classes_kernel(const double* __restrict__ W, int k, uint8_t* __restrict_
 //   consumer : owns the table rows of its class.  Walks its perm segment with lane = column: per row one
 //              contiguous table read, add, write; the X segment of the next row and the next list entries are
 //              already in flight.  Two rows per loop iteration (register rotation without moves).
-template <int VEC, bool HAS_W>
+//   HALF     : n_features == 16 -- a row is 64 bytes, so a warp instruction covers TWO rows of the consumer's
+//              list (lanes 0-15 / 16-31); when both carry the same label the upper half hands its values to
+//              the lower half (one shuffle) and only the lower half updates the table.
+template <int VEC, bool HAS_W, bool HALF = false>
 __global__ void __launch_bounds__((2 + OWN_NA + OWN_CONS) * 32)
 accumulate_owner_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams7 p)
 {
-  constexpr int DS        = 32 * VEC;
+  static_assert(!HALF || VEC == 1, "HALF rows are 16 floats: one float per lane");
+  constexpr int DS        = HALF ? 16 : 32 * VEC;
   constexpr uint32_t ROWB = DS * 4;
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t raw  = ptx::smem_u32(smem_dyn);
@@ -749,6 +753,44 @@ accumulate_owner_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParam
       int j          = (cw & 1) ? static_cast<int>(oo.y) : static_cast<int>(oo.x);
       const int o1   = (cw & 1) ? lds32(offs + cw * 4 + 4) : static_cast<int>(oo.y);
       c_rows += o1 - j;
+      if constexpr (HALF) {
+        // two list entries per instruction: lanes 0-15 take entry j, lanes 16-31 entry j + 1
+        const int half      = lane >> 4;
+        const uint32_t hoff = static_cast<uint32_t>(lane & 15) * 4u;
+        const uint32_t xsh  = base + s * x_bytes + hoff;
+        const uint32_t tabh = tab_u32 + hoff;
+        if (j < o1) {
+          uint32_t e  = static_cast<uint32_t>(lds32(perm + (j + half) * 4));   // past the end: stale, in range
+          float w     = 1.0f;
+          if (HAS_W) w = __int_as_float(lds32(wprm + (j + half) * 4));
+          float x     = __int_as_float(lds32(xsh + (e >> 16) * ROWB));
+          for (; j < o1; j += 2) {
+            const uint32_t en = static_cast<uint32_t>(lds32(perm + (j + 2 + half) * 4));
+            float wn = 1.0f;
+            if (HAS_W) wn = __int_as_float(lds32(wprm + (j + 2 + half) * 4));
+            const float xn = __int_as_float(lds32(xsh + (en >> 16) * ROWB));
+            const bool live   = (j + half) < o1;
+            const uint32_t l  = e & 0xffffu;
+            const uint32_t lo = __shfl_xor_sync(0xffffffffu, l, 16);
+            float v = HAS_W ? x * w : x;
+            const float vo = __shfl_xor_sync(0xffffffffu, v, 16);
+            float wsum = w;
+            if (HAS_W) wsum += __shfl_xor_sync(0xffffffffu, w, 16);
+            const bool same = (j + 1 < o1) && (l == lo);          // both rows of the instruction share a label
+            if (same) v += vo;                                    // (only the lower half stores then)
+            const bool store  = live && !(same && half);
+            const uint32_t ta = tabh + l * ROWB;
+            const float tvv   = __int_as_float(lds32(ta));
+            if (store) asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta), "f"(tvv + v) : "memory");
+            if (HAS_W && counts) {
+              const uint32_t wa = wtab_u32 + l * 4u;
+              const float cur   = __int_as_float(lds32(wa));
+              if (store) asm volatile("st.shared.f32 [%0], %1;" ::"r"(wa), "f"(cur + (same ? wsum : w)) : "memory");
+            }
+            e = en; w = wn; x = xn;
+          }
+        }
+      } else {
       VecIO<VEC> x0, x1, tv;
       // apply one row: table row of label (e & 0xffff) += w * x
       auto apply = [&](uint32_t e, const VecIO<VEC>& x, float w, auto&& between) {
@@ -787,6 +829,7 @@ accumulate_owner_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParam
           w = wn;
         }
       }
+      }   // !HALF
       __syncwarp();
       if (lane == 0) {
         ptx::mbar_arrive(bars_u32 + B_EMPTYX + s * 8);
@@ -973,7 +1016,7 @@ static RowsPlan plan_rows_update(const Handle& h, int d, int k)
 }
 
 struct OwnerPlan {
-  int vec = 0, tr = 0, nstage = 0, slices = 0, ncons = 16, nl = 0;
+  int vec = 0, tr = 0, nstage = 0, slices = 0, ncons = 16, nl = 0, half = 0;
   size_t smem = 0;
 };
 
@@ -983,7 +1026,11 @@ static OwnerPlan plan_owner_update(const Handle& h, int d, int k)
   OwnerPlan best;
   int mode = 1;
   if (const char* e = std::getenv("CUML_B200_UPDATE_OWNER")) mode = std::atoi(e);
-  if (mode == 0 || d < 32 || d % 4 != 0 || k < 16) return best;
+  // 64-byte rows (n_features == 16), two rows per warp instruction: correct but measured slower than the lane = row
+  // kernel at C5 (6.1 vs 3.8 ms: four times the rows per byte make the analysts the bottleneck) -> opt-in
+  static const bool half_ok = std::getenv("CUML_B200_OWNER_HALF") && std::atoi(std::getenv("CUML_B200_OWNER_HALF")) != 0;
+  if (mode == 0 || (d < 32 && !(d == 16 && half_ok)) || d % 4 != 0 || k < 16) return best;
+  const bool half = d == 16;
   int force_vec = 0, force_tr = 0, force_nl = 0, force_ns = 0;
   if (const char* e = std::getenv("CUML_B200_OWNER_VEC")) force_vec = std::atoi(e);
   if (const char* e = std::getenv("CUML_B200_OWNER_TR")) force_tr = std::atoi(e);
@@ -991,9 +1038,9 @@ static OwnerPlan plan_owner_update(const Handle& h, int d, int k)
   if (const char* e = std::getenv("CUML_B200_OWNER_NS")) force_ns = std::atoi(e);
   const size_t budget = h.smem_optin - 512;
   double best_score   = -1.0;
-  for (int vec = 4; vec >= 1; vec >>= 1) {
+  for (int vec = half ? 1 : 4; vec >= 1; vec >>= 1) {
     if (force_vec && vec != force_vec) continue;
-    const int ds = 32 * vec;
+    const int ds = half ? 16 : 32 * vec;
     if (vec > 1 && ds > d) continue;   // do not read padding columns
     const size_t table = (static_cast<size_t>(k) * ds + ((k + 3) & ~3)) * 4 + ((k + 15) & ~15) + (2 * MAX_NSTAGE + 3 * OWN_MAXNL) * 8 + 256;
     if (table + 2 * 8192 > budget) continue;
@@ -1022,6 +1069,7 @@ static OwnerPlan plan_owner_update(const Handle& h, int d, int k)
           best.slices = slices;
           best.smem   = table + lists + nstage * stage + 128;
           best.nl     = nl;
+          best.half   = half ? 1 : 0;
         }
       }
     }
@@ -1079,7 +1127,7 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
     if (partial_W.n < static_cast<size_t>(rb) * k) partial_W.alloc(static_cast<size_t>(rb) * k, h.stream);
     q.labels = labels_padded; q.w = w; q.partial_S = partial_S.get(); q.partial_W = partial_W.get();
     CUtensorMap tm = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
-                                 static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(32 * op.vec),
+                                 static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(op.half ? 16 : 32 * op.vec),
                                  static_cast<uint32_t>(op.tr), CU_TENSOR_MAP_SWIZZLE_NONE,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     dim3 grid(static_cast<unsigned>(rb), static_cast<unsigned>(op.slices));
@@ -1089,10 +1137,14 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
       kern<<<grid, threads, op.smem, h.stream>>>(tm, q);
     };
     const bool hw = w != nullptr;
-    switch (op.vec) {
-      case 4: hw ? launch(accumulate_owner_kernel<4, true>) : launch(accumulate_owner_kernel<4, false>); break;
-      case 2: hw ? launch(accumulate_owner_kernel<2, true>) : launch(accumulate_owner_kernel<2, false>); break;
-      default: hw ? launch(accumulate_owner_kernel<1, true>) : launch(accumulate_owner_kernel<1, false>); break;
+    if (op.half) {
+      hw ? launch(accumulate_owner_kernel<1, true, true>) : launch(accumulate_owner_kernel<1, false, true>);
+    } else {
+      switch (op.vec) {
+        case 4: hw ? launch(accumulate_owner_kernel<4, true>) : launch(accumulate_owner_kernel<4, false>); break;
+        case 2: hw ? launch(accumulate_owner_kernel<2, true>) : launch(accumulate_owner_kernel<2, false>); break;
+        default: hw ? launch(accumulate_owner_kernel<1, true>) : launch(accumulate_owner_kernel<1, false>); break;
+      }
     }
     CB2_CHECK_LAUNCH();
     reduce_partials_f32_kernel<<<static_cast<unsigned>(ceil_div(total, 32)), 256, 0, h.stream>>>(

@@ -79,7 +79,8 @@ def test_regime2_step_matches_oracle(env, engine):
     assert agree >= 0.9999 and bad == 0
 
 
-@pytest.mark.parametrize("n,d,k", [(6000, 24, 11), (5000, 64, 40), (4001, 32, 16), (3000, 160, 300), (7000, 96, 130)])
+@pytest.mark.parametrize("n,d,k", [(6000, 24, 11), (5000, 64, 40), (4001, 32, 16), (3000, 160, 300), (7000, 96, 130),
+                                   (5001, 16, 24)])
 def test_weighted_step(env, n, d, k):
     from oracle import blobs, lloyd
     X, centres, _ = blobs.make_blobs(n, d, k)
