@@ -214,24 +214,15 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
       const int64_t row0 = t * p.tr;
       const int64_t left = p.n - row0;
       const int valid    = left < p.tr ? static_cast<int>(left) : p.tr;
-      // software pipeline: the loads of the next 32-row group are issued before the read-modify-write rounds
-      // of the current one, so their shared-memory latency overlaps the dependent table updates
-      int lb_n = 0, meta_n = 0;
-      float4 x0_n = make_float4(0.f, 0.f, 0.f, 0.f), x1_n = x0_n;
-      auto fetch = [&](int r) {
-        lb_n   = (r < valid) ? lds32(ls + r * 4) : 0;
-        meta_n = lds32(ms + r * 4);
-        const uint32_t xa = xs + static_cast<uint32_t>(r) * ROWB + ((j0 ^ ((static_cast<uint32_t>(r) >> SH) & MSK)) << 4);
-        x0_n = lds128(xa);
-        if (CPL == 2) x1_n = lds128(xa ^ 16u);
-      };
-      fetch(lane);
+#pragma unroll 2
       for (int r = lane; r < p.tr; r += 32) {
         const bool ok    = r < valid;
-        const int lb     = lb_n;
-        const int meta   = meta_n;
-        float4 x0 = x0_n, x1 = x1_n;
-        if (r + 32 < p.tr) fetch(r + 32);
+        const int lb     = ok ? lds32(ls + r * 4) : 0;
+        const int meta   = lds32(ms + r * 4);
+        const uint32_t xa = xs + static_cast<uint32_t>(r) * ROWB + ((j0 ^ ((static_cast<uint32_t>(r) >> SH) & MSK)) << 4);
+        float4 x0 = lds128(xa);
+        float4 x1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (CPL == 2) x1 = lds128(xa ^ 16u);
         const int rank   = meta & 0xff;
         const int maxr   = meta >> 8;                       // warp-uniform
         if (HAS_W) {
