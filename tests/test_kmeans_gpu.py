@@ -362,6 +362,60 @@ def test_large_property_checks(env):
         last = packed[-1].item()
 
 
+def test_full_size_c3_properties(env):
+    # BASELINE config C3 at its FULL size (n = 100M, d = 64, k = 256; 25.6 GB of X, 64-bit row addressing) through
+    # size-independent properties: every row is counted exactly once, the per-cluster sums add up to the column
+    # sums of X (linearity), the inertia does not increase, the E-step is idempotent, and a random sample of rows
+    # carries the exact fp64 argmin.
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    n, d, k = 100_000_000, 64, 256
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40 * 2**30:
+        pytest.skip("needs 40 GB of free device memory")
+    g = torch.Generator(device="cuda").manual_seed(99)
+    cent = torch.rand((k, d), device="cuda", generator=g) * 20 - 10
+    X = torch.empty((n, d), dtype=torch.float32, device="cuda")
+    colsum = torch.zeros(d, dtype=torch.float64, device="cuda")
+    chunk = 1 << 22
+    for s0 in range(0, n, chunk):
+        e0 = min(n, s0 + chunk)
+        lab = torch.randint(0, k, (e0 - s0,), device="cuda", generator=g)
+        X[s0:e0] = cent[lab]
+        X[s0:e0] += torch.randn((e0 - s0, d), device="cuda", generator=g)
+        colsum += X[s0:e0].double().sum(0)
+    Cd = X[torch.randint(0, n, (k,), device="cuda", generator=g)].clone()
+    labels = torch.zeros(n, dtype=torch.int32, device="cuda")
+    packed = torch.zeros(k * d + k + 1, dtype=torch.float64, device="cuda")
+    last = None
+    for it in range(3):
+        C_before = Cd.clone()
+        _lib.check(lib.cuml_b200_kmeans_lloyd_step_f32(h.ptr, X.data_ptr(), n, d, None, k, Cd.data_ptr(),
+                                                       labels.data_ptr(), packed.data_ptr(), None, 0))
+        h.sync()
+        W = packed[k * d:k * d + k]
+        assert abs(W.sum().item() - n) < 0.5                                   # every row counted once
+        assert torch.equal(W, torch.bincount(labels.long(), minlength=k).double())
+        S = packed[:k * d].reshape(k, d)
+        assert ((S.sum(0) - colsum).abs().max() / colsum.abs().max()).item() < 1e-6   # linearity: no row lost
+        if last is not None:
+            assert packed[-1].item() <= last * (1 + 1e-9)                       # inertia non-increasing
+        last = packed[-1].item()
+        # the E-step is a pure function of (X, C): assigning again with the same centroids gives the same labels
+        again = torch.zeros(n, dtype=torch.int32, device="cuda")
+        _lib.check(lib.cuml_b200_kmeans_assign_f32(h.ptr, X.data_ptr(), n, d, k, C_before.data_ptr(),
+                                                   again.data_ptr(), 0))
+        h.sync()
+        assert torch.equal(again, labels)
+        # exact fp64 argmin on a sample that includes the last rows (beyond 2^31 elements)
+        idx = torch.cat([torch.randint(0, n, (100_000,), device="cuda", generator=g),
+                         torch.arange(n - 1000, n, device="cuda")])
+        xs, c64 = X[idx].double(), C_before.double()
+        dist = (xs * xs).sum(1, keepdim=True) - 2 * xs @ c64.T + (c64 * c64).sum(1)[None, :]
+        agree = (dist.argmin(1).int() == labels[idx]).double().mean().item()
+        assert agree >= 0.9999, agree
+        del again, xs, dist
+
+
 def test_cpp_surface_example_kat(tmp_path):
     # the C++ ML::kmeans::{fit,predict} mirror (include/cuml/cluster/kmeans.hpp) on the reference's own
     # example KAT (cpp/examples/kmeans/kmeans_example.cpp:110-113,172-191)
