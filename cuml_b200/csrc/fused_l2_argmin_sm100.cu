@@ -102,6 +102,10 @@ struct FusedParams {
   int dbg_skip;      // profiling knob (env CUML_B200_DBG_SKIP): 1 = no hi/lo split, 2 = no MMA, 4 = no argmin
   int l2_ahead;      // CTA-pair kernel: row tiles prefetched into L2 ahead of the shared-memory ring
   int fold;          // CTA-pair kernel: -1/2||c||^2 enters the accumulator through one extra K=8 MMA (ones x pieces)
+  // Distance-matrix mode (DIST kernels, ML::kmeans::transform) reuses fields that are idle there, so that the
+  // parameter block of the hot E-step instantiations keeps its size (growing it cost them register spills):
+  //   dbg_dots -> output [n, k_sub] | labels -> ||x_i||^2 (as float*) | k_sub -> true n_clusters (row pitch) |
+  //   raw_slots -> 1: write sqrt(max(d, 0))
 };
 
 struct Barriers {
@@ -118,7 +122,7 @@ struct Barriers {
 // accumulator tile (BN/4 columns, at least one 32-column chunk); thread = row.  Per row: four independent
 // running (min, argmin) chains, merged with the first-minimum rule; the column parts are merged through
 // shared memory.  The argmin is instruction-issue bound (4 instructions per distance), hence many warps.
-template <bool PAIR>
+template <bool PAIR, bool DIST = false>
 __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* bars, float* cn_s, float* mrg_v,
                                               int* mrg_i, uint32_t tmem_base, int64_t first_row, int64_t row_stride,
                                               int64_t n_tiles_cta)
@@ -172,13 +176,40 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
         if (p.dbg_skip & 4) break;
         ptx::tmem_ld_32x32(taddr + c0, r);
         ptx::tmem_ld_wait();
-        if (p.dbg_dots) {
+        if (!DIST && p.dbg_dots) {
           const int64_t row = first_row + t * row_stride + rit;
           if (row < p.n) {
             float* o = p.dbg_dots + row * (static_cast<int64_t>(p.k_tiles) * p.bn) + jbase + c0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
           }
+        }
+        if (DIST) {
+          // transform: ||x - c||^2 = ||x||^2 - 2 (x.c - 1/2||c||^2); this thread holds 32 consecutive columns of its row
+          const int64_t row = first_row + t * row_stride + rit;
+          if (row < p.n) {
+            const int dist_k = p.k_sub;
+            const float xx = __ldg(reinterpret_cast<const float*>(p.labels) + row);
+            float* o       = p.dbg_dots + row * static_cast<int64_t>(dist_k) + jbase + c0;
+            const float* cnc = cn + c0;
+            float dv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = fold ? __uint_as_float(r[j]) : __uint_as_float(r[j]) - cnc[j];
+              dv[j]         = fmaxf(xx - 2.0f * s, 0.0f);
+              if (p.raw_slots) dv[j] = sqrtf(dv[j]);
+            }
+            if ((dist_k & 3) == 0 && jbase + c0 + 32 <= dist_k) {   // 16-byte aligned full chunk: vector stores
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(dv[j], dv[j + 1], dv[j + 2], dv[j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (jbase + c0 + j < dist_k) o[j] = dv[j];
+            }
+          }
+          continue;
         }
         const int jb = jbase + c0 - col0;
         if (fold) {
@@ -217,6 +248,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
         else ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[acc]));
       }
     }
+    if (DIST) continue;   // distance-matrix mode: nothing to merge, no labels
     // merge the chains: smaller value wins, equal values -> smaller index (first minimum)
     if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
     if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
@@ -240,6 +272,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
   }
 }
 
+template <bool DIST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                        const __grid_constant__ CUtensorMap tm_lo, const FusedParams p)
@@ -456,7 +489,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     // ===================== epilogue: argmin over the accumulator =====================
     const int64_t n_mine = (p.m_tiles > static_cast<int64_t>(blockIdx.x))
                              ? (p.m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    epilogue_role<false>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, static_cast<int64_t>(blockIdx.x) * TILE_M,
+    epilogue_role<false, DIST>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, static_cast<int64_t>(blockIdx.x) * TILE_M,
                          static_cast<int64_t>(gridDim.x) * TILE_M, n_mine);
   }
 
@@ -479,7 +512,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
 // rounding lo and hi to bf16 perturbs each correction by <= 2^-9 relative: ~2^-20 |x||c| per product -- the size of
 // the lo.lo term every 3xTF32 scheme drops.  Operand slot layout per 32-feature K-block:
 //   [0, 16 KB) hi tf32, 128B swizzle | [16 KB, 24 KB) hi bf16, 64B swizzle | [24 KB, 32 KB) lo bf16, 64B swizzle
-template <bool BF16C>
+template <bool BF16C, bool DIST = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                             const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_lb,
@@ -782,7 +815,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   } else if (warp >= 8 && warp < 24) {
     // ===================== epilogue (own 128 rows of the pair tile) =====================
     const int64_t n_mine = (pair_tiles > pair) ? (pair_tiles - pair + n_pairs - 1) / n_pairs : 0;
-    epilogue_role<true>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, pair * 2 * TILE_M + cta_rank * TILE_M,
+    epilogue_role<true, DIST>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, pair * 2 * TILE_M + cta_rank * TILE_M,
                         n_pairs * 2 * TILE_M, n_mine);
   }
 
@@ -1288,7 +1321,7 @@ int tc_variant(const Handle& h, int d, int k)
   return 1;
 }
 
-void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out)
+void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out, bool allow_bf16)
 {
   if (const int k_sub = pack_k_sub(d, k)) {
     const int k_pad = 2 * k_sub;
@@ -1328,7 +1361,7 @@ void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out)
     out.d_pad = d_pad;
   }
   out.block_n = t.bn;
-  out.bf16c   = (pair && use_bf16_corrections()) ? 1 : 0;
+  out.bf16c   = (pair && allow_bf16 && use_bf16_corrections()) ? 1 : 0;
   if (out.bf16c && out.hb.n < static_cast<size_t>(k_pad) * d_pad) {
     out.hb.alloc(static_cast<size_t>(k_pad) * d_pad, h.stream);
     out.lb.alloc(static_cast<size_t>(k_pad) * d_pad, h.stream);
@@ -1367,10 +1400,18 @@ __global__ void assign_tail_row_kernel(const float* __restrict__ x, int d, int k
   if (threadIdx.x == 0) *label = bidx;
 }
 
+bool tc_transform_supported(const Handle& h, int64_t d, int k)
+{
+  // the distance-matrix epilogue exists for the unpacked shared-memory-operand kernels
+  return h.cc_major == 10 && tc_supported(d, k) && !pack_k_sub(static_cast<int>(d), k) &&
+         !use_ts(h, static_cast<int>(d), k);
+}
+
 void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen, int32_t* labels,
-               float* dbg_dots)
+               float* dbg_dots, const TcDistOut* dist)
 {
   if (n == 0) return;
+  CB2_EXPECTS(!dist || cen.pack == 1, "distance-matrix mode does not support row packing");
   CB2_EXPECTS(h.cc_major == 10, "the tcgen05 k-means engine needs an sm_100-class GPU (B200)");
   CB2_EXPECTS(reinterpret_cast<uintptr_t>(X) % 16 == 0, "X must be 16-byte aligned for TMA");
   if (cen.pack == 2) {
@@ -1396,14 +1437,14 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
       static bool pk_attr = false;
       if (!pk_attr) {
-        CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(h.smem_optin)));
         pk_attr = true;
       }
       EventPair ev{};
       if (h.timing) ev = h.begin_event();
       const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
-      fused_l2_argmin_kernel<<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+      fused_l2_argmin_kernel<false><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
       CB2_CHECK_LAUNCH();
       if (h.timing) h.end_event(ev, true);
     }
@@ -1481,6 +1522,12 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   p.cnh       = cen.cnh.get();
   p.labels    = labels;
   p.dbg_dots  = dbg_dots;
+  if (dist) {   // see FusedParams: idle fields carry the distance-matrix arguments
+    p.dbg_dots  = dist->out;
+    p.labels    = reinterpret_cast<int32_t*>(const_cast<float*>(dist->xnorm));
+    p.k_sub     = k;
+    p.raw_slots = dist->sqrt;
+  }
   {
     const char* e = std::getenv("CUML_B200_DBG_SKIP");
     p.dbg_skip    = e ? std::atoi(e) : 0;
@@ -1506,7 +1553,11 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
 
   static bool attr_set = false;
   if (!attr_set) {
-    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(h.smem_optin)));
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(h.smem_optin)));
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
@@ -1535,12 +1586,15 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                       b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
       fused_l2_argmin_2cta_kernel<true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+    } else if (dist) {
+      fused_l2_argmin_2cta_kernel<false, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     } else {
       fused_l2_argmin_2cta_kernel<false><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     }
   } else {
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
-    fused_l2_argmin_kernel<<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+    if (dist) fused_l2_argmin_kernel<true><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+    else fused_l2_argmin_kernel<false><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
   }
   CB2_CHECK_LAUNCH();
   if (h.timing) h.end_event(ev, true);

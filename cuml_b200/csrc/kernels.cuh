@@ -30,10 +30,17 @@ struct TcCentroids {           // per-iteration operand buffers (hi/lo split + h
   int pack = 1;   // rows of X packed side by side into one 128-byte operand row (2 when n_features <= 16)
   int k_sub = 0;  // centroid rows per packed group (k padded to 32/64/128) when pack == 2
 };
-void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out);
+void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out, bool allow_bf16 = true);
 int tc_variant(const Handle& h, int d, int k);   // 1 one-CTA 3xTF32, 2 pair 3xTF32, 3 pair tf32+bf16, 4 A-in-TMEM
+// distance-matrix mode of the same kernels (ML::kmeans::transform): out[i, j] = ||x_i - c_j||^2 (or its sqrt)
+struct TcDistOut {
+  float* out         = nullptr;   // [n, k] row-major
+  const float* xnorm = nullptr;   // [n] ||x_i||^2
+  int sqrt           = 0;
+};
 void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen,
-               int32_t* labels, float* dbg_dots = nullptr);
+               int32_t* labels, float* dbg_dots = nullptr, const TcDistOut* dist = nullptr);
+bool tc_transform_supported(const Handle& h, int64_t d, int k);
 
 // ---- M-step: centroid sums / weights / exact inertia ----------------------------------------
 template <typename T>

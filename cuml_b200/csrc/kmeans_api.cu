@@ -255,9 +255,26 @@ void transform_impl(Handle& h, const cuml_b200_kmeans_params_t& params, const T*
   CB2_EXPECTS(X_new && is_device_pointer(X_new), "X_new must be device accessible");
   CB2_CUDA(cudaSetDevice(h.device));
   const int k = params.n_clusters, di = static_cast<int>(d);
+  const bool want_sqrt = params.metric == CUML_B200_L2SqrtExpanded;
+  if constexpr (std::is_same<T, float>::value) {
+    // tensor-core distance matrix (3xTF32, same kernels as the E-step with a distance-writing epilogue)
+    static const bool tc_off = std::getenv("CUML_B200_TRANSFORM_TC") && std::atoi(std::getenv("CUML_B200_TRANSFORM_TC")) == 0;
+    if (!tc_off && tc_transform_supported(h, d, k) && reinterpret_cast<uintptr_t>(X) % 16 == 0 &&
+        engine_from_env(ENGINE_AUTO) != ENGINE_SIMT) {
+      TcCentroids cen;
+      tc_prepare(h, centroids, k, di, cen, /*allow_bf16=*/false);
+      DevBuf<float> xn(static_cast<size_t>(n), h.stream);
+      row_norms<float>(h, X, n, di, xn.get());
+      TcDistOut dist;
+      dist.out = X_new; dist.xnorm = xn.get(); dist.sqrt = want_sqrt ? 1 : 0;
+      tc_assign(h, X, n, di, k, cen, nullptr, nullptr, &dist);
+      CB2_CUDA(cudaStreamSynchronize(h.stream));
+      return;
+    }
+  }
   DevBuf<T> cn(k, h.stream);
   row_norms<T>(h, centroids, k, di, cn.get());
-  simt_transform<T>(h, X, n, di, centroids, k, cn.get(), X_new, params.metric == CUML_B200_L2SqrtExpanded);
+  simt_transform<T>(h, X, n, di, centroids, k, cn.get(), X_new, want_sqrt);
   CB2_CUDA(cudaStreamSynchronize(h.stream));
 }
 

@@ -207,6 +207,30 @@ def test_predict_transform_score_match_oracle():
     assert abs(-km.score(X, sample_weight=w) - in_w) / in_w <= 1e-5
 
 
+@pytest.mark.parametrize("n,d,k,sqrt", [(3001, 64, 300, False), (2000, 32, 40, True), (1500, 128, 1030, True),
+                                        (2500, 100, 129, False), (1000, 20, 5, False)])
+def test_transform_matches_oracle(env, n, d, k, sqrt):
+    # distance matrix through the C-ABI: tensor-core epilogue (pair / single-CTA kernels, folded and staged norms,
+    # padded centroid tiles) and the CUDA-core kernel (n_features not a multiple of 4... here d = 20, k = 5 packs)
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    from oracle import blobs, lloyd
+    X, centres, _ = blobs.make_blobs(n, d, k)
+    Cc = (centres + 0.25 * np.random.default_rng(3).standard_normal(centres.shape)).astype(np.float32)
+    Xd, Cd = torch.from_numpy(X).cuda(), torch.from_numpy(Cc).cuda()
+    out = torch.full((n, k), -1.0, dtype=torch.float32, device="cuda")
+    p = _lib.default_params()
+    p.n_clusters, p.metric = k, (1 if sqrt else 0)
+    _lib.check(lib.cuml_b200_kmeans_transform_f32_i32(h.ptr, C.byref(p), Cd.data_ptr(), Xd.data_ptr(), n, d,
+                                                      out.data_ptr()))
+    h.sync()
+    T = out.cpu().numpy()
+    To = lloyd.transform(X, Cc, sqrt=sqrt)
+    assert np.isfinite(T).all() and (T >= 0).all()
+    scale = To.max()
+    assert np.abs(T - To).max() / scale < (2e-4 if sqrt else 1e-5)
+    assert (T.argmin(1) == To.argmin(1)).mean() >= 0.9999
+
+
 def test_int64_index_overloads(env):
     torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
     from oracle import blobs, lloyd

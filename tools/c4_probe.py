@@ -25,11 +25,11 @@ Xs = X[idx].cpu().numpy(); Cn = Cd.cpu().numpy()
 agree, bad = lloyd.label_disagreements_ok(Xs, Cn, labels[idx].cpu().numpy(), 2.0 ** -20)
 print("label agreement on sample", agree, "inexcusable", bad)
 # transform (squared distances) at the same shape on a slice the output of which fits (n_t x k fp32)
-n_t = 200_000
+n_t = 1_000_000
 out = torch.empty((n_t, k), dtype=torch.float32, device="cuda")
 p = _lib.default_params(); p.n_clusters = k
 torch.cuda.synchronize(); 
-for rep in range(2):
+for rep in range(3):
     t0 = time.perf_counter()
     _lib.check(lib.cuml_b200_kmeans_transform_f32_i64(h.ptr, C.byref(p), Cd.data_ptr(), X.data_ptr(), n_t, d, out.data_ptr()))
     h.sync(); dt = time.perf_counter() - t0
