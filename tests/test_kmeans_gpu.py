@@ -20,7 +20,9 @@ def env():
     import torch
     from cuml_b200 import _lib
     lib = _lib.load()
-    h = _lib.Handle()
+    # cudaStreamLegacy (1): ordered with torch's default stream, so the tensors torch fills or uploads right before
+    # a library call are complete when the library reads them (a library-owned stream would race with them)
+    h = _lib.Handle(stream=1)
     return dict(torch=torch, _lib=_lib, lib=lib, h=h)
 
 
@@ -33,6 +35,7 @@ def _step(env, X, C0, k, engine, w=None):
     labels = torch.zeros(n, dtype=torch.int32, device="cuda")
     packed = torch.zeros(k * d + k + 1, dtype=torch.float64, device="cuda")
     shift = torch.zeros(1, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()   # the handle runs on its own stream: torch's uploads / fills must have landed
     _lib.check(lib.cuml_b200_kmeans_lloyd_step_f32(h.ptr, Xd.data_ptr(), n, d, wd.data_ptr() if w is not None else None,
                                                    k, Cd.data_ptr(), labels.data_ptr(), packed.data_ptr(),
                                                    shift.data_ptr(), engine))
@@ -369,6 +372,7 @@ def test_large_property_checks(env):
     last = None
     for it in range(4):
         C_before = Cd.clone()
+        torch.cuda.synchronize()   # the handle runs on its own stream
         _lib.check(lib.cuml_b200_kmeans_lloyd_step_f32(h.ptr, X.data_ptr(), n, d, None, k, Cd.data_ptr(),
                                                        labels.data_ptr(), packed.data_ptr(), None, 0))
         h.sync()
@@ -413,6 +417,7 @@ def test_full_size_c3_properties(env):
     last = None
     for it in range(3):
         C_before = Cd.clone()
+        torch.cuda.synchronize()   # the handle runs on its own stream: torch's fills / generation must have landed
         _lib.check(lib.cuml_b200_kmeans_lloyd_step_f32(h.ptr, X.data_ptr(), n, d, None, k, Cd.data_ptr(),
                                                        labels.data_ptr(), packed.data_ptr(), None, 0))
         h.sync()
@@ -426,6 +431,7 @@ def test_full_size_c3_properties(env):
         last = packed[-1].item()
         # the E-step is a pure function of (X, C): assigning again with the same centroids gives the same labels
         again = torch.zeros(n, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
         _lib.check(lib.cuml_b200_kmeans_assign_f32(h.ptr, X.data_ptr(), n, d, k, C_before.data_ptr(),
                                                    again.data_ptr(), 0))
         h.sync()
