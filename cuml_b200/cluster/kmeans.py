@@ -232,6 +232,8 @@ class KMeans:
             raise ValueError(f"device_buffer_samples={int(self.device_buffer_samples)} is not supported for the "
                              f"multi-GPU KMeans fit path; set device_buffer_samples=0.")
         self._validate_fit_params()
+        if self._streams_from_host(X):
+            return self._fit_out_of_core(X, sample_weight)
         xin = _as_device_matrix(X)
         Xd = xin.t
         if Xd.shape[0] < 1 or Xd.shape[1] < 1:
@@ -258,6 +260,56 @@ class KMeans:
         self._in_kind = xin.kind
         self.inertia_ = inertia
         self.n_iter_ = n_iter
+        return self
+
+    # ---- out-of-core fit: host X streamed through a device buffer of device_buffer_samples rows -------------
+    def _streams_from_host(self, X):
+        buf = int(self.device_buffer_samples)
+        return (not self._multi_gpu and buf > 0 and isinstance(X, np.ndarray) and X.ndim == 2
+                and X.shape[0] > buf and X.dtype in (np.float32, np.float64))
+
+    def _fit_out_of_core(self, X, sample_weight):
+        """Host-resident X larger than ``device_buffer_samples``: the library walks it batch by batch every
+        iteration (reference host-data path, kmeans_fit.cu:167-231); X is never resident on the device."""
+        torch = _torch()
+        lib = _lib.load()
+        Xh = np.ascontiguousarray(X)
+        n_rows, n_cols = Xh.shape
+        if not np.isfinite(Xh).all():
+            raise ValueError("Input X contains NaN or infinity.")
+        wh = None
+        if sample_weight is not None:
+            wh = np.ascontiguousarray(np.asarray(sample_weight, dtype=Xh.dtype).reshape(-1))
+            if wh.shape[0] != n_rows:
+                raise ValueError("sample_weight.shape == {}, expected {}!".format(wh.shape, (n_rows,)))
+        self.n_features_in_ = n_cols
+        self._validate_fit_row_constraints(n_rows)
+        tdt = torch.float32 if Xh.dtype == np.float32 else torch.float64
+        probe = torch.empty((0, n_cols), dtype=tdt, device=torch.device("cuda", torch.cuda.current_device()))
+        centers = self._prepare_centers(probe)
+        handle = get_handle()
+        params = self._c_params()
+        f32 = Xh.dtype == np.float32
+        fn = getattr(lib, "cuml_b200_kmeans_fit_%s_i64" % ("f32" if f32 else "f64"))
+        inertia = (C.c_float if f32 else C.c_double)()
+        n_iter = C.c_int64()
+        torch.cuda.synchronize()
+        _lib.check(fn(handle.ptr, C.byref(params), Xh.ctypes.data, n_rows, n_cols,
+                      wh.ctypes.data if wh is not None else None, centers.data_ptr(), C.byref(inertia),
+                      C.byref(n_iter)))
+        # labels: predict batch by batch (they do not depend on the weights)
+        buf = int(self.device_buffer_samples)
+        labels = torch.empty(n_rows, dtype=torch.int32, device=centers.device)
+        for s0 in range(0, n_rows, buf):
+            xb = torch.from_numpy(Xh[s0:s0 + buf]).to(centers.device)
+            lb, _ = self._c_predict(handle, params, xb, None, centers, normalize_weights=True)
+            labels[s0:s0 + xb.shape[0]] = lb.to(torch.int32)
+        handle.sync()
+        self._centers = centers
+        self._labels = labels
+        self._in_kind = "numpy"
+        self.inertia_ = float(inertia.value)
+        self.n_iter_ = int(n_iter.value)
         return self
 
     def _c_fit(self, handle, params, X, w, centers):

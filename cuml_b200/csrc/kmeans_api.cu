@@ -6,6 +6,7 @@
 // (kmeans_transform.cu:18-78).  Everything below those shims -- which in the reference is the
 // un-vendored cuVS -- is this library's own CUDA code.
 #include <chrono>
+#include <cstring>
 #include <limits>
 
 #include "lloyd.cuh"
@@ -77,8 +78,8 @@ void stage_parts(Handle& h, const T* const* X_parts, const int64_t* n_parts_rows
     if (on_device) {
       out.parts.push_back(Part<T>{X_parts[i], n, wp});
     } else {
-      // host-resident: staged whole.  (The reference streams device_buffer_samples-sized batches;
-      // out-of-core streaming is a "next" row of the scope table.)
+      // host-resident and within device_buffer_samples (or no buffer size given): staged whole; larger inputs
+      // take fit_streamed() above
       out.owned.emplace_back(static_cast<size_t>(n) * d, h.stream);
       T* dx = out.owned.back().get();
       CB2_CUDA(cudaMemcpyAsync(dx, X_parts[i], sizeof(T) * n * d, cudaMemcpyHostToDevice, h.stream));
@@ -120,6 +121,162 @@ int64_t rank_row_offset(Handle& h, int64_t n_local)
   return off;
 }
 
+// ---- out-of-core fit: host-resident partitions streamed through one device buffer ----------------
+// Role of the reference's host-data path (kmeans_fit.cu:167-231 with host X -> cuVS batched fit,
+// KMeansParams::device_buffer_samples): every Lloyd iteration walks the host partitions in batches of
+// `device_buffer_samples` rows -- H2D copy, E-step, M-step accumulation into the same packed sums -- so X never has
+// to fit device memory.  Seeding (other than init=Array) runs on a strided host sample of at most one buffer
+// (the init_size role).  Copy and kernels share the handle's stream: at 55 GB/s the copy is > 20x the compute, so
+// double buffering would hide < 5 %.
+template <typename T>
+bool fit_streamed(Handle& h, const cuml_b200_kmeans_params_t& params, const T* const* X_parts,
+                  const int64_t* n_parts_rows, int64_t n_parts, int64_t d, const T* const* w_parts, T* centroids,
+                  T& inertia_out, int64_t& n_iter_out)
+{
+  if (params.device_buffer_samples <= 0) return false;
+  int64_t n_local = 0;
+  for (int64_t i = 0; i < n_parts; ++i) {
+    CB2_EXPECTS(n_parts_rows[i] >= 0, "negative partition size");
+    if (n_parts_rows[i] == 0) continue;
+    CB2_EXPECTS(X_parts[i] != nullptr, "null partition pointer");
+    if (is_device_pointer(X_parts[i])) return false;   // device data: nothing to stream
+    n_local += n_parts_rows[i];
+  }
+  if (n_local <= params.device_buffer_samples) return false;   // fits the buffer: staged whole
+  const int k  = params.n_clusters;
+  const int di = static_cast<int>(d);
+  const int64_t batch    = params.device_buffer_samples;
+  const int64_t n_global = allreduce_i64_host(h, n_local);
+  CB2_EXPECTS(n_global >= k, "n_samples=" + std::to_string(n_global) + " should be >= n_clusters=" + std::to_string(k) + ".");
+  bool weighted = false;
+  for (int64_t i = 0; i < n_parts; ++i) weighted = weighted || (w_parts && w_parts[i] && n_parts_rows[i] > 0);
+  double wscale = 1.0;
+  if (weighted) {
+    double ws = 0.0;
+    for (int64_t i = 0; i < n_parts; ++i)
+      for (int64_t r = 0; r < n_parts_rows[i]; ++r) ws += (w_parts && w_parts[i]) ? static_cast<double>(w_parts[i][r]) : 1.0;
+    if (h.n_ranks > 1) {
+      DevBuf<double> cell(1, h.stream);
+      CB2_CUDA(cudaMemcpyAsync(cell.get(), &ws, sizeof(double), cudaMemcpyHostToDevice, h.stream));
+      nccl::allreduce_sum_f64(h, cell.get(), 1);
+      CB2_CUDA(cudaMemcpyAsync(&ws, cell.get(), sizeof(double), cudaMemcpyDeviceToHost, h.stream));
+      CB2_CUDA(cudaStreamSynchronize(h.stream));
+    }
+    CB2_EXPECTS(ws > 0.0, "sample weights must have a positive sum");
+    wscale = static_cast<double>(n_global) / ws;
+  }
+
+  DevBuf<T> xb(static_cast<size_t>(batch) * d, h.stream);
+  DevBuf<T> wb;
+  if (weighted) wb.alloc(static_cast<size_t>(batch), h.stream);
+  std::vector<T> ones;   // partitions without weights inside a weighted fit
+  // copies `rows` rows of partition `pi` starting at `off` into the staging buffer
+  auto stage = [&](int64_t pi, int64_t off, int64_t rows) {
+    CB2_CUDA(cudaMemcpyAsync(xb.get(), X_parts[pi] + off * d, sizeof(T) * rows * d, cudaMemcpyHostToDevice, h.stream));
+    if (weighted) {
+      if (w_parts && w_parts[pi]) {
+        CB2_CUDA(cudaMemcpyAsync(wb.get(), w_parts[pi] + off, sizeof(T) * rows, cudaMemcpyHostToDevice, h.stream));
+      } else {
+        if (ones.size() < static_cast<size_t>(rows)) ones.assign(static_cast<size_t>(batch), T(1));
+        CB2_CUDA(cudaMemcpyAsync(wb.get(), ones.data(), sizeof(T) * rows, cudaMemcpyHostToDevice, h.stream));
+      }
+    }
+  };
+  // calls f(partition, offset, rows) for every batch of this rank, in order
+  auto for_each_batch = [&](auto&& f) {
+    for (int64_t pi = 0; pi < n_parts; ++pi)
+      for (int64_t off = 0; off < n_parts_rows[pi]; off += batch) f(pi, off, std::min(batch, n_parts_rows[pi] - off));
+  };
+
+  std::vector<Part<T>> buf_part{Part<T>{xb.get(), batch, weighted ? wb.get() : nullptr}};
+  LloydSolver<T> solver(h, buf_part, di, k, ENGINE_AUTO);
+
+  // seeding sample: up to one buffer of rows taken at a fixed stride over this rank's partitions
+  const int64_t n_seed = std::min<int64_t>(n_local, batch);
+  DevBuf<T> seed_x, seed_w;
+  if (params.init != CUML_B200_INIT_Array) {
+    std::vector<T> hx(static_cast<size_t>(n_seed) * d), hw(weighted ? static_cast<size_t>(n_seed) : 0);
+    const double stride = static_cast<double>(n_local) / static_cast<double>(n_seed);
+    int64_t pi = 0, base = 0;
+    for (int64_t s_i = 0; s_i < n_seed; ++s_i) {
+      const int64_t g = std::min<int64_t>(n_local - 1, static_cast<int64_t>(s_i * stride));
+      while (g >= base + n_parts_rows[pi]) base += n_parts_rows[pi++];
+      std::memcpy(hx.data() + static_cast<size_t>(s_i) * d, X_parts[pi] + (g - base) * d, sizeof(T) * d);
+      if (weighted) hw[s_i] = (w_parts && w_parts[pi]) ? w_parts[pi][g - base] : T(1);
+    }
+    seed_x.alloc(hx.size(), h.stream);
+    CB2_CUDA(cudaMemcpyAsync(seed_x.get(), hx.data(), sizeof(T) * hx.size(), cudaMemcpyHostToDevice, h.stream));
+    if (weighted) {
+      seed_w.alloc(hw.size(), h.stream);
+      CB2_CUDA(cudaMemcpyAsync(seed_w.get(), hw.data(), sizeof(T) * hw.size(), cudaMemcpyHostToDevice, h.stream));
+    }
+    CB2_CUDA(cudaStreamSynchronize(h.stream));   // hx / hw go out of scope
+  }
+  const int64_t seed_global = (params.init != CUML_B200_INIT_Array) ? allreduce_i64_host(h, n_seed) : 0;
+  std::vector<Part<T>> seed_parts{Part<T>{seed_x.get(), n_seed, weighted ? seed_w.get() : nullptr}};
+  SeedContext<T> sctx{h, seed_parts, di, n_seed, seed_global,
+                      (params.init != CUML_B200_INIT_Array) ? rank_row_offset(h, n_seed) : 0, params.rng_seed, ENGINE_AUTO};
+
+  double* packed     = solver.packed();
+  const size_t count = solver.packed_count();
+  const int n_init   = (params.init == CUML_B200_INIT_Array) ? 1 : params.n_init;
+  DevBuf<T> trial(static_cast<size_t>(k) * di, h.stream);
+  double best_inertia = std::numeric_limits<double>::infinity();
+  int64_t best_iter   = 0;
+  for (int run = 0; run < n_init; ++run) {
+    T* C = (n_init == 1) ? centroids : trial.get();
+    sctx.seed = params.rng_seed + 0x9E3779B97F4A7C15ull * static_cast<uint64_t>(run);
+    if (params.init == CUML_B200_INIT_Random) init_random<T>(sctx, k, C);
+    else if (params.init != CUML_B200_INIT_Array && params.oversampling_factor == 0.0) init_kmeans_plus_plus<T>(sctx, k, C);
+    else if (params.init != CUML_B200_INIT_Array) init_scalable<T>(sctx, params, C);
+    int64_t iters = 0;
+    while (iters < params.max_iter) {
+      solver.prepare(C);
+      bool first = true;
+      for_each_batch([&](int64_t pi, int64_t off, int64_t rows) {
+        stage(pi, off, rows);
+        solver.set_rows(rows);
+        solver.assign_one(C, xb.get(), rows, solver.labels(0));
+        solver.accumulate(C, false, !first);
+        first = false;
+      });
+      nccl::allreduce_sum_f64(h, packed, count);
+      finalize_centroids<T>(h, packed, C, k, di, packed + count);
+      ++iters;
+      if (params.tol > 0.0) {
+        CB2_CUDA(cudaMemcpyAsync(h.pinned, packed + count, sizeof(double), cudaMemcpyDeviceToHost, h.stream));
+        CB2_CUDA(cudaStreamSynchronize(h.stream));
+        if (h.pinned[0] < params.tol) break;
+      }
+    }
+    // final pass: labels and cost with the final centroids
+    solver.prepare(C);
+    bool first = true;
+    for_each_batch([&](int64_t pi, int64_t off, int64_t rows) {
+      stage(pi, off, rows);
+      solver.set_rows(rows);
+      solver.assign_one(C, xb.get(), rows, solver.labels(0));
+      solver.inertia_only(C, !first);
+      first = false;
+    });
+    double* cell = packed + count - 1;
+    nccl::allreduce_sum_f64(h, cell, 1);
+    CB2_CUDA(cudaMemcpyAsync(h.pinned, cell, sizeof(double), cudaMemcpyDeviceToHost, h.stream));
+    CB2_CUDA(cudaStreamSynchronize(h.stream));
+    const double inertia = h.pinned[0] * wscale;
+    if (inertia < best_inertia || run == 0) {
+      best_inertia = inertia;
+      best_iter    = iters;
+      if (C != centroids)
+        CB2_CUDA(cudaMemcpyAsync(centroids, C, sizeof(T) * k * di, cudaMemcpyDeviceToDevice, h.stream));
+    }
+  }
+  CB2_CUDA(cudaStreamSynchronize(h.stream));
+  inertia_out = static_cast<T>(best_inertia);
+  n_iter_out  = best_iter;
+  return true;
+}
+
 template <typename T>
 void fit_parts_impl(Handle& h, const cuml_b200_kmeans_params_t& params, const T* const* X_parts,
                     const int64_t* n_parts_rows, int64_t n_parts, int64_t d, const T* const* w_parts, T* centroids,
@@ -132,6 +289,7 @@ void fit_parts_impl(Handle& h, const cuml_b200_kmeans_params_t& params, const T*
   const int k  = params.n_clusters;
   const int di = static_cast<int>(d);
 
+  if (fit_streamed<T>(h, params, X_parts, n_parts_rows, n_parts, d, w_parts, centroids, inertia_out, n_iter_out)) return;
   // CUML_B200_TRACE=1: host-timed phases (adds stream synchronisations; measurement aid only)
   static const bool trace = std::getenv("CUML_B200_TRACE") != nullptr;
   auto tnow = [&] {

@@ -39,6 +39,7 @@ class LloydSolver {
     engine      = engine_from_env(engine);
     n_local_    = 0;
     int64_t nmx = 0;
+    capacity_   = parts_.empty() ? 0 : parts_[0].n;
     bool aligned = true;
     for (auto& p : parts_) {
       n_local_ += p.n;
@@ -112,12 +113,13 @@ class LloydSolver {
   // M-step accumulation over all partitions using the current labels: packed = S | W | inertia.
   // The inertia cell (wrt C, exact difference form) is only filled when with_inertia is set; the
   // Lloyd loop itself does not need it (the stopping rule is the centroid shift).
-  void accumulate(const T* C, bool with_inertia)
+  // `into`: add to what packed already holds (out-of-core batches of one iteration)
+  void accumulate(const T* C, bool with_inertia, bool into = false)
   {
     EventPair ev{};
     if (h_.timing) ev = h_.begin_event();
     double* inertia_cell = packed_.get() + packed_count() - 1;
-    if (parts_.empty()) CB2_CUDA(cudaMemsetAsync(packed_.get(), 0, packed_count() * sizeof(double), h_.stream));
+    if (parts_.empty() && !into) CB2_CUDA(cudaMemsetAsync(packed_.get(), 0, packed_count() * sizeof(double), h_.stream));
     bool need_separate_inertia = with_inertia;
     if (use_tma_update_) {
       if constexpr (std::is_same<T, float>::value) {
@@ -127,26 +129,35 @@ class LloydSolver {
           cls_map = tma_update_balance(h_, packed_.get() + static_cast<size_t>(k_) * d_, d_, k_, cls_map_);
         for (size_t i = 0; i < parts_.size(); ++i)
           tma_update_accumulate(h_, parts_[i].X, parts_[i].n, d_, labels(i), parts_[i].w, k_, tma_S_, tma_W_,
-                                packed_.get(), i != 0, cls_map);
+                                packed_.get(), i != 0 || into, cls_map);
         have_weights_ = true;
       }
-      if (!with_inertia) CB2_CUDA(cudaMemsetAsync(inertia_cell, 0, sizeof(double), h_.stream));
+      if (!with_inertia && !into) CB2_CUDA(cudaMemsetAsync(inertia_cell, 0, sizeof(double), h_.stream));
     } else {
       for (size_t i = 0; i < parts_.size(); ++i)
         update_accumulate<T>(h_, ws_, parts_[i].X, parts_[i].n, d_, labels(i), parts_[i].w, C, k_, packed_.get(),
-                             i != 0, true);
+                             i != 0 || into, true);
       need_separate_inertia = false;  // the generic kernel produces it in the same pass
     }
-    if (need_separate_inertia) inertia_only(C);
+    if (need_separate_inertia) inertia_only(C, into);
     if (h_.timing) h_.end_event(ev, false);
   }
 
-  void inertia_only(const T* C)
+  void inertia_only(const T* C, bool into = false)
   {
     double* inertia_cell = packed_.get() + packed_count() - 1;
-    if (parts_.empty()) CB2_CUDA(cudaMemsetAsync(inertia_cell, 0, sizeof(double), h_.stream));
+    if (parts_.empty() && !into) CB2_CUDA(cudaMemsetAsync(inertia_cell, 0, sizeof(double), h_.stream));
     for (size_t i = 0; i < parts_.size(); ++i)
-      compute_inertia<T>(h_, parts_[i].X, parts_[i].n, d_, labels(i), parts_[i].w, C, inertia_cell, i != 0);
+      compute_inertia<T>(h_, parts_[i].X, parts_[i].n, d_, labels(i), parts_[i].w, C, inertia_cell, i != 0 || into);
+  }
+
+  // out-of-core use: the single partition is a device staging buffer whose fill level changes per batch
+  // (n must not exceed the row count the solver was built with)
+  void set_rows(int64_t n)
+  {
+    CB2_EXPECTS(parts_.size() == 1 && n >= 0 && n <= capacity_, "set_rows: single-partition solver, n within capacity");
+    parts_[0].n = n;
+    n_local_    = n;
   }
 
   // One full Lloyd iteration, centroids updated in place; squared shift left at packed[count]
@@ -193,6 +204,7 @@ class LloydSolver {
   std::vector<Part<T>> parts_;
   int d_, k_;
   int64_t n_local_ = 0;
+  int64_t capacity_ = 0;
   bool use_tc_     = false;
   bool use_tma_update_ = false;
   std::vector<int64_t> label_off_;

@@ -67,7 +67,7 @@ typedef struct cuml_b200_kmeans_params {
   int32_t  batch_samples;         /* = 1<<15 (accepted; tiling is chosen by the engine)      */
   int32_t  batch_centroids;       /* = 0                                                     */
   int64_t  init_size;             /* = 0                                                     */
-  int64_t  device_buffer_samples; /* = 0; host partitions are streamed in batches this big   */
+  int64_t  device_buffer_samples; /* = 0; > 0: host partitions with more rows are streamed in batches this big */
 } cuml_b200_kmeans_params_t;
 
 CUML_B200_API void cuml_b200_kmeans_params_default(cuml_b200_kmeans_params_t* p);

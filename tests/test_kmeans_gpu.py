@@ -273,6 +273,76 @@ def test_host_pointer_fit_through_c_abi(env):
     assert np.array_equal(outs[0][0], outs[1][0]) and outs[0][1] == outs[1][1]
 
 
+@pytest.mark.parametrize("weighted", [False, True])
+def test_out_of_core_host_fit_equals_in_core(env, weighted):
+    # host X larger than device_buffer_samples is streamed batch by batch every iteration (reference host-data path,
+    # kmeans_fit.cu:167-231 + KMeansParams::device_buffer_samples); two ragged host partitions, partial last batches
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    from oracle import blobs, lloyd
+    n, d, k = 20000, 32, 16
+    X, centres, _ = blobs.make_blobs(n, d, k)
+    init = blobs.parity_init(centres)
+    w = np.random.default_rng(9).uniform(0.5, 2.0, n).astype(np.float32) if weighted else None
+    cut = 7001
+    parts = [np.ascontiguousarray(X[:cut]), np.ascontiguousarray(X[cut:])]
+    wparts = [np.ascontiguousarray(w[:cut]), np.ascontiguousarray(w[cut:])] if weighted else None
+    outs = []
+    for buf in (0, 3000):
+        p = _lib.default_params()
+        p.n_clusters, p.init, p.max_iter, p.tol, p.device_buffer_samples = k, _lib.INIT_ARRAY, 5, 0.0, buf
+        Cd = torch.from_numpy(init).cuda()
+        torch.cuda.synchronize()
+        xp = (C.c_void_p * 2)(*[a.ctypes.data for a in parts])
+        rows = (C.c_int64 * 2)(*[a.shape[0] for a in parts])
+        wp = (C.c_void_p * 2)(*[a.ctypes.data for a in wparts]) if weighted else None
+        inertia, it = C.c_float(), C.c_int64()
+        _lib.check(lib.cuml_b200_kmeans_fit_parts_f32(h.ptr, C.byref(p), xp, rows, 2, d, wp, Cd.data_ptr(),
+                                                      C.byref(inertia), C.byref(it)))
+        outs.append((Cd.cpu().numpy(), inertia.value, it.value))
+    (c0, i0, n0), (c1, i1, n1) = outs
+    assert n0 == n1 == 5
+    assert np.abs(c0 - c1).max() / np.abs(c0).max() < 1e-6
+    assert abs(i0 - i1) / i0 < 1e-6
+    ref = lloyd.fit(X, init, max_iter=5, tol=0.0, sample_weight=w)
+    assert np.abs(c1 - ref["centroids"]).max() / np.abs(ref["centroids"]).max() < 1e-4
+    assert abs(i1 - ref["inertia"]) / ref["inertia"] < 1e-5
+
+
+def test_estimator_out_of_core_matches_in_core():
+    # Python surface of the same path: host numpy X larger than device_buffer_samples never becomes device-resident
+    from cuml_b200.cluster import KMeans
+    from oracle import blobs
+    X, centres, _ = blobs.make_blobs(20000, 32, 16)
+    init = blobs.parity_init(centres)
+    w = np.random.default_rng(2).uniform(0.5, 2.0, len(X)).astype(np.float32)
+    a = KMeans(n_clusters=16, init=init, max_iter=6, tol=0.0, n_init=1).fit(X, sample_weight=w)
+    b = KMeans(n_clusters=16, init=init, max_iter=6, tol=0.0, n_init=1, device_buffer_samples=3000).fit(X, sample_weight=w)
+    assert b.n_iter_ == a.n_iter_ == 6
+    assert np.abs(a.cluster_centers_ - b.cluster_centers_).max() / np.abs(a.cluster_centers_).max() < 1e-6
+    assert abs(a.inertia_ - b.inertia_) / a.inertia_ < 1e-5
+    assert np.array_equal(a.labels_, b.labels_)
+    assert np.array_equal(b.predict(X[:500]), a.predict(X[:500]))
+
+
+def test_out_of_core_seeded_fit(env):
+    # k-means|| seeding on the strided host sample + streamed Lloyd iterations recover the blobs
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    from oracle import blobs, lloyd
+    from sklearn.metrics import adjusted_rand_score
+    n, d, k = 30000, 16, 8
+    X, centres, y = blobs.make_blobs(n, d, k)
+    p = _lib.default_params()
+    p.n_clusters, p.init, p.max_iter, p.tol, p.device_buffer_samples = k, _lib.INIT_KMEANS_PLUS_PLUS, 30, 1e-6, 4096
+    p.rng_seed = 7
+    Cd = torch.zeros((k, d), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()
+    inertia, it = C.c_float(), C.c_int32()
+    _lib.check(lib.cuml_b200_kmeans_fit_f32_i32(h.ptr, C.byref(p), X.ctypes.data, n, d, None, Cd.data_ptr(),
+                                                C.byref(inertia), C.byref(it)))
+    lab, _ = lloyd.predict(X, Cd.cpu().numpy())
+    assert adjusted_rand_score(y, lab) >= 0.99
+
+
 def test_partition_list_fit_equals_single_array(env):
     # the partition overload (reference kmeans.hpp:110-130) over ragged + empty partitions
     torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
