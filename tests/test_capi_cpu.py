@@ -112,3 +112,19 @@ def test_mg_random_init_split_rule():
     est.validate(np.zeros((4, 2)), 0, 4)
     b = [shard_bounds(10, r, 4) for r in range(4)]
     assert b == [(0, 3), (3, 6), (6, 8), (8, 10)]
+
+
+def test_out_of_core_dispatch_predicate():
+    # the estimator streams only host numpy fp32/fp64 matrices with more rows than device_buffer_samples
+    import numpy as np
+    from cuml_b200.cluster import KMeans
+    from cuml_b200.cluster.kmeans_mg import KMeansMG
+    X = np.zeros((20, 3), np.float32)
+    assert KMeans(device_buffer_samples=10)._streams_from_host(X)
+    assert not KMeans(device_buffer_samples=0)._streams_from_host(X)
+    assert not KMeans(device_buffer_samples=20)._streams_from_host(X)          # fits the buffer: staged whole
+    assert not KMeans(device_buffer_samples=10)._streams_from_host(X.astype(np.int32))
+    assert not KMeans(device_buffer_samples=10)._streams_from_host(X.tolist())
+    assert KMeans(device_buffer_samples=10)._streams_from_host(X.astype(np.float64))
+    assert KMeansMG._multi_gpu and not KMeans._multi_gpu
+
