@@ -343,9 +343,45 @@ class KMeans:
     def fit_predict(self, X, y=None, sample_weight=None):
         return self.fit(X, sample_weight=sample_weight).labels_
 
+    def _predict_host_chunked(self, X, sample_weight=None):
+        """Host X larger than ``device_buffer_samples``: predict chunk by chunk (reference
+        ``_kmeans_predict_host_chunked``, kmeans.pyx:356-434).  Weights are normalised once over the whole input
+        (sum(w) == n_samples), each chunk is then predicted with ``normalize_weights=False`` and the chunk
+        inertias add up."""
+        torch = _torch()
+        Xh = np.ascontiguousarray(X)
+        n_rows, n_cols = Xh.shape
+        if n_cols != self._centers.shape[1]:
+            raise ValueError(f"X has {n_cols} features, but KMeans is expecting "
+                             f"{self._centers.shape[1]} features as input.")
+        dev, tdt = self._centers.device, self._centers.dtype
+        wh = None
+        if sample_weight is not None:
+            wh = np.asarray(sample_weight, dtype=np.float64).reshape(-1)
+            if wh.shape[0] != n_rows:
+                raise ValueError("sample_weight.shape == {}, expected {}!".format(wh.shape, (n_rows,)))
+            wh = wh * (n_rows / wh.sum())
+        handle = get_handle()
+        params = self._c_params()
+        buf = int(self.device_buffer_samples)
+        labels = torch.empty(n_rows, dtype=torch.int32, device=dev)
+        inertia = 0.0
+        for s0 in range(0, n_rows, buf):
+            xb = torch.from_numpy(Xh[s0:s0 + buf]).to(device=dev, dtype=tdt)
+            wb = None
+            if wh is not None:
+                wb = torch.from_numpy(np.ascontiguousarray(wh[s0:s0 + buf])).to(device=dev, dtype=tdt)
+            lb, ib = self._c_predict(handle, params, xb, wb, self._centers, normalize_weights=False)
+            labels[s0:s0 + xb.shape[0]] = lb.to(torch.int32)
+            inertia += ib
+        handle.sync()
+        return self._out(labels, "numpy"), inertia
+
     def _predict_labels_inertia(self, X, sample_weight=None):
         torch = _torch()
         self._check_is_fitted()
+        if self._streams_from_host(X):
+            return self._predict_host_chunked(X, sample_weight)
         xin = _as_device_matrix(X, dtype=self._centers.dtype, device=self._centers.device)
         if xin.t.shape[1] != self._centers.shape[1]:
             raise ValueError(f"X has {xin.t.shape[1]} features, but KMeans is expecting "

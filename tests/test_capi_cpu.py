@@ -128,3 +128,46 @@ def test_out_of_core_dispatch_predicate():
     assert KMeans(device_buffer_samples=10)._streams_from_host(X.astype(np.float64))
     assert KMeansMG._multi_gpu and not KMeans._multi_gpu
 
+
+
+def test_chunked_host_predict_logic(monkeypatch):
+    # the chunk loop of the estimator's host predict (reference _kmeans_predict_host_chunked, kmeans.pyx:356-434)
+    # with the C call replaced by a numpy nearest-centre: labels are stitched in order, weights are normalised once
+    # over the whole input and the chunk inertias add up
+    import numpy as np
+    import torch
+    from cuml_b200.cluster import kmeans as km_mod
+    from cuml_b200.cluster import KMeans
+
+    rng = np.random.default_rng(0)
+    X = rng.standard_normal((1000, 5)).astype(np.float32)
+    Cc = rng.standard_normal((7, 5)).astype(np.float32)
+    w = rng.uniform(0.5, 2.0, 1000)
+    calls = []
+
+    def fake_predict(self, handle, params, Xb, wb, centers, normalize_weights=True):
+        assert normalize_weights is False
+        x, c = Xb.numpy().astype(np.float64), centers.numpy().astype(np.float64)
+        d2 = ((x[:, None, :] - c[None, :, :]) ** 2).sum(2)
+        lab = d2.argmin(1)
+        ww = np.ones(len(x)) if wb is None else wb.numpy().astype(np.float64)
+        calls.append(len(x))
+        return torch.from_numpy(lab.astype(np.int32)), float((ww * d2[np.arange(len(x)), lab]).sum())
+
+    class FakeHandle:
+        def sync(self):
+            pass
+
+    monkeypatch.setattr(KMeans, "_c_predict", fake_predict)
+    monkeypatch.setattr(KMeans, "_c_params", lambda self: None)
+    monkeypatch.setattr(km_mod, "get_handle", lambda: FakeHandle())
+    est = KMeans(n_clusters=7, device_buffer_samples=300)
+    est._centers = torch.from_numpy(Cc)
+    est._in_kind = "numpy"
+    labels, inertia = est._predict_labels_inertia(X, sample_weight=w)
+    d2 = ((X[:, None, :].astype(np.float64) - Cc[None].astype(np.float64)) ** 2).sum(2)
+    assert calls == [300, 300, 300, 100]
+    assert np.array_equal(np.asarray(labels), d2.argmin(1))
+    wn = w * (len(X) / w.sum())
+    assert abs(inertia - (wn * d2.min(1)).sum()) / inertia < 1e-6
+
