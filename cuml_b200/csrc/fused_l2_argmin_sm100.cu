@@ -512,7 +512,10 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
 // rounding lo and hi to bf16 perturbs each correction by <= 2^-9 relative: ~2^-20 |x||c| per product -- the size of
 // the lo.lo term every 3xTF32 scheme drops.  Operand slot layout per 32-feature K-block:
 //   [0, 16 KB) hi tf32, 128B swizzle | [16 KB, 24 KB) hi bf16, 64B swizzle | [24 KB, 32 KB) lo bf16, 64B swizzle
-template <bool BF16C, bool DIST = false>
+// TRUNC (opt-in experiment, CUML_B200_CONV_TRUNC=1): hi = x truncated to tf32, which is what the tensor core reads
+// from the raw fp32 tile anyway, so the converter neither rounds nor rewrites the tile (fewer instructions on the
+// issue-bound d = 64 path) at the price of |lo| <= 2^-11 |x| instead of 2^-12.
+template <bool BF16C, bool DIST = false, bool TRUNC = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                             const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_lb,
@@ -695,7 +698,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
           for (int i = 0; i < CPT; ++i) {
             const int e = ct + i * 256;
             uint4 h, l;
-            if (BF16C) {   // nearest tf32 (ties away from zero): |lo| <= 2^-12 |x|
+            if (BF16C && !TRUNC) {   // nearest tf32 (ties away from zero): |lo| <= 2^-12 |x|
               h.x = (v[i].x + 0x1000u) & 0xffffe000u;
               h.y = (v[i].y + 0x1000u) & 0xffffe000u;
               h.z = (v[i].z + 0x1000u) & 0xffffe000u;
@@ -707,7 +710,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
             l.y = __float_as_uint(__uint_as_float(v[i].y) - __uint_as_float(h.y));
             l.z = __float_as_uint(__uint_as_float(v[i].z) - __uint_as_float(h.z));
             l.w = __float_as_uint(__uint_as_float(v[i].w) - __uint_as_float(h.w));
-            hi[e] = h;
+            if (!TRUNC) hi[e] = h;
             if (BF16C) {
               // 4 features -> 8 bytes of the 64-byte bf16 row (64B swizzle: 16-byte chunk ^= (row / 2) % 4)
               const uint32_t off = conv_off + static_cast<uint32_t>(i) * (32u * 64u);
@@ -1563,6 +1566,8 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                   static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(h.smem_optin)));
     attr_set = true;
   }
   EventPair ev{};
@@ -1585,7 +1590,11 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       CUtensorMap tm_lb = make_map_2d(cen.lb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
                                       b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-      fused_l2_argmin_2cta_kernel<true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+      static const bool conv_trunc = std::getenv("CUML_B200_CONV_TRUNC") && std::atoi(std::getenv("CUML_B200_CONV_TRUNC")) != 0;
+      if (conv_trunc)
+        fused_l2_argmin_2cta_kernel<true, false, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+      else
+        fused_l2_argmin_2cta_kernel<true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
     } else if (dist) {
       fused_l2_argmin_2cta_kernel<false, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     } else {
