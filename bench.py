@@ -292,7 +292,7 @@ def run_ours(args):
         # kernel with bf16 correction terms issues 1 tf32 + 2 bf16 MMAs: time per product = 1/(bf16/2) + 2/bf16, so
         # peak(2nkd) = bf16/4 (the denominator is larger, the fraction therefore lower, than under the 3xTF32 rule).
         variant = int(lib.cuml_b200_kmeans_estep_variant(h.ptr, d, k))
-        mma_cost = 4.0 if variant == 3 else 6.0
+        mma_cost = 4.0 if variant in (3, 5) else 6.0
         tf_peak = peaks["bf16_tflops_sustained"] / mma_cost
         # which roofline binds the fused kernel: time at the tensor peak vs time at the HBM peak
         tensor_bound = (flop / (tf_peak * 1e12)) >= (fused_bytes / (peaks["hbm_gbs"] * 1e9))
@@ -303,7 +303,8 @@ def run_ours(args):
             roof = {"bound": "hbm", "achieved": gb_achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                     "frac": (gb_achieved / peaks["hbm_gbs"]) if gb_achieved else None}
         variant_name = {0: "CUDA-core fp32", 1: "tcgen05 1-CTA 3xTF32", 2: "tcgen05 CTA-pair 3xTF32",
-                        3: "tcgen05 CTA-pair tf32 + 2 bf16 correction terms", 4: "tcgen05 A-in-TMEM 3xTF32"}[variant]
+                        3: "tcgen05 CTA-pair tf32 + 2 bf16 correction terms", 4: "tcgen05 A-in-TMEM 3xTF32",
+                        5: "tcgen05 1-CTA tf32 + 2 bf16 correction terms"}[variant]
         roof.update({
             "traffic": TRAFFIC_NCU.get(args.workload) if world == 1 and not args.n else None,
             "kernel": f"fused_l2_argmin ({variant_name}: distance + argmin)", "kernel_ms": fused_ms,
@@ -312,7 +313,7 @@ def run_ours(args):
             "issued_mma_products_per_algorithmic": 3,
             "hbm_gbs_fused": gb_achieved,
             "peak_note": f"{peaks['source']}: tensor peak = bf16_tflops_sustained / {mma_cost:g} "
-                         f"({'1 tf32 + 2 bf16 MMAs' if variant == 3 else '3 tf32 MMAs'} per algorithmic product, "
+                         f"({'1 tf32 + 2 bf16 MMAs' if variant in (3, 5) else '3 tf32 MMAs'} per algorithmic product, "
                          f"tf32 = bf16/2); hbm peak = hbm_gbs (copy)",
             "update_kernel": "accumulate_owner (TMA ring, label-class ownership) + reduce_partials",
             "update_kernel_ms": update_ms,

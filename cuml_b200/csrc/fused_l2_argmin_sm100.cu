@@ -122,7 +122,7 @@ struct Barriers {
 // accumulator tile (BN/4 columns, at least one 32-column chunk); thread = row.  Per row: four independent
 // running (min, argmin) chains, merged with the first-minimum rule; the column parts are merged through
 // shared memory.  The argmin is instruction-issue bound (4 instructions per distance), hence many warps.
-template <bool PAIR, bool DIST = false>
+template <bool PAIR, bool DIST = false, bool FOLD1 = false>
 __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* bars, float* cn_s, float* mrg_v,
                                               int* mrg_i, uint32_t tmem_base, int64_t first_row, int64_t row_stride,
                                               int64_t n_tiles_cta)
@@ -149,7 +149,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
   // latency never sits on the epilogue's critical path
   float pre = 0.f;
   auto fetch_cn = [&](int nt) { pre = __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + (et < p.bn ? et : 0)); };
-  const bool fold = PAIR && p.fold;   // accumulator already holds x.c - 1/2||c||^2: pick the maximum
+  const bool fold = (PAIR || FOLD1) && p.fold;   // accumulator already holds x.c - 1/2||c||^2: pick the maximum
   if (!fold) fetch_cn(0);
   if (p.k_tiles == 1 && !fold) {  // single centroid tile: stage the half norms once
     if (et < p.bn) cn_s[et] = pre;
@@ -829,6 +829,320 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   if (warp == 1) ptx::tmem_dealloc_2cta(tmem_base, p.tmem_cols);
 }
 
+// Single-CTA twin of the CTA-pair kernel (opt-in, CUML_B200_SOLO_V2=1; NOT yet validated on hardware): the same
+// roles, bf16 correction terms and folded half norms for k <= 128, with cta_group::1 instructions and local
+// barriers.  Generated from the pair kernel's source; once measured it is meant to replace fused_l2_argmin_kernel.
+template <bool BF16C, bool DIST = false, bool TRUNC = false>
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
+                            const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_lb,
+                            const __grid_constant__ CUtensorMap tm_cn, const FusedParams p)
+{
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t raw_base = ptx::smem_u32(smem_dyn);
+  const uint32_t base     = (raw_base + 1023u) & ~1023u;
+  uint8_t* gbase          = smem_dyn + (base - raw_base);
+
+  const uint32_t cta_rank = 0;
+  const bool leader       = cta_rank == 0;
+  const int64_t pair      = blockIdx.x;
+  const int64_t n_pairs   = gridDim.x;
+  const int half_n        = p.bn;                                       // centroid rows held by this CTA (all)
+
+  const uint32_t b_half_bytes  = static_cast<uint32_t>(half_n) * 128u;   // hi (or lo) rows of this CTA
+  const uint32_t b_stage_bytes = 2u * b_half_bytes;                     // hi then lo
+  const uint32_t a_base  = base;
+  const uint32_t b_base  = a_base + p.a_slots * A_SLOT_BYTES;
+  // fold tiles (p.fold): ones [128 rows x 8 tf32] then one [half_n rows x 8 tf32] tile of half-norm pieces per
+  // centroid tile, 32-byte rows, 4 KB each
+  constexpr uint32_t FOLD_TILE = TILE_M * 32u;
+  const uint32_t fold_off = p.a_slots * A_SLOT_BYTES + p.b_stages * b_stage_bytes;
+  const uint32_t fold_u32 = base + fold_off;
+  const uint32_t cn_off   = fold_off + (p.fold ? (1u + p.k_tiles) * FOLD_TILE : 0u);
+  float* cn_s            = reinterpret_cast<float*>(gbase + cn_off);    // [2][bn]
+  float* mrg_v           = cn_s + 2 * p.bn;                              // [128] epilogue half merge
+  int* mrg_i             = reinterpret_cast<int*>(mrg_v + 3 * TILE_M);   // [3][128]
+  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 6u * TILE_M * 4u);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_A_SLOTS; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->a_raw_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->a_ready[s]), 8);     // 8 converter warps
+      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), 1);
+    }
+    for (int s = 0; s < MAX_ACC; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 16);  // 16 epilogue warps
+    }
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);      // leader's copy: expect_tx covers both CTAs
+      ptx::mbar_init(ptx::smem_u32(&bars->b_empty[s]), 1);
+    }
+    ptx::mbar_init(ptx::smem_u32(&bars->cn_full), 1);
+    ptx::fence_barrier_init();
+  }
+  if (p.fold) {   // all-ones A tile (identical 16-byte chunks: the 32B swizzle does not matter)
+    float* ones = reinterpret_cast<float*>(gbase + fold_off);
+    for (int i = threadIdx.x; i < TILE_M * 8; i += blockDim.x) ones[i] = 1.0f;
+    ptx::fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_x);
+    ptx::prefetch_tmap(&tm_hi);
+    ptx::prefetch_tmap(&tm_lo);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int64_t pair_tiles = p.m_tiles;             // 128-row tiles
+
+  if (warp == 0) {
+    // ===================== X producer (own 128 rows) =====================
+    {
+      uint32_t a_cnt = 0;
+      Ring ra;
+      const int a_reps = p.a_stream ? p.k_tiles : 1;
+      for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
+        const int32_t row0 = static_cast<int32_t>(pt * TILE_M);
+        // L2 prefetch of the row tile p.l2_ahead rounds ahead: the shared-memory ring only holds ~2 row tiles, too
+        // few to cover the ~1.5 us HBM latency; with the tile already in L2 the ring turns around in time
+        if (p.l2_ahead > 0) {
+          const int64_t pf = pt + static_cast<int64_t>(p.l2_ahead) * n_pairs;
+          if (pf < pair_tiles && ptx::elect_one()) {
+            const int32_t prow = static_cast<int32_t>(pf * TILE_M);
+            for (int kbi = 0; kbi < p.kb; ++kbi) ptx::tma_prefetch_l2_2d(&tm_x, kbi * KBLOCK, prow);
+          }
+          __syncwarp();
+        }
+        for (int rep = 0; rep < a_reps; ++rep)
+        for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
+          const uint32_t sa = ra.slot, pa = ra.phase;
+          ra.advance(p.a_slots);
+          ptx::mbar_wait_park(ptx::smem_u32(&bars->a_empty[sa]), pa ^ 1u);
+          if (ptx::elect_one()) {
+            const uint32_t full = ptx::smem_u32(&bars->a_raw_full[sa]);
+            ptx::mbar_arrive_expect_tx(full, KBLOCK_BYTES);
+            ptx::tma_load_2d_hint(a_base + sa * A_SLOT_BYTES, &tm_x, kbi * KBLOCK, row0, full, ptx::kEvictFirst);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================== centroid producer (own half of every block) =====================
+    {
+      uint32_t b_cnt = 0;
+      Ring rb;
+      if (p.fold && pair < pair_tiles) {
+        // half-norm pieces of every centroid tile (this CTA's half of the rows), resident for the whole kernel
+        if (ptx::elect_one()) {
+          const uint32_t full_local  = ptx::smem_u32(&bars->cn_full);
+          const uint32_t full_leader = full_local;
+          ptx::mbar_arrive_expect_tx(full_local, static_cast<uint32_t>(p.k_tiles) * static_cast<uint32_t>(half_n) * 32u);
+          for (int nt = 0; nt < p.k_tiles; ++nt)
+            ptx::tma_load_2d_hint(fold_u32 + (1u + nt) * FOLD_TILE, &tm_cn, 0,
+                                  nt * p.bn + static_cast<int32_t>(cta_rank) * half_n, full_leader, ptx::kEvictLast);
+        }
+        __syncwarp();
+      }
+      for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
+        if (p.b_resident && pt != pair) break;
+        for (int nt = 0; nt < p.k_tiles; ++nt) {
+          for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
+            const uint32_t sb = rb.slot, pb = rb.phase;
+            rb.advance(p.b_stages);
+            ptx::mbar_wait_park(ptx::smem_u32(&bars->b_empty[sb]), pb ^ 1u);
+            if (ptx::elect_one()) {
+              const uint32_t full_local  = ptx::smem_u32(&bars->b_full[sb]);
+              const uint32_t full_leader = full_local;
+              ptx::mbar_arrive_expect_tx(full_local, b_stage_bytes);
+              const uint32_t dst = b_base + sb * b_stage_bytes;
+              const int32_t crow = nt * p.bn + static_cast<int32_t>(cta_rank) * half_n;
+              ptx::tma_load_2d_hint(dst, &tm_hi, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+              if (BF16C) {   // tm_lo = bf16 hi, tm_lb = bf16 lo: two half-size tiles
+                ptx::tma_load_2d_hint(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+                ptx::tma_load_2d_hint(dst + b_half_bytes + b_half_bytes / 2, &tm_lb, kbi * KBLOCK, crow, full_leader,
+                                      ptx::kEvictLast);
+              } else {
+                ptx::tma_load_2d_hint(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
+              }
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if ((warp >= 4 && warp < 8) || warp >= 24) {
+    // ===================== converter (8 warps: 4..7 and 24..27) =====================
+    const int ct = warp >= 24 ? threadIdx.x - 768 + 128 : threadIdx.x - 128;   // 0..255
+    // this thread's chunks are ct + 256 i: 32 rows apart, so the logical chunk and the swizzle phases are fixed
+    const int conv_row       = ct >> 3;
+    const int conv_lc        = (ct & 7) ^ (conv_row & 7);     // logical 16-byte chunk: features [4 lc, 4 lc + 4)
+    const uint32_t conv_off  = static_cast<uint32_t>(conv_row) * 64u +
+                               ((static_cast<uint32_t>(conv_lc >> 1) ^ ((conv_row >> 1) & 3u)) << 4) +
+                               (static_cast<uint32_t>(conv_lc & 1) << 3);
+    uint32_t a_cnt = 0;
+      Ring ra;
+    const int a_reps = p.a_stream ? p.k_tiles : 1;
+    for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
+      for (int rep = 0; rep < a_reps; ++rep)
+      for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
+        const uint32_t sa = ra.slot, pa = ra.phase;
+        ra.advance(p.a_slots);
+        ptx::mbar_wait_park(ptx::smem_u32(&bars->a_raw_full[sa]), pa);
+        uint4* hi = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES);
+        uint4* lo = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES);
+        const int rem_f       = p.d - kbi * KBLOCK;
+        const int live_chunks = BF16C ? 4 * min(2, (rem_f + 15) / 16) : 2 * min(4, (rem_f + 7) / 8);
+        uint8_t* hb = gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES;                    // bf16 hi tile (8 KB)
+        uint8_t* lb = hb + KBLOCK_BYTES / 2;                                       // bf16 lo tile (8 KB)
+        constexpr int CPT = KBLOCK_BYTES / 16 / 256;   // 16-byte chunks per thread
+        // all loads first: the chunks are independent, one shared-memory latency instead of CPT
+        uint4 v[CPT];
+#pragma unroll
+        for (int i = 0; i < CPT; ++i) v[i] = hi[ct + i * 256];
+        if (conv_lc < live_chunks) {   // chunk ct + 256 i keeps the logical chunk and the swizzle phase of chunk ct
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) {
+            const int e = ct + i * 256;
+            uint4 h, l;
+            if (BF16C && !TRUNC) {   // nearest tf32 (ties away from zero): |lo| <= 2^-12 |x|
+              h.x = (v[i].x + 0x1000u) & 0xffffe000u;
+              h.y = (v[i].y + 0x1000u) & 0xffffe000u;
+              h.z = (v[i].z + 0x1000u) & 0xffffe000u;
+              h.w = (v[i].w + 0x1000u) & 0xffffe000u;
+            } else {
+              h.x = v[i].x & 0xffffe000u; h.y = v[i].y & 0xffffe000u; h.z = v[i].z & 0xffffe000u; h.w = v[i].w & 0xffffe000u;
+            }
+            l.x = __float_as_uint(__uint_as_float(v[i].x) - __uint_as_float(h.x));
+            l.y = __float_as_uint(__uint_as_float(v[i].y) - __uint_as_float(h.y));
+            l.z = __float_as_uint(__uint_as_float(v[i].z) - __uint_as_float(h.z));
+            l.w = __float_as_uint(__uint_as_float(v[i].w) - __uint_as_float(h.w));
+            if (!TRUNC) hi[e] = h;
+            if (BF16C) {
+              // 4 features -> 8 bytes of the 64-byte bf16 row (64B swizzle: 16-byte chunk ^= (row / 2) % 4)
+              const uint32_t off = conv_off + static_cast<uint32_t>(i) * (32u * 64u);
+              const __nv_bfloat162 h01 = __floats2bfloat162_rn(__uint_as_float(h.x), __uint_as_float(h.y));
+              const __nv_bfloat162 h23 = __floats2bfloat162_rn(__uint_as_float(h.z), __uint_as_float(h.w));
+              const __nv_bfloat162 l01 = __floats2bfloat162_rn(__uint_as_float(l.x), __uint_as_float(l.y));
+              const __nv_bfloat162 l23 = __floats2bfloat162_rn(__uint_as_float(l.z), __uint_as_float(l.w));
+              *reinterpret_cast<uint2*>(hb + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+              *reinterpret_cast<uint2*>(lb + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+            } else {
+              lo[e] = l;
+            }
+          }
+        }
+        ptx::fence_proxy_async_smem();  // generic-proxy writes to this CTA's operand tiles -> async proxy (pair MMA)
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready[sa]));
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (pair leader only; warp-uniform loop, one elected lane issues) ====
+    if (leader) {
+      const uint32_t idesc   = ptx::umma_idesc_tf32(TILE_M, p.bn);
+      const uint32_t idesc16 = ptx::umma_idesc_bf16(TILE_M, p.bn);
+      (void)idesc16;
+      uint32_t b_cnt = 0, acc_cnt = 0;
+      Ring ra_tile, ra_run, rb, racc;
+      if (p.fold && pair < pair_tiles) ptx::mbar_wait_park(ptx::smem_u32(&bars->cn_full), 0u);
+      const uint32_t first_acc = p.fold ? 1u : 0u;   // the fold MMA initialises the accumulator
+      for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs, ra_tile.advance_by(p.kb, p.a_slots)) {
+        for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
+          const uint32_t acc = racc.slot, pacc = racc.phase;
+          racc.advance(p.n_acc);
+          Ring ra = p.a_stream ? ra_run : ra_tile;
+          ptx::mbar_wait_park(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
+          const uint32_t d_tmem = tmem_base + acc * p.bn;
+          if (p.fold) {
+            ptx::tc_fence_after();
+            if (ptx::elect_one())
+              ptx::mma_tf32_ss(d_tmem, ptx::umma_desc_sw32(fold_u32), ptx::umma_desc_sw32(fold_u32 + (1u + nt) * FOLD_TILE),
+                                    idesc, 0u);
+            __syncwarp();
+          }
+          for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
+            const uint32_t sa = ra.slot, pa = ra.phase;
+            ra.advance(p.a_slots);
+            if (nt == 0 || p.a_stream) ptx::mbar_wait_park(ptx::smem_u32(&bars->a_ready[sa]), pa);
+            uint32_t sb = rb.slot;
+            const uint32_t pb = rb.phase;
+            rb.advance(p.b_stages);
+            if (p.b_resident) {
+              sb = nt * p.kb + kbi;
+              if (pt == pair) ptx::mbar_wait_park(ptx::smem_u32(&bars->b_full[sb]), 0u);
+            } else {
+              ptx::mbar_wait_park(ptx::smem_u32(&bars->b_full[sb]), pb);
+            }
+            ptx::tc_fence_after();
+            const uint64_t da_hi = ptx::umma_desc_sw128(a_base + sa * A_SLOT_BYTES);
+            const uint64_t da_lo = ptx::umma_desc_sw128(a_base + sa * A_SLOT_BYTES + KBLOCK_BYTES);
+            const uint64_t db_hi = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes);
+            const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
+            const int nks = min(4, (p.d - kbi * KBLOCK + 7) / 8);
+            if (ptx::elect_one()) {
+              if (BF16C) {
+                // corrections first (bf16, K = 16), then the tf32 main term
+                const uint32_t a_hb = a_base + sa * A_SLOT_BYTES + KBLOCK_BYTES;
+                const uint32_t b_hb = b_base + sb * b_stage_bytes + b_half_bytes;
+                const uint64_t da_hb = ptx::umma_desc_sw64(a_hb), da_lb = ptx::umma_desc_sw64(a_hb + KBLOCK_BYTES / 2);
+                const uint64_t db_hb = ptx::umma_desc_sw64(b_hb), db_lb = ptx::umma_desc_sw64(b_hb + b_half_bytes / 2);
+                const int nk16 = (nks + 1) / 2;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                  if (ks >= nk16 || (p.dbg_skip & 8)) break;
+                  const uint64_t adv = static_cast<uint64_t>(ks * 2);
+                  ptx::mma_f16_ss(d_tmem, da_lb + adv, db_hb + adv, idesc16, ((kbi | ks) != 0 ? 1u : 0u) | first_acc);
+                  ptx::mma_f16_ss(d_tmem, da_hb + adv, db_lb + adv, idesc16, 1u);
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks >= nks || (p.dbg_skip & 16)) break;
+                  const uint64_t adv = static_cast<uint64_t>(ks * 2);
+                  ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+                }
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                  if (ks >= nks) break;
+                  const uint64_t adv = static_cast<uint64_t>(ks * 2);
+                  ptx::mma_tf32_ss(d_tmem, da_lo + adv, db_hi + adv, idesc, ((kbi | ks) != 0 ? 1u : 0u) | first_acc);
+                  ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
+                  ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+                }
+              }
+              if (!p.b_resident) ptx::mma_commit(ptx::smem_u32(&bars->b_empty[sb]));
+              if (nt == p.k_tiles - 1 || p.a_stream) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[sa]));
+            }
+            __syncwarp();
+          }
+          ra_run = ra;
+          if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->acc_full[acc]));
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 8 && warp < 24) {
+    // ===================== epilogue (own 128 rows of the pair tile) =====================
+    const int64_t n_mine = (pair_tiles > pair) ? (pair_tiles - pair + n_pairs - 1) / n_pairs : 0;
+    epilogue_role<false, DIST, true>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, pair * TILE_M, n_pairs * TILE_M, n_mine);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
 // =================================================================================================
 // A-in-TMEM variant (the fast one).  Measured on B200 (tools/micro/mma_rate.cu): a kind::tf32 MMA with
 // both operands in shared memory costs 43 + N/2 cycles (171 at N = 256 -> 861 TFLOP/s), with the A
@@ -1197,12 +1511,26 @@ TilePlan plan_tiles(int d, int k, size_t smem_limit)
   return t;
 }
 
+// single-CTA twin of the pair kernel (bf16 corrections + folded norms for k <= 128): opt-in until measured
+bool use_solo_v2()
+{
+  const char* e = std::getenv("CUML_B200_SOLO_V2");
+  return e && std::atoi(e) != 0;
+}
+
 // CTA-pair plan: BN = 256 split across the pair (128 centroid rows per CTA), deeper X ring.
 // half norms folded into the accumulator by one extra MMA (default on; CUML_B200_FOLD=0 restores the epilogue add)
 bool use_cn_fold()
 {
   const char* e = std::getenv("CUML_B200_FOLD");
   return e ? std::atoi(e) != 0 : true;
+}
+
+// the solo kernel folds the half norms when the tiles fit next to the single-CTA plan
+bool solo_fold_fits(const TilePlan& t, int k, size_t smem_limit)
+{
+  const int k_tiles = static_cast<int>(ceil_div(k, t.bn));
+  return use_cn_fold() && k_tiles <= 4 && t.smem + static_cast<size_t>(1 + k_tiles) * TILE_M * 32 <= smem_limit;
 }
 
 TilePlan plan_tiles_2cta(int d, int k, size_t smem_limit)
@@ -1321,6 +1649,7 @@ int tc_variant(const Handle& h, int d, int k)
   if (pack_k_sub(d, k)) return 1;
   if (use_ts(h, d, k)) return 4;
   if (use_2cta(h, d, k)) return use_bf16_corrections() ? 3 : 2;
+  if (use_solo_v2() && use_bf16_corrections()) return 5;
   return 1;
 }
 
@@ -1364,12 +1693,13 @@ void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out, bool 
     out.d_pad = d_pad;
   }
   out.block_n = t.bn;
-  out.bf16c   = (pair && allow_bf16 && use_bf16_corrections()) ? 1 : 0;
+  const bool solo = !pair && !ts && use_solo_v2();
+  out.bf16c   = ((pair || solo) && allow_bf16 && use_bf16_corrections()) ? 1 : 0;
   if (out.bf16c && out.hb.n < static_cast<size_t>(k_pad) * d_pad) {
     out.hb.alloc(static_cast<size_t>(k_pad) * d_pad, h.stream);
     out.lb.alloc(static_cast<size_t>(k_pad) * d_pad, h.stream);
   }
-  out.fold = (pair && t.fold) ? 1 : 0;
+  out.fold = ((pair && t.fold) || (solo && solo_fold_fits(t, k, h.smem_optin))) ? 1 : 0;
   if (out.fold && out.cnp.n < static_cast<size_t>(k_pad) * 8) out.cnp.alloc(static_cast<size_t>(k_pad) * 8, h.stream);
   prepare_centroids_kernel<<<static_cast<unsigned>(ceil_div(k_pad, 8)), 256, 0, h.stream>>>(
     C, k, d, k_pad, d_pad, out.hi.get(), out.lo.get(), out.cnh.get(),
@@ -1599,6 +1929,38 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       fused_l2_argmin_2cta_kernel<false, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     } else {
       fused_l2_argmin_2cta_kernel<false><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
+    }
+  } else if (use_solo_v2()) {
+    // opt-in single-CTA twin of the pair kernel (see fused_l2_argmin_solo_kernel)
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
+    p.fold = (cen.fold && !dbg_dots && solo_fold_fits(t, k, h.smem_optin)) ? 1 : 0;
+    const size_t smem = t.smem + (p.fold ? static_cast<size_t>(1 + p.k_tiles) * TILE_M * 32 : 0);
+    CUtensorMap tm_cn = tm_hi;
+    if (p.fold)
+      tm_cn = make_map_2d(cen.cnp.get(), 8, cen.k_pad, 8 * sizeof(float), 8, b_box_rows, CU_TENSOR_MAP_SWIZZLE_32B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    static bool solo_attr = false;
+    if (!solo_attr) {
+      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, false, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
+      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<false, false, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
+      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<false, true, false>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
+      solo_attr = true;
+    }
+    if (cen.bf16c && !dist) {
+      CUtensorMap tm_hb = make_map_2d(cen.hb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
+                                      b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+      CUtensorMap tm_lb = make_map_2d(cen.lb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
+                                      b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+      fused_l2_argmin_solo_kernel<true, false, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+    } else if (dist) {
+      fused_l2_argmin_solo_kernel<false, true, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
+    } else {
+      fused_l2_argmin_solo_kernel<false, false, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     }
   } else {
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));

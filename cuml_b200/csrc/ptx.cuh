@@ -163,6 +163,17 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
     "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
     : "memory");
 }
+// same with 16-bit operands (kind::f16: fp16 / bf16, K = 16 per instruction)
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate)
+{
+  asm volatile(
+    "{\n\t.reg .pred p;\n\t"
+    "setp.ne.b32 p, %4, 0;\n\t"
+    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+    "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+    : "memory");
+}
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint32_t bar)
 {
