@@ -132,3 +132,34 @@ def test_blobs_deterministic():
     X2, c2, l2 = blobs.make_blobs(1000, 8, 4)
     assert np.array_equal(X1, X2) and np.array_equal(c1, c2) and np.array_equal(l1, l2)
     assert X1.dtype == np.float32 and X1.flags.c_contiguous
+
+
+def test_transform_and_predict_match_sklearn():
+    # the oracle's transform / predict against the reference CPU path's own methods (sklearn.cluster.KMeans):
+    # sklearn.transform returns Euclidean distances (== ML::kmeans::transform under L2SqrtExpanded)
+    from sklearn.cluster import KMeans as SK
+    from oracle import blobs, lloyd
+    X, centres, _ = blobs.make_blobs(3000, 12, 9, seed=77)
+    init = blobs.parity_init(centres)
+    sk = SK(n_clusters=9, init=init.astype(np.float64), n_init=1, max_iter=5, tol=0.0, algorithm="lloyd").fit(
+        X.astype(np.float64))
+    Cc = sk.cluster_centers_
+    assert np.allclose(lloyd.transform(X, Cc, sqrt=True), sk.transform(X.astype(np.float64)), rtol=1e-9, atol=1e-9)
+    assert np.allclose(lloyd.transform(X, Cc) , sk.transform(X.astype(np.float64)) ** 2, rtol=1e-9, atol=1e-8)
+    lab, inertia = lloyd.predict(X, Cc)
+    assert np.array_equal(lab, sk.predict(X.astype(np.float64)))
+    assert abs(inertia + sk.score(X.astype(np.float64))) / inertia < 1e-10
+
+
+def test_e_step_random_shapes_against_bruteforce():
+    # the chunked fp64 E-step equals a direct (x - c)^2 argmin on random small shapes, including k = 1 and d = 1
+    from oracle import lloyd
+    rng = np.random.default_rng(5)
+    for n, d, k in [(1, 1, 1), (17, 1, 3), (50, 7, 1), (300, 5, 11), (1000, 33, 64)]:
+        X = rng.standard_normal((n, d)).astype(np.float32)
+        Cc = rng.standard_normal((k, d)).astype(np.float32)
+        lab, dmin = lloyd.e_step(X, Cc)
+        d2 = ((X[:, None, :].astype(np.float64) - Cc[None].astype(np.float64)) ** 2).sum(2)
+        assert np.array_equal(lab, d2.argmin(1))
+        assert np.allclose(dmin, d2.min(1), rtol=1e-9, atol=1e-9)
+
