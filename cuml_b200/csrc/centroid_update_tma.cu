@@ -4,7 +4,7 @@
 // Roles replaced (cuVS side, reached from reference cpp/src/kmeans/kmeans_fit.cu:58-59,153-154):
 // reduce_rows_by_key (centroid sums) and reduce_cols_by_key (cluster weights).
 //
-// Three kernels, chosen by tma_update_accumulate():
+// Two kernels, chosen by tma_update_accumulate():
 //   accumulate_owner_kernel  (n_features >= 32, k >= 16, [k x 32*VEC] table fits shared memory; the default
 //                            for C2 / C3): consumer warp w owns the table rows of the clusters of class w
 //                            (16 size-balanced classes); analyst warps counting-sort each tile's rows by
@@ -15,8 +15,6 @@
 //                            table, rows of one instruction that share a label are ordered by ranks an
 //                            analyst warp computes with __match_any_sync; X tile and table XOR-swizzled.
 //                            Bound by shared-memory wavefronts (3.3-3.6 TB/s).
-//   accumulate_rows_kernel   (opt-in experiment, CUML_B200_UPDATE_ROWS): lane = column with per-warp column
-//                            slices; too few warps per table, kept for the A/B record.
 // Every kernel writes its table once per CTA to a partials buffer; reduce_partials_f32_kernel sums the
 // partials in a fixed order in fp64 (deterministic, bitwise identical on every rank after the all-reduce).
 // Memory parallelism comes from the TMA rings, not from occupancy (one CTA per SM).
@@ -271,188 +269,7 @@ accumulate_tma_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams 
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// "Lane = column" variant (preferred whenever >= 5 consumer warps fit per SM).  A consumer warp owns one
-// sub-slice of <= 32 columns: every shared-memory access of a row segment is ONE contiguous 128-byte
-// wavefront -- X read 1, table read 1, table write 1 -- instead of the ~8 wavefronts per segment the
-// vectorised variant above pays for its 32 random table rows per instruction (ncu: that variant is bound by
-// LSU wavefronts).  Rows are processed four at a time with all loads ahead of all stores when their labels
-// are distinct (the common case), one by one otherwise, so no warp-wide matching and no analyst is needed.
-// DS = columns per sub-slice (32, 16 or 8): a warp instruction covers RPI = 32/DS consecutive rows.
-struct UpdParams6 {
-  int64_t n;
-  int64_t tiles_total;
-  int64_t tiles_per_block;
-  int d, k, tr, nb, nstage;
-  int dbg_skip;   // profiling knob (env CUML_B200_UPD_SKIP): consumers acknowledge stages without touching them
-  const int32_t* labels;
-  const float* w;
-  float* partial_S;
-  float* partial_W;
-};
-
-template <int DS, bool HAS_W>
-__global__ void __launch_bounds__(96)
-accumulate_rows_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams6 p)
-{
-  constexpr int RPI  = 32 / DS;          // rows per warp instruction
-  constexpr int STEPS = 4 / RPI;         // instructions per 4-row batch (DS=32: 4, 16: 2, 8: 1)
-  constexpr uint32_t ROWB = DS * 4;
-  extern __shared__ uint8_t smem_dyn[];
-  const uint32_t raw  = ptx::smem_u32(smem_dyn);
-  const uint32_t base = (raw + 127u) & ~127u;
-  uint8_t* g          = smem_dyn + (base - raw);
-  // layout: stages (nb sub-tiles | labels) | tables (nb) | wtab | barriers
-  const uint32_t sub_bytes  = static_cast<uint32_t>(p.tr) * ROWB;
-  const uint32_t x_bytes    = static_cast<uint32_t>(p.nb) * sub_bytes;
-  const uint32_t lab_bytes  = static_cast<uint32_t>(p.tr) * 4u;
-  const uint32_t stage_full = x_bytes + ((lab_bytes + 127u) & ~127u);
-  const uint32_t tab_bytes  = static_cast<uint32_t>(p.k) * ROWB;
-  const uint32_t tab_u32    = base + p.nstage * stage_full;
-  float* tab       = reinterpret_cast<float*>(g + p.nstage * stage_full);
-  float* wtab      = tab + static_cast<size_t>(p.nb) * p.k * DS;
-  uint64_t* bars   = reinterpret_cast<uint64_t*>(wtab + ((p.k + 3) & ~3));
-  const uint32_t bars_u32 = ptx::smem_u32(bars);
-  const uint32_t wtab_u32 = ptx::smem_u32(wtab);
-  const uint32_t B_FULL = 0, B_EMPTY = MAX_NSTAGE * 8;
-
-  const int warp  = threadIdx.x / 32;
-  const int lane  = threadIdx.x % 32;
-  const int slice = blockIdx.y;
-  const int cs    = slice * (p.nb * DS);
-
-  for (int i = threadIdx.x; i < p.nb * p.k * DS; i += blockDim.x) tab[i] = 0.0f;
-  for (int i = threadIdx.x; i < p.k; i += blockDim.x) wtab[i] = 0.0f;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < MAX_NSTAGE; ++s) {
-      ptx::mbar_init(bars_u32 + B_FULL + s * 8, 1);
-      ptx::mbar_init(bars_u32 + B_EMPTY + s * 8, p.nb);
-    }
-    ptx::fence_barrier_init();
-    ptx::prefetch_tmap(&tm_x);
-  }
-  __syncthreads();
-
-  const int64_t t_begin = static_cast<int64_t>(blockIdx.x) * p.tiles_per_block;
-  const int64_t t_end   = min(p.tiles_total, t_begin + p.tiles_per_block);
-
-  if (warp == 0) {
-    // ---------------- producer ----------------
-    uint32_t s = 0, ph = 0;
-    for (int64_t t = t_begin; t < t_end; ++t) {
-      mbar_wait_spin(bars_u32 + B_EMPTY + s * 8, ph ^ 1u);
-      if (ptx::elect_one()) {
-        const uint32_t full = bars_u32 + B_FULL + s * 8;
-        ptx::mbar_arrive_expect_tx(full, x_bytes + lab_bytes);
-        const uint32_t dst = base + s * stage_full;
-        const int64_t row0 = t * p.tr;
-        for (int sb = 0; sb < p.nb; ++sb)
-          ptx::tma_load_2d_hint(dst + sb * sub_bytes, &tm_x, cs + sb * DS, static_cast<int32_t>(row0), full,
-                                ptx::kEvictFirst);
-        bulk_load_1d(dst + x_bytes, p.labels + row0, lab_bytes, full);
-      }
-      __syncwarp();
-      if (++s == static_cast<uint32_t>(p.nstage)) { s = 0; ph ^= 1u; }
-    }
-  } else {
-    // ---------------- consumers: one sub-slice each ----------------
-    const int sub         = warp - 1;
-    const uint32_t tab_me = tab_u32 + sub * tab_bytes;
-    const int rsel        = lane / DS;                 // which of the RPI rows of an instruction is mine
-    const uint32_t coff   = static_cast<uint32_t>(lane % DS) * 4u;
-    const bool counts     = (slice == 0 && sub == 0);
-    uint32_t s = 0, ph = 0;
-    for (int64_t t = t_begin; t < t_end; ++t) {
-      mbar_wait_spin(bars_u32 + B_FULL + s * 8, ph);
-      const uint32_t st = base + s * stage_full;
-      const uint32_t xs = st + sub * sub_bytes;
-      const uint32_t ls = st + x_bytes;
-      const int64_t row0 = t * p.tr;
-      const int64_t left = p.n - row0;
-      const int valid    = left < p.tr ? static_cast<int>(left) : p.tr;
-      for (int r0 = 0; r0 < p.tr; r0 += 4) {
-        if (r0 >= valid || p.dbg_skip) break;
-        // labels of the 4 rows of this batch (one broadcast 16-byte read); rows past the end get -1
-        int4 lb4;
-        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                     : "=r"(lb4.x), "=r"(lb4.y), "=r"(lb4.z), "=r"(lb4.w) : "r"(ls + r0 * 4));
-        const int nrow = min(4, valid - r0);
-        int l[4] = {lb4.x, nrow > 1 ? lb4.y : -1, nrow > 2 ? lb4.z : -2, nrow > 3 ? lb4.w : -3};
-        float wr[4] = {1.f, 1.f, 1.f, 1.f};
-        if (HAS_W) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) wr[i] = (i < nrow) ? __ldg(p.w + row0 + r0 + i) : 0.f;
-        }
-        const bool distinct = (l[0] != l[1]) & (l[0] != l[2]) & (l[0] != l[3]) & (l[1] != l[2]) & (l[1] != l[3]) &
-                              (l[2] != l[3]);
-        if (distinct) {
-          // all loads first, then all stores: the 4 read-modify-writes are independent
-          float x[STEPS], tv[STEPS];
-          uint32_t ca[STEPS];
-          bool ok[STEPS];
-#pragma unroll
-          for (int q = 0; q < STEPS; ++q) {
-            const int ri = q * RPI + rsel;                            // row of the batch handled by this lane
-            const int lq = (ri == 0) ? l[0] : (ri == 1) ? l[1] : (ri == 2) ? l[2] : l[3];
-            ok[q] = lq >= 0;
-            x[q]  = __int_as_float(lds32(xs + static_cast<uint32_t>(r0 + ri) * ROWB + coff));
-            if (HAS_W) x[q] *= (ri == 0) ? wr[0] : (ri == 1) ? wr[1] : (ri == 2) ? wr[2] : wr[3];
-            ca[q] = tab_me + static_cast<uint32_t>(ok[q] ? lq : 0) * ROWB + coff;
-            tv[q] = __int_as_float(lds32(ca[q]));
-          }
-#pragma unroll
-          for (int q = 0; q < STEPS; ++q) {
-            if (ok[q]) asm volatile("st.shared.f32 [%0], %1;" ::"r"(ca[q]), "f"(tv[q] + x[q]) : "memory");
-          }
-          if (counts && lane < nrow) {
-            const int lq = (lane == 0) ? l[0] : (lane == 1) ? l[1] : (lane == 2) ? l[2] : l[3];
-            const float wq = (lane == 0) ? wr[0] : (lane == 1) ? wr[1] : (lane == 2) ? wr[2] : wr[3];
-            const uint32_t wa = wtab_u32 + static_cast<uint32_t>(lq) * 4u;
-            const float cur = __int_as_float(lds32(wa));
-            asm volatile("st.shared.f32 [%0], %1;" ::"r"(wa), "f"(cur + wq) : "memory");
-          }
-        } else {
-          // some rows share a label: one row at a time (program order keeps the updates exact)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            if (i < nrow) {
-              if (rsel == (i % RPI)) {
-                const uint32_t ca = tab_me + static_cast<uint32_t>(l[i]) * ROWB + coff;
-                float xv = __int_as_float(lds32(xs + static_cast<uint32_t>(r0 + i) * ROWB + coff));
-                if (HAS_W) xv *= wr[i];
-                const float cur = __int_as_float(lds32(ca));
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(ca), "f"(cur + xv) : "memory");
-              }
-              if (counts && lane == 0) {
-                const uint32_t wa = wtab_u32 + static_cast<uint32_t>(l[i]) * 4u;
-                const float cur = __int_as_float(lds32(wa));
-                asm volatile("st.shared.f32 [%0], %1;" ::"r"(wa), "f"(cur + wr[i]) : "memory");
-              }
-              __syncwarp();
-            }
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bars_u32 + B_EMPTY + s * 8);
-      if (++s == static_cast<uint32_t>(p.nstage)) { s = 0; ph ^= 1u; }
-    }
-  }
-  __syncthreads();
-  float* outS     = p.partial_S + static_cast<size_t>(blockIdx.x) * p.k * p.d;
-  const int wcols = min(p.nb * DS, p.d - cs);
-  for (int i = threadIdx.x; i < p.k * wcols; i += blockDim.x) {
-    const int j = i / wcols, c = i % wcols;
-    const int sb = c / DS, cc = c % DS;
-    outS[static_cast<size_t>(j) * p.d + cs + c] = tab[static_cast<size_t>(sb) * p.k * DS + static_cast<size_t>(j) * DS + cc];
-  }
-  if (slice == 0) {
-    float* outW = p.partial_W + static_cast<size_t>(blockIdx.x) * p.k;
-    for (int i = threadIdx.x; i < p.k; i += blockDim.x) outW[i] = wtab[i];
-  }
-}
-
-// ---- v7: label-class ownership ----------------------------------------------------------------------
+// ---- label-class ownership ---------------------------------------------------------------------------
 // One [k x DS] fp32 table per CTA (DS = 32*VEC columns), NCONS consumer warps.  Consumer w exclusively owns
 // the table rows of the clusters with (label % NCONS) == w, so no two warps ever touch the same cell and no
 // atomics or rank bookkeeping are needed.  Per 32-row group every consumer reads the 32 labels (lane = row),
@@ -950,62 +767,6 @@ static TmaUpdatePlan plan_tma_update(const Handle& h, int d, int k)
   return best;
 }
 
-struct RowsPlan {
-  int ds = 0, tr = 0, nb = 1, nstage = 0, slices = 0, ctas_per_sm = 0;
-  size_t smem = 0;
-};
-
-// lane = column kernel: one consumer warp per 32-column sub-slice; wants >= 5 consumer warps per SM
-static RowsPlan plan_rows_update(const Handle& h, int d, int k)
-{
-  RowsPlan best;
-  int mode = 0;   // 0 = off (default: measured slower than the vectorised kernel), 1 = when >= 5 consumer warps
-                  // per SM fit, 2 = always (profiling)
-  {
-    const char* e = std::getenv("CUML_B200_UPDATE_ROWS");
-    if (e) mode = std::atoi(e);
-    if (mode == 0) return best;
-  }
-  if (d % 4 != 0) return best;
-  const int ds = d >= 32 ? 32 : d;
-  if (ds != 32 && ds != 16 && ds != 8) return best;
-  double best_score = -1.0;
-  const size_t sm_total = 228 * 1024;
-  for (int nb = 1; nb <= ((d >= 64) ? 2 : 1); ++nb) {
-    const size_t table = (static_cast<size_t>(k) * ds * nb + ((k + 3) & ~3)) * 4;
-    for (int per_sm = 1; per_sm <= 16; ++per_sm) {
-      const size_t budget = std::min<size_t>(h.smem_optin, sm_total / per_sm - 1024);
-      const size_t fixed  = table + 2 * MAX_NSTAGE * 8 + 256;
-      if (fixed + 2 * 4224 > budget) continue;
-      for (int nstage = 2; nstage <= MAX_NSTAGE; ++nstage) {
-        const size_t stage_budget = (budget - fixed) / nstage;
-        if (stage_budget < 4224) break;
-        int tr = static_cast<int>((stage_budget - 128) / (static_cast<size_t>(ds) * nb * 4 + 4));
-        tr     = std::min(tr, 256);
-        tr -= tr % 32;
-        if (tr < 32) continue;
-        const size_t tile_bytes = static_cast<size_t>(tr) * ds * nb * 4;
-        const int cons_sm       = per_sm * nb;
-        const double inflight   = static_cast<double>(per_sm) * nstage * tile_bytes;
-        const double score = std::min(inflight, 128.0 * 1024) * std::min(cons_sm, 8) / 8.0 + (tile_bytes >= 8192 ? 1.0 : 0.0);
-        if (score > best_score) {
-          best_score       = score;
-          best.ds          = ds;
-          best.nb          = nb;
-          best.tr          = tr;
-          best.nstage      = nstage;
-          best.slices      = static_cast<int>(ceil_div(d, ds * nb));
-          best.ctas_per_sm = per_sm;
-          const uint32_t lab = (static_cast<uint32_t>(tr) * 4 + 127u) & ~127u;
-          best.smem = static_cast<size_t>(nstage) * (tile_bytes + lab) + table + 2 * MAX_NSTAGE * 8 + 128 + 64;
-        }
-      }
-    }
-  }
-  if (mode == 1 && best.ds && best.ctas_per_sm * best.nb < 5) best.ds = 0;   // too few consumer warps: vectorised kernel
-  return best;
-}
-
 struct OwnerPlan {
   int vec = 0, tr = 0, nstage = 0, slices = 0, ncons = 16, nl = 0, half = 0;
   size_t smem = 0;
@@ -1136,47 +897,6 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
         case 2: hw ? launch(accumulate_owner_kernel<2, true>) : launch(accumulate_owner_kernel<2, false>); break;
         default: hw ? launch(accumulate_owner_kernel<1, true>) : launch(accumulate_owner_kernel<1, false>); break;
       }
-    }
-    CB2_CHECK_LAUNCH();
-    reduce_partials_f32_kernel<<<static_cast<unsigned>(ceil_div(total, 32)), 256, 0, h.stream>>>(
-      partial_S.get(), partial_W.get(), static_cast<int>(rb), k, d, packed, accumulate_into ? 1 : 0);
-    CB2_CHECK_LAUNCH();
-    return;
-  }
-  if (const RowsPlan rp = plan_rows_update(h, d, k); rp.ds > 0) {
-    UpdParams6 q{};
-    q.n = n; q.d = d; q.k = k; q.tr = rp.tr; q.nb = rp.nb; q.nstage = rp.nstage;
-    {
-      const char* e = std::getenv("CUML_B200_UPD_SKIP");
-      q.dbg_skip    = e ? std::atoi(e) : 0;
-      if (std::getenv("CUML_B200_UPD_PLAN"))
-        std::printf("[cuml_b200 update plan] ds %d nb %d tr %d nstage %d slices %d ctas/sm %d smem %zu\n", rp.ds, rp.nb, rp.tr,
-                    rp.nstage, rp.slices, rp.ctas_per_sm, rp.smem);
-    }
-    q.tiles_total = ceil_div(n, rp.tr);
-    int64_t rb = std::max<int64_t>(1, static_cast<int64_t>(h.sm_count) * rp.ctas_per_sm / rp.slices);
-    rb         = std::min<int64_t>(rb, q.tiles_total);
-    rb         = std::min<int64_t>(rb, std::max<int64_t>(1, n / (16 * static_cast<int64_t>(k)) + 1));
-    q.tiles_per_block = ceil_div(q.tiles_total, rb);
-    rb                = ceil_div(q.tiles_total, q.tiles_per_block);
-    if (partial_S.n < static_cast<size_t>(rb) * k * d) partial_S.alloc(static_cast<size_t>(rb) * k * d, h.stream);
-    if (partial_W.n < static_cast<size_t>(rb) * k) partial_W.alloc(static_cast<size_t>(rb) * k, h.stream);
-    q.labels = labels_padded; q.w = w; q.partial_S = partial_S.get(); q.partial_W = partial_W.get();
-    CUtensorMap tm = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
-                                 static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(rp.ds),
-                                 static_cast<uint32_t>(rp.tr), CU_TENSOR_MAP_SWIZZLE_NONE,
-                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
-    dim3 grid(static_cast<unsigned>(rb), static_cast<unsigned>(rp.slices));
-    const unsigned threads = (rp.nb + 1) * 32;
-    auto launch = [&](auto kern) {
-      CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
-      kern<<<grid, threads, rp.smem, h.stream>>>(tm, q);
-    };
-    const bool hw = w != nullptr;
-    switch (rp.ds) {
-      case 32: hw ? launch(accumulate_rows_kernel<32, true>) : launch(accumulate_rows_kernel<32, false>); break;
-      case 16: hw ? launch(accumulate_rows_kernel<16, true>) : launch(accumulate_rows_kernel<16, false>); break;
-      default: hw ? launch(accumulate_rows_kernel<8, true>) : launch(accumulate_rows_kernel<8, false>); break;
     }
     CB2_CHECK_LAUNCH();
     reduce_partials_f32_kernel<<<static_cast<unsigned>(ceil_div(total, 32)), 256, 0, h.stream>>>(
