@@ -75,3 +75,81 @@ def test_two_rank_fit_matches_single_gpu(init_kind):
         assert adjusted_rand_score(true, labels) >= 0.6
     else:
         assert adjusted_rand_score(true, labels) >= 0.99
+
+
+# ---- cuml_b200.distributed.KMeans: the orchestration that stands in for cuml.dask.cluster.KMeans -----------------
+def _dist_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    out = None
+    try:
+        from cuml_b200.cluster.kmeans_mg import shard_bounds
+        from cuml_b200.distributed import KMeans as DistKMeans
+        from oracle import blobs
+        n, d, k = 30000, 32, 8
+        X, centres, _ = blobs.make_blobs(n, d, k)
+        w = np.random.default_rng(3).uniform(0.5, 2.0, size=n).astype(np.float32)
+        lo, hi = shard_bounds(n, rank, world)
+        mid = lo + (hi - lo) // 3
+        km = DistKMeans(n_clusters=k, init=blobs.parity_init(centres), max_iter=6, tol=0.0, random_state=None)
+        km.fit([X[lo:mid], X[mid:hi]], sample_weight=[w[lo:mid], w[mid:hi]])
+        score = km.score(X[lo:hi], sample_weight=w[lo:hi])
+        out = dict(centers=km.cluster_centers_, inertia=km.inertia_, labels=np.asarray(km.labels_),
+                   pred=np.asarray(km.predict(X[lo:hi])), score=score, tr=np.asarray(km.transform(X[lo:lo + 5])),
+                   n_iter=km.n_iter_)
+        km.close()
+    except Exception as e:   # report instead of leaving the parent waiting on the queue
+        import traceback
+        out = dict(crash=traceback.format_exc() + repr(e))
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [1, 2])
+def test_distributed_estimator(world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    from cuml_b200.cluster.kmeans_mg import shard_bounds
+    from oracle import blobs, lloyd
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    outs = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    outs = [o for _, o in outs]
+    for o in outs:
+        assert o is not None and "crash" not in o, o
+    n, d, k = 30000, 32, 8
+    X, centres, _ = blobs.make_blobs(n, d, k)
+    w = np.random.default_rng(3).uniform(0.5, 2.0, size=n).astype(np.float32)
+    ref = lloyd.fit(X, blobs.parity_init(centres), max_iter=6, tol=0.0, sample_weight=w)
+    for o in outs:
+        assert np.array_equal(o["centers"], outs[0]["centers"])     # identical on every rank
+        assert o["inertia"] == outs[0]["inertia"] and o["score"] == outs[0]["score"]
+        assert o["n_iter"] == 6
+    assert np.abs(outs[0]["centers"] - ref["centroids"]).max() / np.abs(ref["centroids"]).max() <= 1e-4
+    assert abs(outs[0]["inertia"] - ref["inertia"]) / ref["inertia"] <= 1e-5
+    labels = np.concatenate([o["labels"] for o in outs])
+    assert (labels == ref["labels"]).mean() >= 0.9999
+    assert (np.concatenate([o["pred"] for o in outs]) == ref["labels"]).mean() >= 0.9999
+    # score: weights normalised globally, then each rank's rows scored (and re-normalised) by the local model
+    wn = w.astype(np.float64) * (n / w.astype(np.float64).sum())
+    expect = 0.0
+    for r in range(world):
+        lo, hi = shard_bounds(n, r, world)
+        expect += -lloyd.predict(X[lo:hi], ref["centroids"], wn[lo:hi], normalize=True)[1]
+    assert abs(outs[0]["score"] - expect) / abs(expect) <= 1e-5
+    To = lloyd.transform(X[:5], ref["centroids"])
+    assert np.abs(outs[0]["tr"] - To).max() / To.max() < 1e-5
