@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- Lloyd iterations/s (and sample-centroid distances/s) of the k-means hot path.
 
-    python bench.py --gpus N --steps K --warmup W [--workload C3|C2|C1|C5] [--impl ours|reference]
+    python bench.py --gpus N --steps K --warmup W [--workload C3|C2|C1|C4|C5] [--impl ours|reference]
 
 Contract (see the task statement): W untimed warm-up steps, then exactly K Lloyd iterations timed
 with CUDA events between barriers, max over ranks, ONE JSON line from rank 0.
@@ -10,6 +10,8 @@ Workloads are the BASELINE.json configs; the default (and what the driver runs a
 C3 = "KMeans fit n=100M d=64 k=256 fp32 row-sharded across 1/2/4/8 B200" -- the config the
 metric and the north-star target are quoted on; it fits one B200 (25.6 GB), total work is fixed
 as N grows ("scaling": "strong").  Inputs are ~200x larger than L2, so no explicit L2 flush.
+C4 is the inference config: a "step" is one ML::kmeans::predict call (labels + inertia) over the rank's rows,
+`value` = predict passes/s.  C5 additionally reports the k-means|| seeding time (`init` object).
 """
 from __future__ import annotations
 
@@ -31,6 +33,7 @@ WORKLOADS = {
     "C1": (1_000_000, 32, 16, "KMeans fit n=1M d=32 k=16 fp32 init=array max_iter=50 tol=0"),
     "C2": (10_000_000, 128, 1024, "KMeans fit n=10M d=128 k=1024 fp32"),
     "C3": (100_000_000, 64, 256, "KMeans fit n=100M d=64 k=256 fp32 row-sharded"),
+    "C4": (50_000_000, 256, 4096, "KMeans predict n=50M d=256 k=4096 fp32 (fused distance+argmin inference)"),
     "C5": (200_000_000, 16, 64, "KMeans fit n=200M d=16 k=64 fp32 row-sharded"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant (fused) kernel at the full
@@ -38,6 +41,11 @@ WORKLOADS = {
 TRAFFIC_NCU = {"C3": 25.602643e9 + 0.401213e9, "C2": 5.121371e9 + 0.042751e9}
 METRIC = "kmeans_lloyd_iters_per_sec"
 UNIT = "Lloyd iter/s"
+
+
+def metric_unit(workload):
+    # C4 is inference: one step = one predict pass over the rows
+    return ("kmeans_predict_passes_per_sec", "predict passes/s") if workload == "C4" else (METRIC, UNIT)
 
 
 def measured_peaks():
@@ -146,6 +154,22 @@ def cpu_reference_rate(n_full, d, k, budget_rows=None, iters=3):
     return rate_full, cores, sample
 
 
+def cpu_reference_predict_rate(n_full, d, k):
+    """reference CPU path's predict on a bounded row sample -> (full-workload passes/s, cores, sample)"""
+    import numpy as np
+    from oracle import sklearn_ref
+    cores = sklearn_ref.n_threads()
+    target_flop = 5.0 * 5e9 * max(cores, 1)                    # ~5 s per repetition, 3 repetitions
+    rows = int(max(4 * k, min(n_full, target_flop / (2.0 * k * d))))
+    rng = np.random.default_rng(1234)
+    centres = rng.uniform(-10, 10, size=(k, d)).astype(np.float32)
+    X = centres[rng.integers(0, k, size=rows)] + rng.standard_normal((rows, d), dtype=np.float32)
+    t = sklearn_ref.time_predict(X, centres, reps=3)
+    sample = (f"sklearn {__import__('sklearn').__version__} KMeans.predict on {rows} of {n_full} rows (same d={d}, "
+              f"k={k}), best of 3; full-size rate = sample rate x rows ratio")
+    return (1.0 / t) * (rows / n_full), cores, sample
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -155,17 +179,21 @@ def run_reference(args):
         n = args.n
     rates = []
     for _ in range(max(1, min(args.steps, 3))):
-        rate, cores, sample = cpu_reference_rate(n, d, k, iters=3)
+        if args.workload == "C4":
+            rate, cores, sample = cpu_reference_predict_rate(n, d, k)
+        else:
+            rate, cores, sample = cpu_reference_rate(n, d, k, iters=3)
         rates.append(rate)
     rate = max(rates)
+    metric, unit = metric_unit(args.workload)
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric, "value": rate, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "n": n, "d": d, "k": k},
         "dists_per_sec": rate * n * k,
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
-        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline": {"value": rate, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
@@ -209,7 +237,19 @@ def run_ours(args):
     labels = torch.zeros(n_local, dtype=torch.int32, device="cuda")
     engine = {"auto": 0, "simt": 1, "tc": 2}[args.engine]
 
+    predict_only = args.workload == "C4"
+    if predict_only:
+        # ML::kmeans::predict through the C-ABI, int64 index overload (n*d > INT_MAX, reference kmeans.pyx:277-281)
+        pp = _lib.default_params()
+        pp.n_clusters = k
+        labels = torch.zeros(n_local, dtype=torch.int64, device="cuda")
+        pred_inertia = C.c_float()
+
     def step():
+        if predict_only:
+            _lib.check(lib.cuml_b200_kmeans_predict_f32_i64(h.ptr, C.byref(pp), Cd.data_ptr(), X.data_ptr(), n_local, d,
+                                                            None, 1, labels.data_ptr(), C.byref(pred_inertia)))
+            return
         _lib.check(lib.cuml_b200_kmeans_lloyd_step_f32(h.ptr, X.data_ptr(), n_local, d, None, k, Cd.data_ptr(),
                                                        None, None, None, engine))
 
@@ -248,9 +288,64 @@ def run_ours(args):
     ms_per_step = ms_total / args.steps
     value = 1e3 / ms_per_step
 
+    # ---- C5: k-means|| seeding time = fit(init=k-means||, max_iter=0) - fit(init=Array, max_iter=0), device X
+    # (both calls end with the same final E-step + inertia pass; SURVEY 8d "report init time separately")
+    init_info = None
+    if args.workload == "C5":
+        def fit0(init_method):
+            p0 = _lib.default_params()
+            p0.n_clusters, p0.init, p0.max_iter, p0.tol, p0.n_init = k, init_method, 0, 0.0, 1
+            p0.oversampling_factor, p0.rng_seed = 2.0, 42
+            Cs = C0.clone()
+            inertia0, it0 = C.c_float(), C.c_int64()
+            xp0 = (C.c_void_p * 1)(X.data_ptr())
+            rows0 = (C.c_int64 * 1)(n_local)
+            barrier()
+            t0 = time.perf_counter()
+            _lib.check(lib.cuml_b200_kmeans_fit_parts_f32(h.ptr, C.byref(p0), xp0, rows0, 1, d, None, Cs.data_ptr(),
+                                                          C.byref(inertia0), C.byref(it0)))
+            torch.cuda.synchronize()
+            return time.perf_counter() - t0, float(inertia0.value)
+        fit0(_lib.INIT_ARRAY)                                   # warm-up of the final pass
+        t_arr, _ = fit0(_lib.INIT_ARRAY)
+        t_seed, inertia_seed = fit0(_lib.INIT_KMEANS_PLUS_PLUS)
+        tt = torch.tensor([t_arr, t_seed], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_arr, t_seed = [float(v) for v in tt.tolist()]
+        init_info = {"method": "k-means|| (oversampling_factor 2.0)", "seconds": max(0.0, t_seed - t_arr),
+                     "fit_max_iter0_seconds": t_seed, "final_pass_seconds": t_arr, "inertia_after_init": inertia_seed}
+
     # ---- end-to-end through the C-ABI fit with HOST buffers (H2D + K iterations + final predict pass)
     e2e = None
-    if not args.no_e2e:
+    if predict_only and not args.no_e2e:
+        # predict with HOST rows: chunks of pinned host memory copied to a device buffer and predicted one by one
+        # (the estimator's chunked host predict, reference _kmeans_predict_host_chunked kmeans.pyx:356-434)
+        chunk = min(n_local, 4_000_000)
+        Xh = torch.empty((chunk, d), dtype=torch.float32, pin_memory=True)
+        Xh.copy_(X[:chunk])
+        xb = torch.empty((chunk, d), dtype=torch.float32, device="cuda")
+        lb = torch.zeros(chunk, dtype=torch.int64, device="cuda")
+        lab_host = torch.empty(chunk, dtype=torch.int64, pin_memory=True)
+        n_chunks = (n_local + chunk - 1) // chunk
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_chunks):                             # every chunk re-sends the same pinned rows
+            xb.copy_(Xh, non_blocking=True)
+            _lib.check(lib.cuml_b200_kmeans_predict_f32_i64(h.ptr, C.byref(pp), Cd.data_ptr(), xb.data_ptr(), chunk, d,
+                                                            None, 1, lb.data_ptr(), C.byref(pred_inertia)))
+            lab_host.copy_(lb, non_blocking=True)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        e2e = {"value": (n_chunks * chunk / n_local) / dt, "unit": "predict passes/s",
+               "h2d_bytes_per_step": int(n_chunks * chunk * d * 4), "d2h_bytes_per_step": int(n_chunks * chunk * 8),
+               "seconds": dt, "call": f"cuml_b200_kmeans_predict_f32_i64 on {n_chunks} host chunks of {chunk} rows"}
+        del Xh, xb, lb
+    elif not args.no_e2e:
         Xh = torch.empty((n_local, d), dtype=torch.float32, pin_memory=True)
         Xh.copy_(X)
         del X, labels
@@ -321,13 +416,15 @@ def run_ours(args):
             "update_kernel_frac_of_hbm_peak": (4.0 * n_local * (d + 1) / (update_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
                                               if update_ms > 0 else None,
             "hbm_peak_gbs": peaks["hbm_gbs"], "tensor_peak_tflops": tf_peak})
+        metric, unit = metric_unit(args.workload)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 (split-precision tensor-core contraction: tf32 + bf16 corrections or 3xTF32; fp32/fp64 reductions)",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "n": n, "d": d, "k": k, "rows_per_gpu": n_local,
-                       "parallelism": f"row-sharded x{world}, 1 allreduce of (k*d+k+1) f64 per iteration",
+                       "parallelism": (f"row-sharded x{world}, rank-local predict (no collective)" if predict_only else
+                                       f"row-sharded x{world}, 1 allreduce of (k*d+k+1) f64 per iteration"),
                        "l2": "inputs_exceed_l2", "engine": args.engine, "init": "array (k data rows)"},
             "dists_per_sec": value * n * k,
             "gpu_launches": launches,
@@ -335,9 +432,11 @@ def run_ours(args):
             "e2e": e2e,
             "roofline": roof,
         }
+        if init_info is not None:
+            line["init"] = init_info
         if world == 1 and not args.no_cpu:
-            rate, cores, sample = cpu_reference_rate(n, d, k)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample}
+            rate, cores, sample = (cpu_reference_predict_rate if predict_only else cpu_reference_rate)(n, d, k)
+            line["cpu_baseline"] = {"value": rate, "unit": unit, "cores": cores, "kind": "reference", "sample": sample}
         print(json.dumps(line), flush=True)
     h.close()
     if world > 1:

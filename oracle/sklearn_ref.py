@@ -46,3 +46,20 @@ def time_fit(X, init, max_iter, reps=3):
         if best is None or r["seconds"] < best:
             best, n_iter = r["seconds"], r["n_iter"]
     return best, n_iter
+
+
+def time_predict(X, centers, reps=3):
+    """best-of-reps wall time of the CPU path's ``predict`` (labels of X for fixed centres) -> seconds."""
+    from sklearn.cluster import KMeans
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        km = KMeans(n_clusters=centers.shape[0], init=np.asarray(centers), n_init=1, max_iter=1, tol=0.0,
+                    algorithm="lloyd").fit(X[:max(centers.shape[0], min(len(X), 4 * centers.shape[0]))])
+        km.cluster_centers_ = np.ascontiguousarray(centers, dtype=X.dtype)
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            km.predict(X)
+            dt = time.perf_counter() - t0
+            best = dt if best is None or dt < best else best
+    return best
