@@ -1,0 +1,33 @@
+#!/bin/bash
+# First GPU call of the next round: validates what was written after round 1's GPU budget was spent and A/B-measures
+# the prepared opt-in variants.  Run as:  gpurun --timeout 1500 -- 'bash tools/ab_round2.sh'
+# Everything lands in gpurun_out/r2/.  No step depends on another; a failure is logged and the script goes on.
+set -u
+OUT=gpurun_out/r2
+mkdir -p "$OUT"
+run() { name=$1; shift; echo "== $name: $*" | tee -a "$OUT/index.log"; ( "$@" ) > "$OUT/$name.log" 2>&1; echo "rc=$? $name" | tee -a "$OUT/index.log"; }
+
+# 1. correctness of everything new (fp64, callers, distributed world size 1, C-ABI as before)
+run pytest_gpu timeout 900 python -m pytest tests -m gpu -x -q
+run smoke timeout 300 python __graft_entry__.py smoke
+
+# 2. MMA-issue floor of the pair kernel (cta_group::2): decides whether C3's E-step is at 84 % or 63 % of it
+run mma_rate_pair timeout 120 ./tools/micro/mma_rate_pair
+
+# 3. E-step variants at C3 (fused kernel time is in roofline.kernel_ms)
+run bench_c3_default timeout 600 python bench.py --workload C3 --steps 10 --no-e2e --no-cpu
+CUML_B200_CONV_TRUNC=1 run bench_c3_conv_trunc timeout 600 env CUML_B200_CONV_TRUNC=1 python bench.py --workload C3 --steps 10 --no-e2e --no-cpu
+# parity of the truncating converter before its number means anything
+run parity_conv_trunc timeout 600 env CUML_B200_CONV_TRUNC=1 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "single_lloyd_step or dot_accuracy or regime2"
+
+# 4. single-CTA twin (k <= 128): parity first, then C1 / C5
+run parity_solo_v2 timeout 600 env CUML_B200_SOLO_V2=1 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "single_lloyd_step or dot_accuracy or regime2 or transform_matches"
+run bench_c1_default timeout 300 python bench.py --workload C1 --steps 50 --no-e2e --no-cpu
+run bench_c1_solo_v2 timeout 300 env CUML_B200_SOLO_V2=1 python bench.py --workload C1 --steps 50 --no-e2e --no-cpu
+run bench_c5_default timeout 600 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
+run bench_c5_solo_v2 timeout 600 env CUML_B200_SOLO_V2=1 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
+
+# 5. the inference config (new bench workload)
+run bench_c4 timeout 900 python bench.py --workload C4 --steps 3 --no-cpu
+grep -h '^{' "$OUT"/bench_*.log > "$OUT/bench_lines.jsonl" 2>/dev/null
+tail -n 3 "$OUT"/*.log | tail -n 120
