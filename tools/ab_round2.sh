@@ -12,11 +12,12 @@ run pytest_gpu timeout 900 python -m pytest tests -m gpu -x -q
 run smoke timeout 300 python __graft_entry__.py smoke
 
 # 2. MMA-issue floor of the pair kernel (cta_group::2): decides whether C3's E-step is at 84 % or 63 % of it
+[ -x tools/micro/mma_rate_pair ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -Icuml_b200/csrc -o tools/micro/mma_rate_pair tools/micro/mma_rate_pair.cu
 run mma_rate_pair timeout 120 ./tools/micro/mma_rate_pair
 
 # 3. E-step variants at C3 (fused kernel time is in roofline.kernel_ms)
 run bench_c3_default timeout 600 python bench.py --workload C3 --steps 10 --no-e2e --no-cpu
-CUML_B200_CONV_TRUNC=1 run bench_c3_conv_trunc timeout 600 env CUML_B200_CONV_TRUNC=1 python bench.py --workload C3 --steps 10 --no-e2e --no-cpu
+run bench_c3_conv_trunc timeout 600 env CUML_B200_CONV_TRUNC=1 python bench.py --workload C3 --steps 10 --no-e2e --no-cpu
 # parity of the truncating converter before its number means anything
 run parity_conv_trunc timeout 600 env CUML_B200_CONV_TRUNC=1 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "single_lloyd_step or dot_accuracy or regime2"
 
