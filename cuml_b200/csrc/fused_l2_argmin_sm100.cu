@@ -1530,7 +1530,10 @@ bool use_cn_fold()
 bool solo_fold_fits(const TilePlan& t, int k, size_t smem_limit)
 {
   const int k_tiles = static_cast<int>(ceil_div(k, t.bn));
-  return use_cn_fold() && k_tiles <= 4 && t.smem + static_cast<size_t>(1 + k_tiles) * TILE_M * 32 <= smem_limit;
+  // the pieces tile of one centroid tile is bn rows x 32 bytes and must fit the 4 KB fold-tile stride (bn <= 128);
+  // bn = 256 only happens here when the pair kernel is switched off for k > 128
+  return use_cn_fold() && t.bn <= TILE_M && k_tiles <= 4 &&
+         t.smem + static_cast<size_t>(1 + k_tiles) * TILE_M * 32 <= smem_limit;
 }
 
 TilePlan plan_tiles_2cta(int d, int k, size_t smem_limit)
