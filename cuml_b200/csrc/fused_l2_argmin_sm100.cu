@@ -122,7 +122,8 @@ struct Barriers {
 // accumulator tile (BN/4 columns, at least one 32-column chunk); thread = row.  Per row: four independent
 // running (min, argmin) chains, merged with the first-minimum rule; the column parts are merged through
 // shared memory.  The argmin is instruction-issue bound (4 instructions per distance), hence many warps.
-template <bool PAIR, bool DIST = false, bool FOLD1 = false>
+// DIST: 0 = argmin epilogue, 1 = distance matrix (transform), 2 = distance matrix with the lane-pair store pattern
+template <bool PAIR, int DIST = 0, bool FOLD1 = false>
 __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* bars, float* cn_s, float* mrg_v,
                                               int* mrg_i, uint32_t tmem_base, int64_t first_row, int64_t row_stride,
                                               int64_t n_tiles_cta)
@@ -183,6 +184,51 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
 #pragma unroll
             for (int j = 0; j < 32; ++j) o[j] = __uint_as_float(r[j]);
           }
+        }
+        if (DIST == 2) {
+          // opt-in store pattern (CUML_B200_DIST_PAIRST=1 selects the DIST = 2 instantiations; not yet measured): lanes 2i and 2i+1 swap half of every
+          // 8-column group, so each store instruction writes 32 contiguous bytes (a whole sector) of ONE row per
+          // lane pair instead of 16 bytes in two different rows.  Same values, same addresses, other lanes.
+          const int64_t row   = first_row + t * row_stride + rit;
+          const int dist_k    = p.k_sub;
+          const bool odd      = (lane & 1) != 0;
+          const int64_t row_e = row - (odd ? 1 : 0);          // the pair's even / odd rows (consecutive)
+          const int64_t row_o = row_e + 1;
+          const float xx      = (row < p.n) ? __ldg(reinterpret_cast<const float*>(p.labels) + row) : 0.0f;
+          const float* cnc    = cn + c0;
+          if ((dist_k & 3) == 0 && jbase + c0 + 32 <= dist_k) {   // warp-uniform: shuffles are legal
+            float* oe = p.dbg_dots + row_e * static_cast<int64_t>(dist_k) + jbase + c0 + (odd ? 4 : 0);
+            float* oo = p.dbg_dots + row_o * static_cast<int64_t>(dist_k) + jbase + c0 + (odd ? 4 : 0);
+#pragma unroll
+            for (int g8 = 0; g8 < 4; ++g8) {
+              float a[4], b[4], rcv[4];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const int c   = g8 * 8 + j;
+                const float s = fold ? __uint_as_float(r[c]) : __uint_as_float(r[c]) - cnc[c];
+                float v       = fmaxf(xx - 2.0f * s, 0.0f);
+                if (p.raw_slots) v = sqrtf(v);
+                if (j < 4) a[j] = v; else b[j - 4] = v;
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) rcv[j] = __shfl_xor_sync(0xffffffffu, odd ? a[j] : b[j], 1);
+              // even lane: own a -> row_e, partner's a -> row_o;  odd lane: partner's b -> row_e, own b -> row_o
+              const float4 ve = odd ? make_float4(rcv[0], rcv[1], rcv[2], rcv[3]) : make_float4(a[0], a[1], a[2], a[3]);
+              const float4 vo = odd ? make_float4(b[0], b[1], b[2], b[3]) : make_float4(rcv[0], rcv[1], rcv[2], rcv[3]);
+              if (row_e < p.n) *reinterpret_cast<float4*>(oe + g8 * 8) = ve;
+              if (row_o < p.n) *reinterpret_cast<float4*>(oo + g8 * 8) = vo;
+            }
+          } else if (row < p.n) {
+            float* o = p.dbg_dots + row * static_cast<int64_t>(dist_k) + jbase + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = fold ? __uint_as_float(r[j]) : __uint_as_float(r[j]) - cnc[j];
+              float v       = fmaxf(xx - 2.0f * s, 0.0f);
+              if (p.raw_slots) v = sqrtf(v);
+              if (jbase + c0 + j < dist_k) o[j] = v;
+            }
+          }
+          continue;
         }
         if (DIST) {
           // transform: ||x - c||^2 = ||x||^2 - 2 (x.c - 1/2||c||^2); this thread holds 32 consecutive columns of its row
@@ -272,7 +318,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
   }
 }
 
-template <bool DIST>
+template <int DIST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                        const __grid_constant__ CUtensorMap tm_lo, const FusedParams p)
@@ -515,7 +561,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
 // TRUNC (opt-in experiment, CUML_B200_CONV_TRUNC=1): hi = x truncated to tf32, which is what the tensor core reads
 // from the raw fp32 tile anyway, so the converter neither rounds nor rewrites the tile (fewer instructions on the
 // issue-bound d = 64 path) at the price of |lo| <= 2^-11 |x| instead of 2^-12.
-template <bool BF16C, bool DIST = false, bool TRUNC = false>
+template <bool BF16C, int DIST = 0, bool TRUNC = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                             const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_lb,
@@ -832,7 +878,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
 // Single-CTA twin of the CTA-pair kernel (opt-in, CUML_B200_SOLO_V2=1; NOT yet validated on hardware): the same
 // roles, bf16 correction terms and folded half norms for k <= 128, with cta_group::1 instructions and local
 // barriers.  Generated from the pair kernel's source; once measured it is meant to replace fused_l2_argmin_kernel.
-template <bool BF16C, bool DIST = false, bool TRUNC = false>
+template <bool BF16C, int DIST = 0, bool TRUNC = false>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                             const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_lb,
@@ -1773,14 +1819,14 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
       static bool pk_attr = false;
       if (!pk_attr) {
-        CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(h.smem_optin)));
         pk_attr = true;
       }
       EventPair ev{};
       if (h.timing) ev = h.begin_event();
       const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
-      fused_l2_argmin_kernel<false><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+      fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
       CB2_CHECK_LAUNCH();
       if (h.timing) h.end_event(ev, true);
     }
@@ -1862,7 +1908,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     p.dbg_dots  = dist->out;
     p.labels    = reinterpret_cast<int32_t*>(const_cast<float*>(dist->xnorm));
     p.k_sub     = k;
-    p.raw_slots = dist->sqrt;
+    p.raw_slots = dist->sqrt ? 1 : 0;
   }
   {
     const char* e = std::getenv("CUML_B200_DBG_SKIP");
@@ -1889,20 +1935,27 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
 
   static bool attr_set = false;
   if (!attr_set) {
-    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
-    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
-    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(h.smem_optin)));
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(h.smem_optin)));
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
-    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
     attr_set = true;
   }
+  // transform only: lane-pair store pattern of the distance-matrix epilogue (DIST = 2 instantiations), opt-in
+  static const bool dist_pair_store =
+    std::getenv("CUML_B200_DIST_PAIRST") && std::atoi(std::getenv("CUML_B200_DIST_PAIRST")) != 0;
   EventPair ev{};
   if (h.timing) ev = h.begin_event();
   const long long grid_dbg = pair ? h.sm_count / 2 : h.sm_count;
@@ -1925,11 +1978,13 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
       static const bool conv_trunc = std::getenv("CUML_B200_CONV_TRUNC") && std::atoi(std::getenv("CUML_B200_CONV_TRUNC")) != 0;
       if (conv_trunc)
-        fused_l2_argmin_2cta_kernel<true, false, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+        fused_l2_argmin_2cta_kernel<true, 0, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
       else
         fused_l2_argmin_2cta_kernel<true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+    } else if (dist && dist_pair_store) {
+      fused_l2_argmin_2cta_kernel<false, 2><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     } else if (dist) {
-      fused_l2_argmin_2cta_kernel<false, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
+      fused_l2_argmin_2cta_kernel<false, 1><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     } else {
       fused_l2_argmin_2cta_kernel<false><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     }
@@ -1944,11 +1999,11 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     static bool solo_attr = false;
     if (!solo_attr) {
-      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, false, false>,
+      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, 0, false>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
-      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<false, false, false>,
+      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<false, 0, false>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
-      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<false, true, false>,
+      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<false, 1, false>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
       solo_attr = true;
     }
@@ -1959,16 +2014,17 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       CUtensorMap tm_lb = make_map_2d(cen.lb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
                                       b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-      fused_l2_argmin_solo_kernel<true, false, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+      fused_l2_argmin_solo_kernel<true, 0, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
     } else if (dist) {
-      fused_l2_argmin_solo_kernel<false, true, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
+      fused_l2_argmin_solo_kernel<false, 1, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     } else {
-      fused_l2_argmin_solo_kernel<false, false, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
+      fused_l2_argmin_solo_kernel<false, 0, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     }
   } else {
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
-    if (dist) fused_l2_argmin_kernel<true><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
-    else fused_l2_argmin_kernel<false><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+    if (dist && dist_pair_store) fused_l2_argmin_kernel<2><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+    else if (dist) fused_l2_argmin_kernel<1><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+    else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
   }
   CB2_CHECK_LAUNCH();
   if (h.timing) h.end_event(ev, true);

@@ -30,6 +30,11 @@ run bench_c5_default timeout 600 python bench.py --workload C5 --steps 10 --no-e
 run bench_c5_solo_v2_nopack timeout 600 env CUML_B200_SOLO_V2=1 CUML_B200_PACK=0 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
 run bench_c5_nopack timeout 600 env CUML_B200_PACK=0 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
 
+# 4b. transform: lane-pair store pattern (DIST = 2 instantiations) -- parity, then the C4-shape probe both ways
+run parity_dist_pairst timeout 600 env CUML_B200_DIST_PAIRST=1 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "transform"
+run c4_probe_default timeout 600 python tools/c4_probe.py
+run c4_probe_pairst timeout 600 env CUML_B200_DIST_PAIRST=1 python tools/c4_probe.py
+
 # 5. the inference config (new bench workload)
 run bench_c4 timeout 900 python bench.py --workload C4 --steps 3 --no-cpu
 grep -h '^{' "$OUT"/bench_*.log > "$OUT/bench_lines.jsonl" 2>/dev/null
