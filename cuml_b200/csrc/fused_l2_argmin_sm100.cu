@@ -45,6 +45,19 @@ namespace {
     }                                               \
   } while (0)
 
+// the same for kernels that take the profiling as a template parameter CLK (the default instantiations carry no
+// trace of it)
+#define CB2_WAIT_CLK(bar, parity, acc)              \
+  do {                                              \
+    if constexpr (CLK) {                            \
+      const long long t__ = clock64();              \
+      ptx::mbar_wait_park((bar), (parity));         \
+      (acc) += clock64() - t__;                     \
+    } else {                                        \
+      ptx::mbar_wait_park((bar), (parity));         \
+    }                                               \
+  } while (0)
+
 constexpr int TILE_M       = 128;
 constexpr int KBLOCK       = 32;              // fp32 elements per 128-byte swizzle row
 constexpr int KBLOCK_BYTES = TILE_M * 128;    // one K-block of an A tile: 16 KB
@@ -123,7 +136,7 @@ struct Barriers {
 // running (min, argmin) chains, merged with the first-minimum rule; the column parts are merged through
 // shared memory.  The argmin is instruction-issue bound (4 instructions per distance), hence many warps.
 // DIST: 0 = argmin epilogue, 1 = distance matrix (transform), 2 = distance matrix with the lane-pair store pattern
-template <bool PAIR, int DIST = 0, bool FOLD1 = false>
+template <bool PAIR, int DIST = 0, bool FOLD1 = false, bool CLK = false>
 __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* bars, float* cn_s, float* mrg_v,
                                               int* mrg_i, uint32_t tmem_base, int64_t first_row, int64_t row_stride,
                                               int64_t n_tiles_cta)
@@ -151,6 +164,8 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
   float pre = 0.f;
   auto fetch_cn = [&](int nt) { pre = __ldg(p.cnh + static_cast<int64_t>(nt) * p.bn + (et < p.bn ? et : 0)); };
   const bool fold = (PAIR || FOLD1) && p.fold;   // accumulator already holds x.c - 1/2||c||^2: pick the maximum
+  long long w_acc = 0, w_merge = 0, t_hold = 0, t_start = 0;   // CLK only: waits for the accumulator / the merge
+  if constexpr (CLK) t_start = clock64();                      // barriers, time an accumulator is held
   if (!fold) fetch_cn(0);
   if (p.k_tiles == 1 && !fold) {  // single centroid tile: stage the half norms once
     if (et < p.bn) cn_s[et] = pre;
@@ -168,7 +183,9 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
         fetch_cn(nt + 1 == p.k_tiles ? 0 : nt + 1);
         ptx::named_bar_sync(1, EPI_THREADS);
       }
-      ptx::mbar_wait_park(ptx::smem_u32(&bars->acc_full[acc]), pacc);
+      CB2_WAIT_CLK(ptx::smem_u32(&bars->acc_full[acc]), pacc, w_acc);
+      long long t_got = 0;
+      if constexpr (CLK) t_got = clock64();
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.bn;
       const int jbase      = nt * p.bn;
@@ -293,6 +310,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
         if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->acc_empty[acc]), 0));
         else ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[acc]));
       }
+      if constexpr (CLK) t_hold += clock64() - t_got;
     }
     if (DIST) continue;   // distance-matrix mode: nothing to merge, no labels
     // merge the chains: smaller value wins, equal values -> smaller index (first minimum)
@@ -304,7 +322,13 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
       mrg_v[(part - 1) * TILE_M + rit] = b0;
       mrg_i[(part - 1) * TILE_M + rit] = i0;
     }
-    ptx::named_bar_sync(2, EPI_THREADS);
+    if constexpr (CLK) {
+      const long long t__ = clock64();
+      ptx::named_bar_sync(2, EPI_THREADS);
+      w_merge += clock64() - t__;
+    } else {
+      ptx::named_bar_sync(2, EPI_THREADS);
+    }
     if (lead) {
       for (int q = 1; q < ppg; ++q) {
         const float ov = mrg_v[(part + q - 1) * TILE_M + rit];
@@ -314,7 +338,18 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
       const int64_t row = (first_row + t * row_stride + rit) * p.pack + grp;
       if (row < p.n) p.labels[row] = i0;
     }
-    ptx::named_bar_sync(3, EPI_THREADS);  // mrg_* may be overwritten by the next tile
+    if constexpr (CLK) {
+      const long long t__ = clock64();
+      ptx::named_bar_sync(3, EPI_THREADS);
+      w_merge += clock64() - t__;
+    } else {
+      ptx::named_bar_sync(3, EPI_THREADS);  // mrg_* may be overwritten by the next tile
+    }
+  }
+  if constexpr (CLK) {
+    if (p.dbg_clk && blockIdx.x == 0 && et == 0) {
+      p.dbg_clk[8] = w_acc; p.dbg_clk[9] = clock64() - t_start; p.dbg_clk[10] = t_hold; p.dbg_clk[11] = w_merge;
+    }
   }
 }
 
@@ -561,7 +596,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
 // TRUNC (opt-in experiment, CUML_B200_CONV_TRUNC=1): hi = x truncated to tf32, which is what the tensor core reads
 // from the raw fp32 tile anyway, so the converter neither rounds nor rewrites the tile (fewer instructions on the
 // issue-bound d = 64 path) at the price of |lo| <= 2^-11 |x| instead of 2^-12.
-template <bool BF16C, int DIST = 0, bool TRUNC = false>
+template <bool BF16C, int DIST = 0, bool TRUNC = false, bool CLK = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(PAIR_THREADS, 1)
 fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                             const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_lb,
@@ -639,6 +674,8 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     {
       uint32_t a_cnt = 0;
       Ring ra;
+      long long w_empty = 0, t_start = 0;
+      if constexpr (CLK) t_start = clock64();
       const int a_reps = p.a_stream ? p.k_tiles : 1;
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
         const int32_t row0 = static_cast<int32_t>(pt * 2 * TILE_M + cta_rank * TILE_M);
@@ -656,7 +693,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
         for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
           const uint32_t sa = ra.slot, pa = ra.phase;
           ra.advance(p.a_slots);
-          ptx::mbar_wait_park(ptx::smem_u32(&bars->a_empty[sa]), pa ^ 1u);
+          CB2_WAIT_CLK(ptx::smem_u32(&bars->a_empty[sa]), pa ^ 1u, w_empty);
           if (ptx::elect_one()) {
             const uint32_t full = ptx::smem_u32(&bars->a_raw_full[sa]);
             ptx::mbar_arrive_expect_tx(full, KBLOCK_BYTES);
@@ -664,6 +701,9 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
           }
           __syncwarp();
         }
+      }
+      if constexpr (CLK) {
+        if (p.dbg_clk && blockIdx.x == 0 && lane == 0) { p.dbg_clk[0] = w_empty; p.dbg_clk[1] = clock64() - t_start; }
       }
     }
   } else if (warp == 2) {
@@ -721,13 +761,15 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
                                (static_cast<uint32_t>(conv_lc & 1) << 3);
     uint32_t a_cnt = 0;
       Ring ra;
+    long long w_raw = 0, t_start = 0;
+    if constexpr (CLK) t_start = clock64();
     const int a_reps = p.a_stream ? p.k_tiles : 1;
     for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
       for (int rep = 0; rep < a_reps; ++rep)
       for (int kbi = 0; kbi < p.kb; ++kbi, ++a_cnt) {
         const uint32_t sa = ra.slot, pa = ra.phase;
         ra.advance(p.a_slots);
-        ptx::mbar_wait_park(ptx::smem_u32(&bars->a_raw_full[sa]), pa);
+        CB2_WAIT_CLK(ptx::smem_u32(&bars->a_raw_full[sa]), pa, w_raw);
         uint4* hi = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES);
         uint4* lo = reinterpret_cast<uint4*>(gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES);
         const int rem_f       = p.d - kbi * KBLOCK;
@@ -776,6 +818,9 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
         if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->a_ready[sa]), 0));
       }
     }
+    if constexpr (CLK) {
+      if (p.dbg_clk && blockIdx.x == 0 && ct == 0) { p.dbg_clk[2] = w_raw; p.dbg_clk[3] = clock64() - t_start; }
+    }
   } else if (warp == 1) {
     // ===================== MMA issuer (pair leader only; warp-uniform loop, one elected lane issues) ====
     if (leader) {
@@ -784,6 +829,8 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
       (void)idesc16;
       uint32_t b_cnt = 0, acc_cnt = 0;
       Ring ra_tile, ra_run, rb, racc;
+      long long w_acc = 0, w_a = 0, w_b = 0, t_start = 0;
+      if constexpr (CLK) t_start = clock64();
       if (p.fold && pair < pair_tiles) ptx::mbar_wait_park(ptx::smem_u32(&bars->cn_full), 0u);
       const uint32_t first_acc = p.fold ? 1u : 0u;   // the fold MMA initialises the accumulator
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs, ra_tile.advance_by(p.kb, p.a_slots)) {
@@ -791,7 +838,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
           const uint32_t acc = racc.slot, pacc = racc.phase;
           racc.advance(p.n_acc);
           Ring ra = p.a_stream ? ra_run : ra_tile;
-          ptx::mbar_wait_park(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
+          CB2_WAIT_CLK(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u, w_acc);
           const uint32_t d_tmem = tmem_base + acc * p.bn;
           if (p.fold) {
             ptx::tc_fence_after();
@@ -803,15 +850,15 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sa = ra.slot, pa = ra.phase;
             ra.advance(p.a_slots);
-            if (nt == 0 || p.a_stream) ptx::mbar_wait_park(ptx::smem_u32(&bars->a_ready[sa]), pa);
+            if (nt == 0 || p.a_stream) CB2_WAIT_CLK(ptx::smem_u32(&bars->a_ready[sa]), pa, w_a);
             uint32_t sb = rb.slot;
             const uint32_t pb = rb.phase;
             rb.advance(p.b_stages);
             if (p.b_resident) {
               sb = nt * p.kb + kbi;
-              if (pt == pair) ptx::mbar_wait_park(ptx::smem_u32(&bars->b_full[sb]), 0u);
+              if (pt == pair) CB2_WAIT_CLK(ptx::smem_u32(&bars->b_full[sb]), 0u, w_b);
             } else {
-              ptx::mbar_wait_park(ptx::smem_u32(&bars->b_full[sb]), pb);
+              CB2_WAIT_CLK(ptx::smem_u32(&bars->b_full[sb]), pb, w_b);
             }
             ptx::tc_fence_after();
             const uint64_t da_hi = ptx::umma_desc_sw128(a_base + sa * A_SLOT_BYTES);
@@ -860,11 +907,16 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
           __syncwarp();
         }
       }
+      if constexpr (CLK) {
+        if (p.dbg_clk && blockIdx.x == 0 && lane == 0) {
+          p.dbg_clk[4] = w_acc; p.dbg_clk[5] = w_a; p.dbg_clk[6] = w_b; p.dbg_clk[7] = clock64() - t_start;
+        }
+      }
     }
   } else if (warp >= 8 && warp < 24) {
     // ===================== epilogue (own 128 rows of the pair tile) =====================
     const int64_t n_mine = (pair_tiles > pair) ? (pair_tiles - pair + n_pairs - 1) / n_pairs : 0;
-    epilogue_role<true, DIST>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, pair * 2 * TILE_M + cta_rank * TILE_M,
+    epilogue_role<true, DIST, false, CLK>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, pair * 2 * TILE_M + cta_rank * TILE_M,
                         n_pairs * 2 * TILE_M, n_mine);
   }
 
@@ -1977,7 +2029,15 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                       b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
       static const bool conv_trunc = std::getenv("CUML_B200_CONV_TRUNC") && std::atoi(std::getenv("CUML_B200_CONV_TRUNC")) != 0;
-      if (conv_trunc)
+      if (want_clk && !conv_trunc) {   // role-level cycle counters: a separate instantiation, printed below
+        static bool clk_attr = false;
+        if (!clk_attr) {
+          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true, 0, false, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
+          clk_attr = true;
+        }
+        fused_l2_argmin_2cta_kernel<true, 0, false, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+      } else if (conv_trunc)
         fused_l2_argmin_2cta_kernel<true, 0, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
       else
         fused_l2_argmin_2cta_kernel<true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);

@@ -15,6 +15,9 @@ run smoke timeout 300 python __graft_entry__.py smoke
 [ -x tools/micro/mma_rate_pair ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -Icuml_b200/csrc -o tools/micro/mma_rate_pair tools/micro/mma_rate_pair.cu
 run mma_rate_pair timeout 120 ./tools/micro/mma_rate_pair
 
+# 2b. where the C3 E-step waits: role-level cycle counters of the pair kernel (CLK instantiation, CTA 0)
+run clk_c3 timeout 600 env CUML_B200_DBG_CLK=1 python bench.py --workload C3 --steps 2 --warmup 3 --no-e2e --no-cpu
+
 # 3. E-step variants at C3 (fused kernel time is in roofline.kernel_ms)
 run bench_c3_default timeout 600 python bench.py --workload C3 --steps 10 --no-e2e --no-cpu
 run bench_c3_conv_trunc timeout 600 env CUML_B200_CONV_TRUNC=1 python bench.py --workload C3 --steps 10 --no-e2e --no-cpu
