@@ -68,6 +68,9 @@ struct Handle {
   double* pinned = nullptr;
   // solver cached by the lloyd_step measurement hook (freed with the handle)
   std::shared_ptr<void> step_cache;
+  // second stream + hand-off events of the opt-in E-step / M-step overlap (CUML_B200_OVERLAP), created on first use
+  cudaStream_t aux_stream = nullptr;
+  cudaEvent_t ev_fwd = nullptr, ev_back = nullptr;
 
   EventPair begin_event();
   void end_event(EventPair ev, bool fused);

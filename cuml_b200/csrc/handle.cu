@@ -184,6 +184,12 @@ void free_handle(Handle* h)
   if (!h) return;
   cudaStreamSynchronize(h->stream);
   h->step_cache.reset();
+  if (h->aux_stream) {
+    cudaStreamSynchronize(h->aux_stream);
+    cudaStreamDestroy(h->aux_stream);
+  }
+  if (h->ev_fwd) cudaEventDestroy(h->ev_fwd);
+  if (h->ev_back) cudaEventDestroy(h->ev_back);
   nccl::destroy(*h);
   for (auto& v : {&h->fused_events, &h->update_events, &h->event_pool})
     for (auto& e : *v) {

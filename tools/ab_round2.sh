@@ -24,6 +24,14 @@ run bench_c3_conv_trunc timeout 600 env CUML_B200_CONV_TRUNC=1 python bench.py -
 # parity of the truncating converter before its number means anything
 run parity_conv_trunc timeout 600 env CUML_B200_CONV_TRUNC=1 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "single_lloyd_step or dot_accuracy or regime2"
 
+# 3b. E-step / M-step overlap on two streams (chunks:m_sms); parity at the sizes that take the overlapped path first
+run parity_overlap timeout 900 env CUML_B200_OVERLAP=8:24 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "large_property or full_size_c3"
+for cfg in 8:24 8:32 16:24 4:24; do
+  run bench_c3_overlap_${cfg/:/_} timeout 600 env CUML_B200_OVERLAP=$cfg python bench.py --workload C3 --steps 10 --no-e2e --no-cpu
+done
+run bench_c2_overlap_8_24 timeout 600 env CUML_B200_OVERLAP=8:24 python bench.py --workload C2 --steps 10 --no-e2e --no-cpu
+run bench_c2_default timeout 600 python bench.py --workload C2 --steps 10 --no-e2e --no-cpu
+
 # 4. single-CTA twin (k <= 128): parity first, then C1 / C5
 run parity_solo_v2 timeout 600 env CUML_B200_SOLO_V2=1 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "single_lloyd_step or dot_accuracy or regime2 or transform_matches"
 run bench_c1_default timeout 300 python bench.py --workload C1 --steps 50 --no-e2e --no-cpu
