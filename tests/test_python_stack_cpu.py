@@ -66,6 +66,10 @@ def test_bodies_of_estimator_level_gpu_tests(fake):
     test_kmeans_gpu.test_doctest_kat_and_empty_cluster_rule()
     test_callers.test_kmeans_bin_edges_gpu()
     test_callers.test_kmeans_sampling_gpu()
+    import glob
+    import os
+    for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "sk_*.npz"))):
+        test_kmeans_gpu.test_fit_matches_reference_cpu_path_golden(path)
 
 
 def test_distributed_estimator_world_size_one(fake, monkeypatch):
