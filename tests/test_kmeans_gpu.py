@@ -210,31 +210,6 @@ def test_predict_transform_score_match_oracle():
     assert abs(-km.score(X, sample_weight=w) - in_w) / in_w <= 1e-5
 
 
-def test_fp64_fit_predict_transform_match_oracle():
-    # the double overloads (reference cpp/include/cuml/cluster/kmeans.hpp:47-79,166-195,222-242): fp64 end to end
-    from cuml_b200.cluster import KMeans
-    from oracle import blobs, lloyd
-    X, centres, _ = blobs.make_blobs(20000, 24, 16)
-    X64 = X.astype(np.float64)
-    init = blobs.parity_init(centres).astype(np.float64)
-    w = np.random.default_rng(2).uniform(0.5, 2, len(X64))
-    for sw in (None, w):
-        km = KMeans(n_clusters=16, init=init, max_iter=20, tol=1e-9).fit(X64, sample_weight=sw)
-        o = lloyd.fit(X64, init, max_iter=20, tol=1e-9, sample_weight=sw)
-        assert km.cluster_centers_.dtype == np.float64
-        assert np.abs(km.cluster_centers_ - o["centroids"]).max() / np.abs(o["centroids"]).max() <= 1e-10
-        assert abs(km.inertia_ - o["inertia"]) / o["inertia"] <= 1e-10
-        assert (km.labels_ == o["labels"]).mean() >= 0.9999
-    Cc = km.cluster_centers_
-    lab_o, inertia_o = lloyd.predict(X64, Cc)
-    assert (km.predict(X64) == lab_o).mean() >= 0.9999
-    assert abs(-km.score(X64) - inertia_o) / inertia_o <= 1e-10
-    T = km.transform(X64[:1000])
-    assert T.dtype == np.float64
-    To = lloyd.transform(X64[:1000], Cc)
-    assert np.abs(T - To).max() / To.max() < 1e-10
-
-
 @pytest.mark.parametrize("n,d,k,sqrt", [(3001, 64, 300, False), (2000, 32, 40, True), (1500, 128, 1030, True),
                                         (2500, 100, 129, False), (1000, 20, 5, False)])
 def test_transform_matches_oracle(env, n, d, k, sqrt):
@@ -559,3 +534,28 @@ def test_cpp_surface_example_kat(tmp_path):
     subprocess.run(cmd, check=True, capture_output=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout + r.stderr
+
+
+def test_fp64_fit_predict_transform_match_oracle():
+    # the double overloads (reference cpp/include/cuml/cluster/kmeans.hpp:47-79,166-195,222-242): fp64 end to end
+    from cuml_b200.cluster import KMeans
+    from oracle import blobs, lloyd
+    X, centres, _ = blobs.make_blobs(20000, 24, 16)
+    X64 = X.astype(np.float64)
+    init = blobs.parity_init(centres).astype(np.float64)
+    w = np.random.default_rng(2).uniform(0.5, 2, len(X64))
+    for sw in (None, w):
+        km = KMeans(n_clusters=16, init=init, max_iter=20, tol=1e-9).fit(X64, sample_weight=sw)
+        o = lloyd.fit(X64, init, max_iter=20, tol=1e-9, sample_weight=sw)
+        assert km.cluster_centers_.dtype == np.float64
+        assert np.abs(km.cluster_centers_ - o["centroids"]).max() / np.abs(o["centroids"]).max() <= 1e-10
+        assert abs(km.inertia_ - o["inertia"]) / o["inertia"] <= 1e-10
+        assert (km.labels_ == o["labels"]).mean() >= 0.9999
+    Cc = km.cluster_centers_
+    lab_o, inertia_o = lloyd.predict(X64, Cc)
+    assert (km.predict(X64) == lab_o).mean() >= 0.9999
+    assert abs(-km.score(X64) - inertia_o) / inertia_o <= 1e-10
+    T = km.transform(X64[:1000])
+    assert T.dtype == np.float64
+    To = lloyd.transform(X64[:1000], Cc)
+    assert np.abs(T - To).max() / To.max() < 1e-10

@@ -57,7 +57,7 @@ def test_partition_list_fit_single_rank(fake):
 def test_bodies_of_estimator_level_gpu_tests(fake):
     """the same assertions the GPU box checks, with the library replaced by the oracle: a failure here is a bug in
     the Python layer or in the test itself, found without spending GPU time"""
-    import test_callers
+    import test_z_callers as test_callers
     import test_kmeans_gpu
     test_kmeans_gpu.test_fp64_fit_predict_transform_match_oracle()
     test_kmeans_gpu.test_predict_transform_score_match_oracle()
