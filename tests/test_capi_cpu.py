@@ -171,3 +171,23 @@ def test_chunked_host_predict_logic(monkeypatch):
     wn = w * (len(X) / w.sum())
     assert abs(inertia - (wn * d2.min(1)).sum()) / inertia < 1e-6
 
+
+
+@pytest.mark.parametrize("src", ["kmeans_example.cpp", "kmeans_bench.cpp"])
+def test_cpp_surface_compiles_and_links(tmp_path, src):
+    # the C++ ML::kmeans::* mirror (include/cuml/cluster/kmeans.hpp) against the built library: every forwarder the
+    # examples use resolves to an exported C-ABI symbol (no GPU needed to compile and link)
+    import shutil
+    import subprocess
+    from cuml_b200 import build
+    gxx = shutil.which("g++")
+    if gxx is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("no g++ / CUDA headers")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(build.lib_path())
+    exe = str(tmp_path / src.replace(".cpp", ""))
+    cmd = [gxx, "-std=c++17", "-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include",
+           os.path.join(root, "examples", src), "-L" + libdir, "-lcuml_b200", "-L/usr/local/cuda/lib64", "-lcudart",
+           "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -46,6 +46,10 @@ run parity_dist_pairst timeout 600 env CUML_B200_DIST_PAIRST=1 python -m pytest 
 run c4_probe_default timeout 600 python tools/c4_probe.py
 run c4_probe_pairst timeout 600 env CUML_B200_DIST_PAIRST=1 python tools/c4_probe.py
 
+# 4c. the reference's C++ benchmark shapes through the C++ surface (examples/kmeans_bench.cpp)
+g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include examples/kmeans_bench.cpp -Lcuml_b200/lib -lcuml_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/cuml_b200/lib -o /tmp/kmeans_bench
+run cpp_bench timeout 900 /tmp/kmeans_bench
+
 # 5. the inference config (new bench workload)
 run bench_c4 timeout 900 python bench.py --workload C4 --steps 3 --no-cpu
 grep -h '^{' "$OUT"/bench_*.log > "$OUT/bench_lines.jsonl" 2>/dev/null
