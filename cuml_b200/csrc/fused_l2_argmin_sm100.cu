@@ -135,7 +135,8 @@ struct Barriers {
 // accumulator tile (BN/4 columns, at least one 32-column chunk); thread = row.  Per row: four independent
 // running (min, argmin) chains, merged with the first-minimum rule; the column parts are merged through
 // shared memory.  The argmin is instruction-issue bound (4 instructions per distance), hence many warps.
-// DIST: 0 = argmin epilogue, 1 = distance matrix (transform), 2 = distance matrix with the lane-pair store pattern
+// DIST: 0 = argmin epilogue, 1 = distance matrix (transform), 2 = distance matrix with the lane-pair store pattern,
+//       3 = argmin epilogue that also stores the winning value 1/2||c||^2 - x.c per row (seeding: min distance update)
 template <bool PAIR, int DIST = 0, bool FOLD1 = false, bool CLK = false>
 __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* bars, float* cn_s, float* mrg_v,
                                               int* mrg_i, uint32_t tmem_base, int64_t first_row, int64_t row_stride,
@@ -247,7 +248,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
           }
           continue;
         }
-        if (DIST) {
+        if (DIST == 1) {
           // transform: ||x - c||^2 = ||x||^2 - 2 (x.c - 1/2||c||^2); this thread holds 32 consecutive columns of its row
           const int64_t row = first_row + t * row_stride + rit;
           if (row < p.n) {
@@ -312,7 +313,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
       }
       if constexpr (CLK) t_hold += clock64() - t_got;
     }
-    if (DIST) continue;   // distance-matrix mode: nothing to merge, no labels
+    if (DIST == 1 || DIST == 2) continue;   // distance-matrix mode: nothing to merge, no labels
     // merge the chains: smaller value wins, equal values -> smaller index (first minimum)
     if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
     if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
@@ -336,7 +337,10 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
         if (ov < b0 || (ov == b0 && oi < i0)) { b0 = ov; i0 = oi; }
       }
       const int64_t row = (first_row + t * row_stride + rit) * p.pack + grp;
-      if (row < p.n) p.labels[row] = i0;
+      if (row < p.n) {
+        p.labels[row] = i0;
+        if (DIST == 3) p.dbg_dots[row] = b0;   // b0 = 1/2||c||^2 - x.c of the winner in both (folded / staged) modes
+      }
     }
     if constexpr (CLK) {
       const long long t__ = clock64();
@@ -1841,10 +1845,16 @@ bool tc_transform_supported(const Handle& h, int64_t d, int k)
          !use_ts(h, static_cast<int>(d), k);
 }
 
+bool tc_best_supported(const Handle& h, int d, int k)
+{
+  return h.cc_major == 10 && tc_supported(d, k) && !use_ts(h, d, k);
+}
+
 void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen, int32_t* labels,
-               float* dbg_dots, const TcDistOut* dist)
+               float* dbg_dots, const TcDistOut* dist, float* best_out)
 {
   if (n == 0) return;
+  CB2_EXPECTS(!best_out || (!dbg_dots && !dist && labels), "best-value output excludes the debug dump and the distance matrix");
   CB2_EXPECTS(!dist || cen.pack == 1, "distance-matrix mode does not support row packing");
   CB2_EXPECTS(h.cc_major == 10, "the tcgen05 k-means engine needs an sm_100-class GPU (B200)");
   CB2_EXPECTS(reinterpret_cast<uintptr_t>(X) % 16 == 0, "X must be 16-byte aligned for TMA");
@@ -1861,7 +1871,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       uint32_t cols = 32;
       while (cols < static_cast<uint32_t>(p.n_acc * t.bn)) cols <<= 1;
       p.tmem_cols = cols;
-      p.cnh = cen.cnh.get(); p.labels = labels; p.dbg_dots = nullptr;
+      p.cnh = cen.cnh.get(); p.labels = labels; p.dbg_dots = best_out;   // DIST = 3: winning value per row
       CUtensorMap tm_x  = make_map_2d(X, static_cast<uint64_t>(2 * d), static_cast<uint64_t>(n2),
                                       static_cast<uint64_t>(2 * d) * sizeof(float), KBLOCK, TILE_M,
                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
@@ -1873,22 +1883,26 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       if (!pk_attr) {
         CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(h.smem_optin)));
+        CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(h.smem_optin)));
         pk_attr = true;
       }
       EventPair ev{};
       if (h.timing) ev = h.begin_event();
       const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
-      fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+      if (best_out) fused_l2_argmin_kernel<3><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+      else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
       CB2_CHECK_LAUNCH();
       if (h.timing) h.end_event(ev, true);
     }
-    if (n & 1) {
+    if (n & 1) {   // (labels only: a caller that wants the winning value of an odd last row computes it itself)
       assign_tail_row_kernel<<<1, 32, 0, h.stream>>>(X + (n - 1) * d, d, k, cen.hi.get(), cen.lo.get(), labels + (n - 1));
       CB2_CHECK_LAUNCH();
     }
     return;
   }
   if (use_ts(h, d, k)) {
+    CB2_EXPECTS(!best_out, "the A-in-TMEM variant has no best-value epilogue");
     const TsPlan tp = plan_ts(h, d, k);
     CB2_EXPECTS(tp.bn == cen.block_n, "centroid operand buffers were prepared for a different tile plan");
     FusedParams p{};
@@ -1955,7 +1969,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   p.tmem_cols = cols;
   p.cnh       = cen.cnh.get();
   p.labels    = labels;
-  p.dbg_dots  = dbg_dots;
+  p.dbg_dots  = best_out ? best_out : dbg_dots;   // DIST = 3 instantiations store the winning value there
   if (dist) {   // see FusedParams: idle fields carry the distance-matrix arguments
     p.dbg_dots  = dist->out;
     p.labels    = reinterpret_cast<int32_t*>(const_cast<float*>(dist->xnorm));
@@ -1997,6 +2011,12 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                   static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(h.smem_optin)));
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(h.smem_optin)));
+    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2029,7 +2049,9 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                       b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
       static const bool conv_trunc = std::getenv("CUML_B200_CONV_TRUNC") && std::atoi(std::getenv("CUML_B200_CONV_TRUNC")) != 0;
-      if (want_clk && !conv_trunc) {   // role-level cycle counters: a separate instantiation, printed below
+      if (best_out) {
+        fused_l2_argmin_2cta_kernel<true, 3><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+      } else if (want_clk && !conv_trunc) {   // role-level cycle counters: a separate instantiation, printed below
         static bool clk_attr = false;
         if (!clk_attr) {
           CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true, 0, false, true>,
@@ -2041,6 +2063,8 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
         fused_l2_argmin_2cta_kernel<true, 0, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
       else
         fused_l2_argmin_2cta_kernel<true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+    } else if (best_out) {
+      fused_l2_argmin_2cta_kernel<false, 3><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     } else if (dist && dist_pair_store) {
       fused_l2_argmin_2cta_kernel<false, 2><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     } else if (dist) {
@@ -2048,7 +2072,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     } else {
       fused_l2_argmin_2cta_kernel<false><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     }
-  } else if (use_solo_v2()) {
+  } else if (use_solo_v2() && !best_out) {
     // opt-in single-CTA twin of the pair kernel (see fused_l2_argmin_solo_kernel)
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
     p.fold = (cen.fold && !dbg_dots && solo_fold_fits(t, k, h.smem_optin)) ? 1 : 0;
@@ -2082,7 +2106,8 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     }
   } else {
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
-    if (dist && dist_pair_store) fused_l2_argmin_kernel<2><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+    if (best_out) fused_l2_argmin_kernel<3><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+    else if (dist && dist_pair_store) fused_l2_argmin_kernel<2><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
     else if (dist) fused_l2_argmin_kernel<1><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
     else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
   }

@@ -38,8 +38,10 @@ struct TcDistOut {
   const float* xnorm = nullptr;   // [n] ||x_i||^2
   int sqrt           = 0;
 };
+// best_out (optional, [n]): the winning value 1/2||c_label||^2 - x.c per row, i.e. (min distance - ||x||^2) / 2
 void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen,
-               int32_t* labels, float* dbg_dots = nullptr, const TcDistOut* dist = nullptr);
+               int32_t* labels, float* dbg_dots = nullptr, const TcDistOut* dist = nullptr, float* best_out = nullptr);
+bool tc_best_supported(const Handle& h, int d, int k);
 bool tc_transform_supported(const Handle& h, int64_t d, int k);
 
 // ---- M-step: centroid sums / weights / exact inertia ----------------------------------------

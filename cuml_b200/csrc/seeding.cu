@@ -167,6 +167,17 @@ __global__ void kpp_update_kernel(const T* __restrict__ X, int64_t n, int d, con
   }
 }
 
+// mind_i = [min(mind_i, ] max(||x_i||^2 + 2 best_i, 0) [)]  -- best_i = 1/2||c||^2 - x_i.c of the nearest new candidate
+// (the winning value the fused tensor-core kernel stores next to the label)
+__global__ void min_from_best_kernel(const float* __restrict__ xn, const float* __restrict__ best,
+                                     float* __restrict__ mind, int64_t n, int fresh)
+{
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = fmaxf(xn[i] + 2.0f * best[i], 0.0f);
+  mind[i]       = fresh ? v : fminf(mind[i], v);
+}
+
 template <typename T>
 double weighted_total(Handle& h, const T* v, const T* w, int64_t n)
 {
@@ -371,7 +382,59 @@ void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params,
   }
 
   DevBuf<T> cn(cap, h.stream);
+  // Opt-in (CUML_B200_SEED_TC=1, not yet measured): the min-distance updates of the rounds run on the fused tensor-core
+  // kernel (its DIST = 3 epilogue stores the winning value next to the label) instead of the CUDA-core kernel:
+  // mind = ||x||^2 + 2 (1/2||c||^2 - x.c).  ||x||^2 is computed once per partition.
+  bool seed_tc = false;
+  std::vector<DevBuf<float>> xn_tc, best_tc;
+  std::vector<DevBuf<int32_t>> lab_tc;
+  TcCentroids cen_tc;
+  if constexpr (std::is_same<T, float>::value) {
+    static const bool env_on = std::getenv("CUML_B200_SEED_TC") && std::atoi(std::getenv("CUML_B200_SEED_TC")) != 0;
+    seed_tc = env_on && h.cc_major == 10 && engine_from_env(ctx.engine) != ENGINE_SIMT;
+    for (auto& pt : ctx.parts)
+      if (pt.n > 0 && reinterpret_cast<uintptr_t>(pt.X) % 16 != 0) seed_tc = false;
+    if (seed_tc) {
+      xn_tc.resize(ctx.parts.size());
+      best_tc.resize(ctx.parts.size());
+      lab_tc.resize(ctx.parts.size());
+      for (size_t p = 0; p < ctx.parts.size(); ++p) {
+        const int64_t np = std::max<int64_t>(ctx.parts[p].n, 1);
+        xn_tc[p].alloc(np, h.stream);
+        best_tc[p].alloc(np, h.stream);
+        lab_tc[p].alloc(np, h.stream);
+        row_norms<float>(h, ctx.parts[p].X, ctx.parts[p].n, d, xn_tc[p].get());
+      }
+    }
+  }
   auto update_min = [&](int first, int count, bool fresh) {
+    if constexpr (std::is_same<T, float>::value) {
+      if (seed_tc && tc_best_supported(h, d, count)) {
+        const float* cnew = cand.get() + static_cast<size_t>(first) * d;
+        tc_prepare(h, cnew, count, d, cen_tc);
+        bool cn_ready = false;
+        for (size_t p = 0; p < ctx.parts.size(); ++p) {
+          auto& pt = ctx.parts[p];
+          if (pt.n == 0) continue;
+          tc_assign(h, pt.X, pt.n, d, count, cen_tc, lab_tc[p].get(), nullptr, nullptr, best_tc[p].get());
+          // the row-packed kernel leaves the winning value of an odd last row to the caller
+          const bool tail   = cen_tc.pack == 2 && (pt.n & 1);
+          const int64_t nte = pt.n - (tail ? 1 : 0);
+          if (nte > 0) {
+            min_from_best_kernel<<<static_cast<unsigned>(ceil_div(nte, 256)), 256, 0, h.stream>>>(
+              xn_tc[p].get(), best_tc[p].get(), mind[p].get(), nte, fresh ? 1 : 0);
+            CB2_CHECK_LAUNCH();
+          }
+          if (tail) {
+            if (!cn_ready) row_norms<T>(h, cnew, count, d, cn.get());
+            cn_ready = true;
+            if (fresh) simt_assign<T>(h, pt.X + nte * d, 1, d, cnew, count, cn.get(), nullptr, mind[p].get() + nte);
+            else simt_min_update<T>(h, pt.X + nte * d, 1, d, cnew, count, cn.get(), mind[p].get() + nte);
+          }
+        }
+        return;
+      }
+    }
     row_norms<T>(h, cand.get() + static_cast<size_t>(first) * d, count, d, cn.get());
     for (size_t p = 0; p < ctx.parts.size(); ++p) {
       auto& pt = ctx.parts[p];

@@ -50,6 +50,11 @@ run c4_probe_pairst timeout 600 env CUML_B200_DIST_PAIRST=1 python tools/c4_prob
 g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include examples/kmeans_bench.cpp -Lcuml_b200/lib -lcuml_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/cuml_b200/lib -o /tmp/kmeans_bench
 run cpp_bench timeout 900 /tmp/kmeans_bench
 
+# 4d. k-means|| seeding with the min-distance updates on the tensor-core kernel: parity, then the C5 init time both ways
+run parity_seed_tc timeout 900 env CUML_B200_SEED_TC=1 python -m pytest tests/test_kmeans_gpu.py tests/test_z_callers.py -m gpu -q -k "seeded or sampling"
+run bench_c5_seed_tc timeout 900 env CUML_B200_SEED_TC=1 python bench.py --workload C5 --steps 5 --no-e2e --no-cpu
+# (bench_c5_default above carries the CUDA-core init time in its "init" object)
+
 # 5. the inference config (new bench workload)
 run bench_c4 timeout 900 python bench.py --workload C4 --steps 3 --no-cpu
 grep -h '^{' "$OUT"/bench_*.log > "$OUT/bench_lines.jsonl" 2>/dev/null
