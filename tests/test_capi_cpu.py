@@ -173,6 +173,26 @@ def test_chunked_host_predict_logic(monkeypatch):
 
 
 
+def test_cpp_surface_has_the_reference_signatures(tmp_path):
+    # all 14 ML::kmeans overloads with the reference's exact parameter types + KMeansParams fields / defaults
+    # (tests/cpp/surface_signatures.cpp does not compile otherwise); runs without a GPU: nothing is called
+    import shutil
+    import subprocess
+    from cuml_b200 import build
+    gxx = shutil.which("g++")
+    if gxx is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime.h"):
+        pytest.skip("no g++ / CUDA headers")
+    libdir = os.path.dirname(build.lib_path())
+    exe = str(tmp_path / "surface_signatures")
+    cmd = [gxx, "-std=c++17", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+           os.path.join(ROOT, "tests", "cpp", "surface_signatures.cpp"), "-L" + libdir, "-lcuml_b200",
+           "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir, "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "surface ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("src", ["kmeans_example.cpp", "kmeans_bench.cpp"])
 def test_cpp_surface_compiles_and_links(tmp_path, src):
     # the C++ ML::kmeans::* mirror (include/cuml/cluster/kmeans.hpp) against the built library: every forwarder the

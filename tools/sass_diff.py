@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Compare the SASS of two builds of libcuml_b200.so kernel by kernel.
+
+    python tools/sass_diff.py OLD.so NEW.so
+
+Used to check that a change which only adds opt-in instantiations leaves the kernels that were measured on
+hardware untouched.  For every kernel (demangled name) of OLD it reports: identical / same multiset of
+instructions (order differs) / different (instruction-count delta), and lists kernels only present on one side.
+Addresses, the control-code words and register-allocation-neutral whitespace are stripped before comparing.
+"""
+import collections
+import re
+import subprocess
+import sys
+
+
+def kernels(path):
+    sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True, check=True).stdout
+    out, name = collections.OrderedDict(), None
+    for line in sass.splitlines():
+        m = re.match(r"\s*Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            out[name] = []
+            continue
+        m = re.match(r"\s*/\*[0-9a-f]{4,}\*/\s+(.*?);\s*/\*", line)
+        if m and name is not None:
+            out[name].append(re.sub(r"\s+", " ", m.group(1)))
+    names = list(out)
+    dem = subprocess.run(["c++filt"], input="\n".join(names), capture_output=True, text=True).stdout.splitlines()
+    return {d: out[n] for n, d in zip(names, dem)}
+
+
+def main():
+    old, new = kernels(sys.argv[1]), kernels(sys.argv[2])
+    same = reordered = changed = 0
+    for name, ins in old.items():
+        short = name if len(name) < 150 else name[:147] + "..."
+        if name not in new:
+            print("ONLY OLD  ", short)
+            continue
+        other = new[name]
+        if ins == other:
+            same += 1
+        elif collections.Counter(ins) == collections.Counter(other):
+            reordered += 1
+            print("REORDERED ", len(ins), short)
+        else:
+            changed += 1
+            print("CHANGED   ", len(ins), "->", len(other), short)
+    for name in new:
+        if name not in old:
+            print("ONLY NEW  ", len(new[name]), name if len(name) < 150 else name[:147] + "...")
+    print(f"identical {same}, reordered {reordered}, changed {changed}, old {len(old)}, new {len(new)}")
+
+
+if __name__ == "__main__":
+    main()
