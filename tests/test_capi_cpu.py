@@ -173,6 +173,30 @@ def test_chunked_host_predict_logic(monkeypatch):
 
 
 
+@pytest.mark.parametrize("which,own", [("estep", "fused_l2_argmin_sm100"), ("mstep", "centroid_update_tma")])
+def test_kernel_planners_hold_their_invariants_on_a_shape_grid(tmp_path, which, own):
+    # tests/cpp/plan_check_*.cu include the kernel source (the planners are file-local) and walk ~8k (d, k) shapes on
+    # the host: shared-memory budget, ring depths, thread counts.  Links against the library's other objects.
+    import glob
+    import shutil
+    import subprocess
+    from cuml_b200 import build
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc")
+    build.build()
+    objs = [o for o in glob.glob(os.path.join(build.OBJDIR, "*.o")) if os.path.basename(o) != own + ".o"]
+    assert objs, "library objects missing"
+    exe = str(tmp_path / ("plan_check_" + which))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O1", "-std=c++17", "--expt-relaxed-constexpr",
+           "-I" + os.path.join(ROOT, "include"), "-I" + build.CSRC, "-o", exe,
+           os.path.join(ROOT, "tests", "cpp", "plan_check_%s.cu" % which), *objs, "-lcuda", "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "bad 0" in r.stdout, r.stdout[-2000:]
+
+
 def test_cpp_surface_has_the_reference_signatures(tmp_path):
     # all 14 ML::kmeans overloads with the reference's exact parameter types + KMeansParams fields / defaults
     # (tests/cpp/surface_signatures.cpp does not compile otherwise); runs without a GPU: nothing is called
