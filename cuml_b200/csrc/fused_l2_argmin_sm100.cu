@@ -1887,6 +1887,14 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                       static_cast<int>(h.smem_optin)));
         pk_attr = true;
       }
+      // role-level cycle counters of CTA 0 (measurement aid, CUML_B200_DBG_CLK=1), as in the unpacked path below
+      DevBuf<long long> clk;
+      const bool want_clk = std::getenv("CUML_B200_DBG_CLK") != nullptr;
+      if (want_clk) {
+        clk.alloc(16, h.stream);
+        CB2_CUDA(cudaMemsetAsync(clk.get(), 0, 16 * sizeof(long long), h.stream));
+        p.dbg_clk = clk.get();
+      }
       EventPair ev{};
       if (h.timing) ev = h.begin_event();
       const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
@@ -1894,6 +1902,14 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
       CB2_CHECK_LAUNCH();
       if (h.timing) h.end_event(ev, true);
+      if (want_clk) {
+        long long hc[16];
+        CB2_CUDA(cudaMemcpyAsync(hc, clk.get(), sizeof(hc), cudaMemcpyDeviceToHost, h.stream));
+        CB2_CUDA(cudaStreamSynchronize(h.stream));
+        std::printf("[cuml_b200 clk packed] tiles/CTA %lld | producer wait %lld / %lld | converter wait %lld / %lld | mma wait acc %lld a %lld "
+                    "b %lld / %lld (cycles, CTA 0)\n",
+                    static_cast<long long>((p.m_tiles + grid - 1) / grid), hc[0], hc[1], hc[2], hc[3], hc[4], hc[5], hc[6], hc[7]);
+      }
     }
     if (n & 1) {   // (labels only: a caller that wants the winning value of an odd last row computes it itself)
       assign_tail_row_kernel<<<1, 32, 0, h.stream>>>(X + (n - 1) * d, d, k, cen.hi.get(), cen.lo.get(), labels + (n - 1));

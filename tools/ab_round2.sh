@@ -18,6 +18,15 @@ run mma_rate_pair timeout 120 ./tools/micro/mma_rate_pair
 # 2b. where the C3 E-step waits: role-level cycle counters of the pair kernel (CLK instantiation, CTA 0)
 run clk_c3 timeout 600 env CUML_B200_DBG_CLK=1 python bench.py --workload C3 --steps 2 --warmup 3 --no-e2e --no-cpu
 
+# 2c. the weakest roofline fractions of round 1 are the small-d configs (C5 fused kernel 0.30 of HBM, C1 0.33): where does
+# the single-CTA kernel wait?  Role-level cycle counters (row-packed path included) + one full ncu capture of the
+# fused kernel and the lane = row M-step kernel at C5
+run clk_c5 timeout 600 env CUML_B200_DBG_CLK=1 python bench.py --workload C5 --steps 2 --warmup 3 --no-e2e --no-cpu
+run clk_c5_nopack timeout 600 env CUML_B200_DBG_CLK=1 CUML_B200_PACK=0 python bench.py --workload C5 --steps 2 --warmup 3 --no-e2e --no-cpu
+run clk_c1 timeout 300 env CUML_B200_DBG_CLK=1 python bench.py --workload C1 --steps 2 --warmup 3 --no-e2e --no-cpu
+run ncu_full_c5 timeout 900 ncu --set full --import-source on --clock-control none -k regex:"fused_l2_argmin|accumulate_tma" -c 2 -o "$OUT/full_c5" python bench.py --workload C5 --steps 1 --warmup 0 --no-cpu --no-e2e
+run ncu_full_c5_txt timeout 300 python tools/ncu_raw.py "$OUT/full_c5.ncu-rep"
+
 # 3. E-step variants at C3 (fused kernel time is in roofline.kernel_ms)
 run bench_c3_default timeout 600 python bench.py --workload C3 --steps 10 --no-e2e --no-cpu
 run bench_c3_conv_trunc timeout 600 env CUML_B200_CONV_TRUNC=1 python bench.py --workload C3 --steps 10 --no-e2e --no-cpu
