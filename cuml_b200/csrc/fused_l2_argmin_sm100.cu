@@ -1560,6 +1560,40 @@ __global__ void prepare_centroids_packed_kernel(const float* __restrict__ C, int
   if (lane == 0) cnh[jj] = (j < k) ? static_cast<float>(0.5 * s) : __int_as_float(0x7f800000);
 }
 
+// The same block-diagonal operands for the opt-in single-CTA tf32 + bf16 kernel (CUML_B200_SOLO_V2=1): hi rounded to
+// the nearest tf32, bf16 copies of hi / lo for the two correction terms and the tf32-exact pieces of -1/2||c||^2 the
+// fold MMA adds to every accumulator column (row jj of the pieces tile = accumulator column jj).  A separate kernel,
+// so the default row-packed path keeps its measured binary.
+__global__ void prepare_centroids_packed_v2_kernel(const float* __restrict__ C, int k, int d, int k_sub,
+                                                   float* __restrict__ hi, float* __restrict__ lo,
+                                                   float* __restrict__ cnh, __nv_bfloat16* __restrict__ hb,
+                                                   __nv_bfloat16* __restrict__ lb, float* __restrict__ cnp)
+{
+  const int jj   = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;   // row of B' in [0, 2*k_sub)
+  const int lane = threadIdx.x % 32;
+  if (jj >= 2 * k_sub) return;
+  const int g = jj / k_sub, j = jj % k_sub;
+  const int c = lane - g * d;
+  const float v = (j < k && c >= 0 && c < d) ? C[static_cast<int64_t>(j) * d + c] : 0.0f;
+  const float h = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+  hi[static_cast<int64_t>(jj) * KBLOCK + lane] = h;
+  lo[static_cast<int64_t>(jj) * KBLOCK + lane] = v - h;
+  hb[static_cast<int64_t>(jj) * KBLOCK + lane] = __float2bfloat16_rn(h);
+  lb[static_cast<int64_t>(jj) * KBLOCK + lane] = __float2bfloat16_rn(v - h);
+  double s = static_cast<double>(v) * static_cast<double>(v);
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) cnh[jj] = (j < k) ? static_cast<float>(0.5 * s) : __int_as_float(0x7f800000);
+  if (cnp && lane < 8) {
+    const float m  = (j < k) ? -static_cast<float>(0.5 * s) : -3.0e38f;
+    const float p1 = __uint_as_float(__float_as_uint(m) & 0xffffe000u);
+    const float r1 = m - p1;
+    const float p2 = __uint_as_float(__float_as_uint(r1) & 0xffffe000u);
+    const float p3 = r1 - p2;
+    cnp[static_cast<int64_t>(jj) * 8 + lane] = lane == 0 ? p1 : lane == 1 ? p2 : lane == 2 ? p3 : 0.0f;
+  }
+}
+
 // packing applies to short rows with few clusters (both halves of the block-diagonal operand fit N <= 256)
 int pack_k_sub(int d, int k)
 {
@@ -1751,7 +1785,7 @@ bool tc_supported(int64_t d, int k)
 
 int tc_variant(const Handle& h, int d, int k)
 {
-  if (pack_k_sub(d, k)) return 1;
+  if (pack_k_sub(d, k)) return (use_solo_v2() && use_bf16_corrections()) ? 5 : 1;
   if (use_ts(h, d, k)) return 4;
   if (use_2cta(h, d, k)) return use_bf16_corrections() ? 3 : 2;
   if (use_solo_v2() && use_bf16_corrections()) return 5;
@@ -1772,6 +1806,25 @@ void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out, bool 
     out.block_n = k_pad;
     out.pack    = 2;
     out.k_sub   = k_sub;
+    out.bf16c   = 0;
+    out.fold    = 0;
+    if (use_solo_v2() && allow_bf16 && use_bf16_corrections()) {
+      // opt-in single-CTA tf32 + bf16 kernel on the row-packed operands (see prepare_centroids_packed_v2_kernel)
+      const TilePlan t = plan_tiles(2 * d, k_pad, h.smem_optin);
+      CB2_EXPECTS(t.bn == k_pad && t.kb == 1, "row-packed plan mismatch");
+      out.bf16c = 1;
+      out.fold  = solo_fold_fits(t, k_pad, h.smem_optin) ? 1 : 0;
+      if (out.hb.n < static_cast<size_t>(k_pad) * KBLOCK) {
+        out.hb.alloc(static_cast<size_t>(k_pad) * KBLOCK, h.stream);
+        out.lb.alloc(static_cast<size_t>(k_pad) * KBLOCK, h.stream);
+      }
+      if (out.fold && out.cnp.n < static_cast<size_t>(k_pad) * 8) out.cnp.alloc(static_cast<size_t>(k_pad) * 8, h.stream);
+      prepare_centroids_packed_v2_kernel<<<static_cast<unsigned>(ceil_div(k_pad, 8)), 256, 0, h.stream>>>(
+        C, k, d, k_sub, out.hi.get(), out.lo.get(), out.cnh.get(), reinterpret_cast<__nv_bfloat16*>(out.hb.get()),
+        reinterpret_cast<__nv_bfloat16*>(out.lb.get()), out.fold ? out.cnp.get() : nullptr);
+      CB2_CHECK_LAUNCH();
+      return;
+    }
     prepare_centroids_packed_kernel<<<static_cast<unsigned>(ceil_div(k_pad, 8)), 256, 0, h.stream>>>(
       C, k, d, k_sub, out.hi.get(), out.lo.get(), out.cnh.get());
     CB2_CHECK_LAUNCH();
@@ -1898,7 +1951,31 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       EventPair ev{};
       if (h.timing) ev = h.begin_event();
       const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
-      if (best_out) fused_l2_argmin_kernel<3><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+      if (cen.bf16c && !best_out) {
+        // opt-in single-CTA tf32 + bf16 kernel (CUML_B200_SOLO_V2=1) on the row-packed operands.  (It has no best-value
+        // epilogue; the 3xTF32 kernel below reads the same buffers: hi rounded to nearest is still tf32-exact and
+        // lo = c - hi is exact.)
+        p.fold = (cen.fold && solo_fold_fits(t, cen.k_pad, h.smem_optin)) ? 1 : 0;
+        p.l2_ahead = 3;
+        const size_t smem = t.smem + (p.fold ? static_cast<size_t>(1 + p.k_tiles) * TILE_M * 32 : 0);
+        CUtensorMap tm_hb = make_map_2d(cen.hb.get(), KBLOCK, cen.k_pad, static_cast<uint64_t>(KBLOCK) * 2, KBLOCK, t.bn,
+                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        CUtensorMap tm_lb = make_map_2d(cen.lb.get(), KBLOCK, cen.k_pad, static_cast<uint64_t>(KBLOCK) * 2, KBLOCK, t.bn,
+                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        CUtensorMap tm_cn = tm_hi;
+        if (p.fold)
+          tm_cn = make_map_2d(cen.cnp.get(), 8, cen.k_pad, 8 * sizeof(float), 8, t.bn, CU_TENSOR_MAP_SWIZZLE_32B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        static bool pk_solo_attr = false;
+        if (!pk_solo_attr) {
+          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, 0, false>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
+          pk_solo_attr = true;
+        }
+        fused_l2_argmin_solo_kernel<true, 0, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+      } else if (best_out) fused_l2_argmin_kernel<3><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
       else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
       CB2_CHECK_LAUNCH();
       if (h.timing) h.end_event(ev, true);

@@ -46,7 +46,9 @@ run parity_solo_v2 timeout 600 env CUML_B200_SOLO_V2=1 python -m pytest tests/te
 run bench_c1_default timeout 300 python bench.py --workload C1 --steps 50 --no-e2e --no-cpu
 run bench_c1_solo_v2 timeout 300 env CUML_B200_SOLO_V2=1 python bench.py --workload C1 --steps 50 --no-e2e --no-cpu
 run bench_c5_default timeout 600 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
-# C5 is row-packed by default (old kernel); the solo kernel takes it only with packing off (half-empty K-block, nks = 2)
+# C5 is row-packed (two rows per 128-byte operand row, block-diagonal centroids): the solo kernel takes the packed operands
+# too (9 MMAs per 256 rows instead of 12), and the unpacked shape for comparison (half-empty K-block, nks = 2)
+run bench_c5_solo_v2 timeout 600 env CUML_B200_SOLO_V2=1 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
 run bench_c5_solo_v2_nopack timeout 600 env CUML_B200_SOLO_V2=1 CUML_B200_PACK=0 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
 run bench_c5_nopack timeout 600 env CUML_B200_PACK=0 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
 
