@@ -62,6 +62,16 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v)
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
 }
+__device__ __forceinline__ float lds32f(uint32_t addr)
+{
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t addr, float v)
+{
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
 __device__ __forceinline__ int lds32(uint32_t addr)
 {
   int v;
@@ -691,6 +701,160 @@ reduce_partials_f32_kernel(const float* __restrict__ partial_S, const float* __r
   }
 }
 
+// ---- opt-in M-step for short rows (n_features 4 / 8 / 16, e.g. C5): lane = column, warp-private tables -------------
+// CUML_B200_UPD_LANECOL=1; written after round 1's GPU budget was spent -- parity and speed not yet measured.
+// The lane = row kernel above is bound by shared-memory wavefronts (32 random table rows per instruction).  Here one
+// warp instruction covers R = 32 / D consecutive rows with lane = (sub-row r, column c), lane == r * D + c, so a batch
+// of 32 * U consecutive floats of X is loaded with U perfectly coalesced 128-byte loads and needs no staging at all.
+// Every warp owns a private table of k x 32 floats: row j holds R sub-tables side by side (sub-row r adds into columns
+// [r * D, r * D + D)), i.e. lane l only ever touches bank l -- no bank conflicts, and rows of one instruction that
+// share a label never touch the same cell, so there is nothing to match, rank or sort.  Per R rows: 1 shuffle (label),
+// 1 address, LDS + FADD + STS.  Memory parallelism: two batches of U loads per lane in flight (register double buffer)
+// in each of up to 16 warps.  Cluster weights: integer shared-memory counts per warp (exact) or, weighted, one more
+// private [R][k] table updated by the c == 0 lanes.  The CTA folds its warps' tables in a fixed order into the same
+// partials format as the other kernels (deterministic).
+struct LaneColParams {
+  int64_t n;
+  int64_t rows_per_block;   // multiple of the batch (U * R rows)
+  int k, warps;
+  const float* X;
+  const int32_t* labels;
+  const float* w;
+  float* partial_S;
+  float* partial_W;
+};
+
+constexpr int LC_U = 32;   // loads per lane and batch (batch = 32 * LC_U floats = 4 KB of X)
+
+template <int D, bool HAS_W>
+__global__ void __launch_bounds__(512, 1)
+accumulate_lanecol_kernel(const LaneColParams p)
+{
+  constexpr int R  = 32 / D;          // rows per warp instruction
+  constexpr int BR = LC_U * R;        // rows per batch
+  constexpr int NQ = BR / 32;         // label (weight) registers per lane and batch (== R)
+  extern __shared__ float lc_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r    = lane / D;
+  const size_t per_warp = static_cast<size_t>(p.k) * 32 + static_cast<size_t>(R) * p.k;   // floats
+  float* tbl = lc_smem + per_warp * warp;          // [k][32]
+  float* aux = tbl + static_cast<size_t>(p.k) * 32;   // HAS_W: [R][k] weights; else [k] int counts (rest unused)
+  for (size_t i = threadIdx.x; i < per_warp * p.warps; i += blockDim.x) lc_smem[i] = 0.0f;
+  __syncthreads();
+
+  const int64_t row_begin = static_cast<int64_t>(blockIdx.x) * p.rows_per_block;
+  const int64_t row_end   = min(p.n, row_begin + p.rows_per_block);
+  const int64_t n_batches = row_end > row_begin ? (row_end - row_begin + BR - 1) / BR : 0;
+
+  float xa[LC_U], xb[LC_U];
+  int la[NQ], lb[NQ];
+  float wa[NQ], wb[NQ];
+
+  // batch b of this CTA: rows [row_begin + b * BR, +BR) clipped to row_end; rows past the end read as label -1, x = w = 0
+  auto load = [&](float (&x)[LC_U], int (&lab)[NQ], float (&wv)[NQ], int64_t b) {
+    const int64_t row0 = row_begin + b * BR;
+    const float* src   = p.X + row0 * D;
+    if (row0 + BR <= row_end) {
+#pragma unroll
+      for (int u = 0; u < LC_U; ++u) x[u] = __ldcs(src + u * 32 + lane);
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        lab[q] = __ldcs(p.labels + row0 + q * 32 + lane);
+        if (HAS_W) wv[q] = __ldg(p.w + row0 + q * 32 + lane);
+      }
+    } else {
+      const int64_t left = (row_end - row0) * D;   // floats of this batch that exist (<= 0: none)
+#pragma unroll
+      for (int u = 0; u < LC_U; ++u) x[u] = (u * 32 + lane < left) ? __ldcs(src + u * 32 + lane) : 0.0f;
+#pragma unroll
+      for (int q = 0; q < NQ; ++q) {
+        const bool ok = row0 + q * 32 + lane < row_end;
+        lab[q] = ok ? __ldcs(p.labels + row0 + q * 32 + lane) : -1;
+        if (HAS_W) wv[q] = ok ? __ldg(p.w + row0 + q * 32 + lane) : 0.0f;
+      }
+    }
+  };
+  const uint32_t cell0 = ptx::smem_u32(tbl) + static_cast<uint32_t>(lane) * 4u;   // this lane's column of table row 0
+  auto apply = [&](const float (&x)[LC_U], const int (&lab)[NQ], const float (&wv)[NQ]) {
+    int byte_off[NQ];   // label -> byte offset of its table row (rows past the end: row 0, they add zeros)
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      if (!HAS_W && lab[q] >= 0) atomicAdd(reinterpret_cast<int*>(aux) + lab[q], 1);   // warp-private exact counts
+      byte_off[q] = max(lab[q], 0) * 128;
+    }
+#pragma unroll
+    for (int u = 0; u < LC_U; ++u) {
+      // step u covers batch rows u * R + r; their labels sit in register (u * R) / 32 of lane (u * R + r) % 32
+      const int q         = (u * R) >> 5;
+      const int src       = ((u * R) & 31) + r;
+      const uint32_t cell = cell0 + static_cast<uint32_t>(__shfl_sync(0xffffffffu, byte_off[q], src));
+      if (HAS_W) {
+        const float wr = __shfl_sync(0xffffffffu, wv[q], src);
+        sts32f(cell, fmaf(wr, x[u], lds32f(cell)));
+        if (lane % D == 0) {
+          float* wc = aux + r * p.k + (static_cast<uint32_t>(cell - cell0) >> 7);
+          *wc += wr;
+        }
+      } else {
+        sts32f(cell, lds32f(cell) + x[u]);
+      }
+    }
+  };
+
+  // warp w takes batches w, w + warps, ... of its CTA.  Every warp runs the same number of rounds (a batch past the
+  // end loads nothing and adds zeros), so the loop is CTA-uniform and the shuffles need no re-convergence; the next
+  // batch's loads are in flight while the current one is applied.
+  const int64_t rounds = (n_batches + p.warps - 1) / p.warps;
+  if (rounds > 0) load(xa, la, wa, warp);
+  for (int64_t it = 0; it < rounds; it += 2) {
+    if (it + 1 < rounds) load(xb, lb, wb, (it + 1) * p.warps + warp);
+    apply(xa, la, wa);
+    if (it + 1 < rounds) {
+      if (it + 2 < rounds) load(xa, la, wa, (it + 2) * p.warps + warp);
+      apply(xb, lb, wb);
+    }
+  }
+  __syncthreads();
+
+  // fold the warps' tables (fixed order: warp, then sub-row) into this CTA's partials
+  float* outS = p.partial_S + static_cast<size_t>(blockIdx.x) * p.k * D;
+  for (int e = threadIdx.x; e < p.k * D; e += blockDim.x) {
+    const int j = e / D, c = e % D;
+    float sum = 0.0f;
+    for (int w = 0; w < p.warps; ++w) {
+      const float* t = lc_smem + per_warp * w + j * 32 + c;
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) sum += t[rr * D];
+    }
+    outS[e] = sum;
+  }
+  float* outW = p.partial_W + static_cast<size_t>(blockIdx.x) * p.k;
+  for (int j = threadIdx.x; j < p.k; j += blockDim.x) {
+    float sum = 0.0f;
+    int cnt   = 0;
+    for (int w = 0; w < p.warps; ++w) {
+      const float* a = lc_smem + per_warp * w + static_cast<size_t>(p.k) * 32;
+      if (HAS_W) {
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) sum += a[rr * p.k + j];
+      } else {
+        cnt += reinterpret_cast<const int*>(a)[j];
+      }
+    }
+    outW[j] = HAS_W ? sum : static_cast<float>(cnt);
+  }
+}
+
+// warps whose private tables fit shared memory (0: the kernel does not apply)
+static int lanecol_warps(const Handle& h, int d, int k)
+{
+  static const bool on = std::getenv("CUML_B200_UPD_LANECOL") && std::atoi(std::getenv("CUML_B200_UPD_LANECOL")) != 0;
+  if (!on || (d != 4 && d != 8 && d != 16)) return 0;
+  const size_t per_warp = (static_cast<size_t>(k) * 32 + static_cast<size_t>(32 / d) * k) * sizeof(float);
+  const int warps       = static_cast<int>(std::min<size_t>(16, (h.smem_optin - 1024) / per_warp));
+  return warps >= 4 ? warps : 0;
+}
+
 }  // namespace
 
 struct TmaUpdatePlan {
@@ -856,6 +1020,39 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
   const int64_t total = static_cast<int64_t>(k) * d + k;
   if (n == 0) {
     if (!accumulate_into) CB2_CUDA(cudaMemsetAsync(packed, 0, total * sizeof(double), h.stream));
+    return;
+  }
+  if (const int lc_warps = lanecol_warps(h, d, k); lc_warps > 0) {
+    // opt-in lane = column kernel for short rows (see accumulate_lanecol_kernel)
+    const int rows_batch = LC_U * (32 / d);
+    const int64_t batches = ceil_div(n, rows_batch);
+    int64_t rb = std::min<int64_t>(h.sm_count, ceil_div(batches, lc_warps));
+    rb         = std::min<int64_t>(rb, std::max<int64_t>(1, n / (16 * static_cast<int64_t>(k)) + 1));
+    LaneColParams q{};
+    q.n = n; q.k = k; q.warps = lc_warps;
+    q.rows_per_block = ceil_div(batches, rb) * rows_batch;
+    rb               = ceil_div(n, q.rows_per_block);
+    if (partial_S.n < static_cast<size_t>(rb) * k * d) partial_S.alloc(static_cast<size_t>(rb) * k * d, h.stream);
+    if (partial_W.n < static_cast<size_t>(rb) * k) partial_W.alloc(static_cast<size_t>(rb) * k, h.stream);
+    q.X = X; q.labels = labels_padded; q.w = w; q.partial_S = partial_S.get(); q.partial_W = partial_W.get();
+    const size_t smem = (static_cast<size_t>(k) * 32 + static_cast<size_t>(32 / d) * k) * sizeof(float) * lc_warps;
+    if (std::getenv("CUML_B200_UPD_PLAN"))
+      std::printf("[cuml_b200 update plan lanecol] d %d warps %d row blocks %lld rows/block %lld smem %zu\n", d, lc_warps,
+                  static_cast<long long>(rb), static_cast<long long>(q.rows_per_block), smem);
+    auto launch = [&](auto kern) {
+      CB2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
+      kern<<<static_cast<unsigned>(rb), lc_warps * 32, smem, h.stream>>>(q);
+    };
+    const bool hw = w != nullptr;
+    switch (d) {
+      case 4: hw ? launch(accumulate_lanecol_kernel<4, true>) : launch(accumulate_lanecol_kernel<4, false>); break;
+      case 8: hw ? launch(accumulate_lanecol_kernel<8, true>) : launch(accumulate_lanecol_kernel<8, false>); break;
+      default: hw ? launch(accumulate_lanecol_kernel<16, true>) : launch(accumulate_lanecol_kernel<16, false>); break;
+    }
+    CB2_CHECK_LAUNCH();
+    reduce_partials_f32_kernel<<<static_cast<unsigned>(ceil_div(total, 32)), 256, 0, h.stream>>>(
+      partial_S.get(), partial_W.get(), static_cast<int>(rb), k, d, packed, accumulate_into ? 1 : 0);
+    CB2_CHECK_LAUNCH();
     return;
   }
   if (const OwnerPlan op = plan_owner_update(h, d, k); op.vec > 0) {

@@ -52,6 +52,11 @@ run bench_c5_solo_v2 timeout 600 env CUML_B200_SOLO_V2=1 python bench.py --workl
 run bench_c5_solo_v2_nopack timeout 600 env CUML_B200_SOLO_V2=1 CUML_B200_PACK=0 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
 run bench_c5_nopack timeout 600 env CUML_B200_PACK=0 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
 
+# 4a. M-step for short rows: lane = column kernel with warp-private tables (plain CUDA, no TMA ring) vs the lane = row kernel
+run parity_upd_lanecol timeout 600 env CUML_B200_UPD_LANECOL=1 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "single_lloyd_step or weighted_step or skewed or regime2"
+run bench_c5_upd_lanecol timeout 600 env CUML_B200_UPD_LANECOL=1 CUML_B200_UPD_PLAN=1 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
+run bench_c5_lanecol_solo_v2 timeout 600 env CUML_B200_UPD_LANECOL=1 CUML_B200_SOLO_V2=1 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
+
 # 4b. transform: lane-pair store pattern (DIST = 2 instantiations) -- parity, then the C4-shape probe both ways
 run parity_dist_pairst timeout 600 env CUML_B200_DIST_PAIRST=1 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "transform"
 run c4_probe_default timeout 600 python tools/c4_probe.py
