@@ -357,6 +357,89 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
   }
 }
 
+// ===================== row-owner epilogue (opt-in, CUML_B200_EPI_ROWOWN=1; single centroid tile, BN <= 128) ===========
+// Written after round 1's GPU budget was spent -- not yet validated on hardware.  With few clusters the epilogue above
+// gives each of its 16 warps ONE 32-column chunk per tile and then pays two 512-thread named barriers and a shared-
+// memory merge per tile: a per-tile latency chain (accumulator wait -> tcgen05.ld -> compare -> barrier -> merge ->
+// store -> barrier) that all 16 warps walk together, one tile at a time.  Here the 16 warps form 4 groups of 4 (one
+// warp per TMEM lane quarter); group g owns the row tiles t = g, g + 4, ... of its CTA, each thread scans ALL columns
+// of its row (both packed groups when two data rows share an operand row) and stores the label itself: no merge, no
+// named barriers, and four tiles' epilogues in flight on different accumulator stages (BN <= 128 leaves >= 4 stages).
+// Only 4 warps arrive on an accumulator's empty barrier (the kernel initialises it with 4 in this mode).
+template <bool FOLD1>
+__device__ __forceinline__ void epilogue_role_rowown(const FusedParams& p, Barriers* bars, float* cn_s,
+                                                     uint32_t tmem_base, int64_t first_row, int64_t row_stride,
+                                                     int64_t n_tiles_cta)
+{
+  const int et      = threadIdx.x - 256;      // 0..511
+  const int ew      = et >> 5;                // epilogue warp 0..15
+  const int lane    = et & 31;
+  const int quarter = ew & 3;                 // TMEM lane quarter this warp may access
+  const int group   = ew >> 2;                // row tiles t = group, group + 4, ...
+  const int rit     = quarter * 32 + lane;    // row within the 128-row tile
+  const float inf   = __int_as_float(0x7f800000);
+  const bool fold   = FOLD1 && p.fold;        // accumulator already holds x.c - 1/2||c||^2
+  const int gcols   = p.pack > 1 ? p.k_sub : p.bn;   // accumulator columns per data row
+  if (!fold) {   // stage the half norms once (single centroid tile)
+    if (et < p.bn) cn_s[et] = __ldg(p.cnh + et);
+    ptx::named_bar_sync(1, EPI_THREADS);
+  }
+  Ring racc;                  // accumulator stage of tile t: t % n_acc, phase (t / n_acc) & 1 (n_acc >= 4 here)
+  racc.slot = static_cast<uint32_t>(group);
+  for (int64_t t = group; t < n_tiles_cta; t += 4, racc.advance_by(4, p.n_acc)) {
+    const uint32_t acc = racc.slot, pacc = racc.phase;
+    ptx::mbar_wait_park(ptx::smem_u32(&bars->acc_full[acc]), pacc);
+    ptx::tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.bn;
+    for (int g = 0; g < p.pack; ++g) {
+      float b0 = inf, b1 = inf, b2 = inf, b3 = inf;
+      int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
+      uint32_t r[32];
+      for (int c0 = 0; c0 < gcols; c0 += 32) {
+        const int col = g * gcols + c0;
+        ptx::tmem_ld_32x32(taddr + col, r);
+        ptx::tmem_ld_wait();
+        if (fold) {
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float v0 = -__uint_as_float(r[q4 * 4 + 0]);
+            const float v1 = -__uint_as_float(r[q4 * 4 + 1]);
+            const float v2 = -__uint_as_float(r[q4 * 4 + 2]);
+            const float v3 = -__uint_as_float(r[q4 * 4 + 3]);
+            if (v0 < b0) { b0 = v0; i0 = c0 + q4 * 4 + 0; }
+            if (v1 < b1) { b1 = v1; i1 = c0 + q4 * 4 + 1; }
+            if (v2 < b2) { b2 = v2; i2 = c0 + q4 * 4 + 2; }
+            if (v3 < b3) { b3 = v3; i3 = c0 + q4 * 4 + 3; }
+          }
+        } else {
+          const float4* cn4 = reinterpret_cast<const float4*>(cn_s + col);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 c4 = cn4[q4];
+            const float v0 = c4.x - __uint_as_float(r[q4 * 4 + 0]);
+            const float v1 = c4.y - __uint_as_float(r[q4 * 4 + 1]);
+            const float v2 = c4.z - __uint_as_float(r[q4 * 4 + 2]);
+            const float v3 = c4.w - __uint_as_float(r[q4 * 4 + 3]);
+            if (v0 < b0) { b0 = v0; i0 = c0 + q4 * 4 + 0; }
+            if (v1 < b1) { b1 = v1; i1 = c0 + q4 * 4 + 1; }
+            if (v2 < b2) { b2 = v2; i2 = c0 + q4 * 4 + 2; }
+            if (v3 < b3) { b3 = v3; i3 = c0 + q4 * 4 + 3; }
+          }
+        }
+      }
+      // merge the chains: smaller value wins, equal values -> smaller index (first minimum)
+      if (b1 < b0 || (b1 == b0 && i1 < i0)) { b0 = b1; i0 = i1; }
+      if (b3 < b2 || (b3 == b2 && i3 < i2)) { b2 = b3; i2 = i3; }
+      if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
+      const int64_t row = (first_row + t * row_stride + rit) * p.pack + g;
+      if (row < p.n) p.labels[row] = i0;
+    }
+    ptx::tc_fence_before();
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[acc]));
+  }
+}
+
 template <int DIST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
@@ -934,7 +1017,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
 // Single-CTA twin of the CTA-pair kernel (opt-in, CUML_B200_SOLO_V2=1; NOT yet validated on hardware): the same
 // roles, bf16 correction terms and folded half norms for k <= 128, with cta_group::1 instructions and local
 // barriers.  Generated from the pair kernel's source; once measured it is meant to replace fused_l2_argmin_kernel.
-template <bool BF16C, int DIST = 0, bool TRUNC = false>
+template <bool BF16C, int DIST = 0, bool TRUNC = false, bool ROWOWN = false>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                             const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_lb,
@@ -977,7 +1060,7 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     }
     for (int s = 0; s < MAX_ACC; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 16);  // 16 epilogue warps
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), ROWOWN ? 4 : 16);  // epilogue warps per accumulator
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);      // leader's copy: expect_tx covers both CTAs
@@ -1236,7 +1319,10 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   } else if (warp >= 8 && warp < 24) {
     // ===================== epilogue (own 128 rows of the pair tile) =====================
     const int64_t n_mine = (pair_tiles > pair) ? (pair_tiles - pair + n_pairs - 1) / n_pairs : 0;
-    epilogue_role<false, DIST, true>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, pair * TILE_M, n_pairs * TILE_M, n_mine);
+    if constexpr (ROWOWN)
+      epilogue_role_rowown<true>(p, bars, cn_s, tmem_base, pair * TILE_M, n_pairs * TILE_M, n_mine);
+    else
+      epilogue_role<false, DIST, true>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, pair * TILE_M, n_pairs * TILE_M, n_mine);
   }
 
   ptx::tc_fence_before();
@@ -1654,6 +1740,13 @@ bool use_solo_v2()
   return e && std::atoi(e) != 0;
 }
 
+// row-owner epilogue of the single-CTA tf32 + bf16 kernel (see epilogue_role_rowown): opt-in until measured
+bool use_epi_rowown()
+{
+  const char* e = std::getenv("CUML_B200_EPI_ROWOWN");
+  return e && std::atoi(e) != 0;
+}
+
 // CTA-pair plan: BN = 256 split across the pair (128 centroid rows per CTA), deeper X ring.
 // half norms folded into the accumulator by one extra MMA (default on; CUML_B200_FOLD=0 restores the epilogue add)
 bool use_cn_fold()
@@ -1972,9 +2065,14 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
         if (!pk_solo_attr) {
           CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, 0, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
+          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, 0, false, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
           pk_solo_attr = true;
         }
-        fused_l2_argmin_solo_kernel<true, 0, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+        if (use_epi_rowown() && t.bn <= TILE_M)   // one centroid tile, >= 4 accumulator stages
+          fused_l2_argmin_solo_kernel<true, 0, false, true><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+        else
+          fused_l2_argmin_solo_kernel<true, 0, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
       } else if (best_out) fused_l2_argmin_kernel<3><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
       else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
       CB2_CHECK_LAUNCH();
@@ -2182,6 +2280,8 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
       CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<false, 1, false>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
+      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, 0, false, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
       solo_attr = true;
     }
     if (cen.bf16c && !dist) {
@@ -2191,7 +2291,10 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       CUtensorMap tm_lb = make_map_2d(cen.lb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
                                       b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-      fused_l2_argmin_solo_kernel<true, 0, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+      if (use_epi_rowown() && p.k_tiles == 1 && t.bn <= TILE_M && !dbg_dots)
+        fused_l2_argmin_solo_kernel<true, 0, false, true><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+      else
+        fused_l2_argmin_solo_kernel<true, 0, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
     } else if (dist) {
       fused_l2_argmin_solo_kernel<false, 1, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     } else {
