@@ -440,7 +440,7 @@ __device__ __forceinline__ void epilogue_role_rowown(const FusedParams& p, Barri
   }
 }
 
-template <int DIST>
+template <int DIST, bool ROWOWN = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                        const __grid_constant__ CUtensorMap tm_lo, const FusedParams p)
@@ -472,7 +472,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     }
     for (int s = 0; s < MAX_ACC; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 16);   // one arrive per epilogue warp
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), ROWOWN ? 4 : 16);   // one arrive per epilogue warp of the accumulator
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);
@@ -657,8 +657,12 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     // ===================== epilogue: argmin over the accumulator =====================
     const int64_t n_mine = (p.m_tiles > static_cast<int64_t>(blockIdx.x))
                              ? (p.m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    epilogue_role<false, DIST>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, static_cast<int64_t>(blockIdx.x) * TILE_M,
-                         static_cast<int64_t>(gridDim.x) * TILE_M, n_mine);
+    if constexpr (ROWOWN)
+      epilogue_role_rowown<false>(p, bars, cn_s, tmem_base, static_cast<int64_t>(blockIdx.x) * TILE_M,
+                                  static_cast<int64_t>(gridDim.x) * TILE_M, n_mine);
+    else
+      epilogue_role<false, DIST>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, static_cast<int64_t>(blockIdx.x) * TILE_M,
+                                 static_cast<int64_t>(gridDim.x) * TILE_M, n_mine);
   }
 
   ptx::tc_fence_before();
@@ -2074,7 +2078,15 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
         else
           fused_l2_argmin_solo_kernel<true, 0, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
       } else if (best_out) fused_l2_argmin_kernel<3><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
-      else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+      else if (use_epi_rowown() && t.bn <= TILE_M) {   // opt-in row-owner epilogue on the 3xTF32 kernel
+        static bool ro_attr = false;
+        if (!ro_attr) {
+          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(h.smem_optin)));
+          ro_attr = true;
+        }
+        fused_l2_argmin_kernel<0, true><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+      } else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
       CB2_CHECK_LAUNCH();
       if (h.timing) h.end_event(ev, true);
       if (want_clk) {
@@ -2305,7 +2317,15 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     if (best_out) fused_l2_argmin_kernel<3><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
     else if (dist && dist_pair_store) fused_l2_argmin_kernel<2><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
     else if (dist) fused_l2_argmin_kernel<1><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
-    else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+    else if (use_epi_rowown() && p.k_tiles == 1 && t.bn <= TILE_M && !dbg_dots) {   // opt-in row-owner epilogue
+      static bool ro_attr = false;
+      if (!ro_attr) {
+        CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(h.smem_optin)));
+        ro_attr = true;
+      }
+      fused_l2_argmin_kernel<0, true><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+    } else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
   }
   CB2_CHECK_LAUNCH();
   if (h.timing) h.end_event(ev, true);

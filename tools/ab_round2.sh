@@ -49,6 +49,10 @@ run bench_c5_default timeout 600 python bench.py --workload C5 --steps 10 --no-e
 # C5 is row-packed (two rows per 128-byte operand row, block-diagonal centroids): the solo kernel takes the packed operands
 # too (9 MMAs per 256 rows instead of 12), and the unpacked shape for comparison (half-empty K-block, nks = 2)
 run bench_c5_solo_v2 timeout 600 env CUML_B200_SOLO_V2=1 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
+# the row-owner epilogue on the measured 3xTF32 kernel alone (independent of the solo kernel): parity, C5, C1
+run parity_rowown timeout 600 env CUML_B200_EPI_ROWOWN=1 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "single_lloyd_step or regime2 or weighted_step or golden"
+run bench_c5_rowown timeout 600 env CUML_B200_EPI_ROWOWN=1 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
+run bench_c1_rowown timeout 300 env CUML_B200_EPI_ROWOWN=1 python bench.py --workload C1 --steps 50 --no-e2e --no-cpu
 # ... and with the row-owner epilogue (4 warps per accumulator, 4 tiles in flight, no merge / named barriers): parity, C5, C1
 run parity_solo_v2_rowown timeout 600 env CUML_B200_SOLO_V2=1 CUML_B200_EPI_ROWOWN=1 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "single_lloyd_step or dot_accuracy or regime2 or weighted_step"
 run bench_c5_solo_v2_rowown timeout 600 env CUML_B200_SOLO_V2=1 CUML_B200_EPI_ROWOWN=1 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
