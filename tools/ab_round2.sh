@@ -1,18 +1,35 @@
 #!/bin/bash
-# First GPU call of the next round: validates what was written after round 1's GPU budget was spent and A/B-measures
-# the prepared opt-in variants.  Run as:  gpurun --timeout 1500 -- 'bash tools/ab_round2.sh'
+# First GPU calls of the next round: validates what was written after round 1's GPU budget was spent and A/B-measures the
+# prepared opt-in variants.  Phases (one gpurun call each keeps every call well inside its time limit):
+#   gpurun --timeout 1500 -- 'bash tools/ab_round2.sh A'   validation (pytest -m gpu, smoke) + diagnostics (cycle counters, ncu at C5)
+#   gpurun --timeout 1500 -- 'bash tools/ab_round2.sh B'   small-d variants (C5 / C1): solo kernel, row-owner epilogue, lane = column M-step
+#   gpurun --timeout 1500 -- 'bash tools/ab_round2.sh C'   C3 / C2 variants: truncating converter, E-step / M-step overlap
+#   gpurun --timeout 1500 -- 'bash tools/ab_round2.sh D'   transform store pattern, C++ bench shapes, seeding on the tensor cores, C4
+# No argument = all phases.  BUDGET_S (default 1300) stops starting new steps once that much wall-clock has passed.
 # Everything lands in gpurun_out/r2/.  No step depends on another; a failure is logged and the script goes on.
 set -u
+PHASES=${1:-ABCD}
+BUDGET_S=${BUDGET_S:-1300}
+T0=$(date +%s)
 OUT=gpurun_out/r2
 mkdir -p "$OUT"
-run() { name=$1; shift; echo "== $name: $*" | tee -a "$OUT/index.log"; ( "$@" ) > "$OUT/$name.log" 2>&1; echo "rc=$? $name" | tee -a "$OUT/index.log"; }
+PH=A
+phase() { PH=$1; }
+run() {
+  name=$1; shift
+  case "$PHASES" in *"$PH"*) ;; *) return 0 ;; esac
+  if [ $(( $(date +%s) - T0 )) -gt "$BUDGET_S" ]; then echo "skipped (budget) $name" | tee -a "$OUT/index.log"; return 0; fi
+  echo "== [$PH] $name: $*" | tee -a "$OUT/index.log"; ( "$@" ) > "$OUT/$name.log" 2>&1; echo "rc=$? $name" | tee -a "$OUT/index.log"
+}
 
+
+phase A
 # 1. correctness of everything new (fp64, callers, distributed world size 1, C-ABI as before)
 run pytest_gpu timeout 900 python -m pytest tests -m gpu -x -q
 run smoke timeout 300 python __graft_entry__.py smoke
 
 # 2. MMA-issue floor of the pair kernel (cta_group::2): decides whether C3's E-step is at 84 % or 63 % of it
-[ -x tools/micro/mma_rate_pair ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -Icuml_b200/csrc -o tools/micro/mma_rate_pair tools/micro/mma_rate_pair.cu
+case "$PHASES" in *A*) [ -x tools/micro/mma_rate_pair ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -Icuml_b200/csrc -o tools/micro/mma_rate_pair tools/micro/mma_rate_pair.cu ;; esac
 run mma_rate_pair timeout 120 ./tools/micro/mma_rate_pair
 
 # 2b. where the C3 E-step waits: role-level cycle counters of the pair kernel (CLK instantiation, CTA 0)
@@ -27,6 +44,7 @@ run clk_c1 timeout 300 env CUML_B200_DBG_CLK=1 python bench.py --workload C1 --s
 run ncu_full_c5 timeout 900 ncu --set full --import-source on --clock-control none -k regex:"fused_l2_argmin|accumulate_tma" -c 2 -o "$OUT/full_c5" python bench.py --workload C5 --steps 1 --warmup 0 --no-cpu --no-e2e
 run ncu_full_c5_txt timeout 300 python tools/ncu_raw.py "$OUT/full_c5.ncu-rep"
 
+phase C
 # 3. E-step variants at C3 (fused kernel time is in roofline.kernel_ms)
 run bench_c3_default timeout 600 python bench.py --workload C3 --steps 10 --no-e2e --no-cpu
 run bench_c3_conv_trunc timeout 600 env CUML_B200_CONV_TRUNC=1 python bench.py --workload C3 --steps 10 --no-e2e --no-cpu
@@ -41,6 +59,7 @@ done
 run bench_c2_overlap_8_24 timeout 600 env CUML_B200_OVERLAP=8:24 python bench.py --workload C2 --steps 10 --no-e2e --no-cpu
 run bench_c2_default timeout 600 python bench.py --workload C2 --steps 10 --no-e2e --no-cpu
 
+phase B
 # 4. single-CTA twin (k <= 128): parity first, then C1 / C5
 run parity_solo_v2 timeout 600 env CUML_B200_SOLO_V2=1 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "single_lloyd_step or dot_accuracy or regime2 or transform_matches"
 run bench_c1_default timeout 300 python bench.py --workload C1 --steps 50 --no-e2e --no-cpu
@@ -65,13 +84,14 @@ run parity_upd_lanecol timeout 600 env CUML_B200_UPD_LANECOL=1 python -m pytest 
 run bench_c5_upd_lanecol timeout 600 env CUML_B200_UPD_LANECOL=1 CUML_B200_UPD_PLAN=1 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
 run bench_c5_lanecol_solo_v2 timeout 600 env CUML_B200_UPD_LANECOL=1 CUML_B200_SOLO_V2=1 python bench.py --workload C5 --steps 10 --no-e2e --no-cpu
 
+phase D
 # 4b. transform: lane-pair store pattern (DIST = 2 instantiations) -- parity, then the C4-shape probe both ways
 run parity_dist_pairst timeout 600 env CUML_B200_DIST_PAIRST=1 python -m pytest tests/test_kmeans_gpu.py -m gpu -q -k "transform"
 run c4_probe_default timeout 600 python tools/c4_probe.py
 run c4_probe_pairst timeout 600 env CUML_B200_DIST_PAIRST=1 python tools/c4_probe.py
 
 # 4c. the reference's C++ benchmark shapes through the C++ surface (examples/kmeans_bench.cpp)
-g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include examples/kmeans_bench.cpp -Lcuml_b200/lib -lcuml_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/cuml_b200/lib -o /tmp/kmeans_bench
+case "$PHASES" in *D*) g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include examples/kmeans_bench.cpp -Lcuml_b200/lib -lcuml_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/cuml_b200/lib -o /tmp/kmeans_bench ;; esac
 run cpp_bench timeout 900 /tmp/kmeans_bench
 
 # 4d. k-means|| seeding with the min-distance updates on the tensor-core kernel: parity, then the C5 init time both ways
