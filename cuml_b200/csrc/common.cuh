@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -43,6 +44,25 @@ struct Error : public std::runtime_error {
 void count_launch();
 int64_t launches();
 void reset_launches();
+
+// cudaFuncSetAttribute applies to the current device only, and the boundary may be entered from several host
+// threads (one handle per thread): one flag per device behind a mutex, not a function-local `static bool`.
+class PerDeviceOnce {
+  std::mutex m_;
+  std::vector<char> done_;
+
+ public:
+  template <typename F>
+  void run(int device, F&& f)
+  {
+    std::lock_guard<std::mutex> lock(m_);
+    if (device >= static_cast<int>(done_.size())) done_.resize(device + 1, 0);
+    if (!done_[device]) {
+      f();
+      done_[device] = 1;
+    }
+  }
+};
 
 struct EventPair {
   cudaEvent_t a, b;

@@ -2029,14 +2029,13 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
       CUtensorMap tm_lo = make_map_2d(cen.lo.get(), KBLOCK, cen.k_pad, KBLOCK * sizeof(float), KBLOCK, t.bn,
                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-      static bool pk_attr = false;
-      if (!pk_attr) {
+      static PerDeviceOnce pk_attr;
+      pk_attr.run(h.device, [&] {
         CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(h.smem_optin)));
         CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(h.smem_optin)));
-        pk_attr = true;
-      }
+      });
       // role-level cycle counters of CTA 0 (measurement aid, CUML_B200_DBG_CLK=1), as in the unpacked path below
       DevBuf<long long> clk;
       const bool want_clk = std::getenv("CUML_B200_DBG_CLK") != nullptr;
@@ -2065,26 +2064,24 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
         if (p.fold)
           tm_cn = make_map_2d(cen.cnp.get(), 8, cen.k_pad, 8 * sizeof(float), 8, t.bn, CU_TENSOR_MAP_SWIZZLE_32B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-        static bool pk_solo_attr = false;
-        if (!pk_solo_attr) {
+        static PerDeviceOnce pk_solo_attr;
+        pk_solo_attr.run(h.device, [&] {
           CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, 0, false>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
           CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, 0, false, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
-          pk_solo_attr = true;
-        }
+        });
         if (use_epi_rowown() && t.bn <= TILE_M)   // one centroid tile, >= 4 accumulator stages
           fused_l2_argmin_solo_kernel<true, 0, false, true><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
         else
           fused_l2_argmin_solo_kernel<true, 0, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
       } else if (best_out) fused_l2_argmin_kernel<3><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
       else if (use_epi_rowown() && t.bn <= TILE_M) {   // opt-in row-owner epilogue on the 3xTF32 kernel
-        static bool ro_attr = false;
-        if (!ro_attr) {
+        static PerDeviceOnce ro_attr;
+        ro_attr.run(h.device, [&] {
           CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         static_cast<int>(h.smem_optin)));
-          ro_attr = true;
-        }
+        });
         fused_l2_argmin_kernel<0, true><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
       } else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
       CB2_CHECK_LAUNCH();
@@ -2121,14 +2118,13 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                     KBLOCK, rows_box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     CUtensorMap tm_lo = make_map_2d(cen.lo.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * sizeof(float),
                                     KBLOCK, rows_box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-    static bool ts_attr = false;
-    if (!ts_attr) {
+    static PerDeviceOnce ts_attr;
+    ts_attr.run(h.device, [&] {
       CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(h.smem_optin)));
       CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     static_cast<int>(h.smem_optin)));
-      ts_attr = true;
-    }
+    });
     EventPair ev{};
     if (h.timing) ev = h.begin_event();
     if (tp.pair) {
@@ -2202,8 +2198,8 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   CUtensorMap tm_lo = make_map_2d(cen.lo.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * sizeof(float),
                                   KBLOCK, b_box_rows, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  attr_set.run(h.device, [&] {
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2226,8 +2222,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                   static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
-    attr_set = true;
-  }
+  });
   // transform only: lane-pair store pattern of the distance-matrix epilogue (DIST = 2 instantiations), opt-in
   static const bool dist_pair_store =
     std::getenv("CUML_B200_DIST_PAIRST") && std::atoi(std::getenv("CUML_B200_DIST_PAIRST")) != 0;
@@ -2255,12 +2250,11 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       if (best_out) {
         fused_l2_argmin_2cta_kernel<true, 3><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
       } else if (want_clk && !conv_trunc) {   // role-level cycle counters: a separate instantiation, printed below
-        static bool clk_attr = false;
-        if (!clk_attr) {
+        static PerDeviceOnce clk_attr;
+        clk_attr.run(h.device, [&] {
           CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true, 0, false, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
-          clk_attr = true;
-        }
+        });
         fused_l2_argmin_2cta_kernel<true, 0, false, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
       } else if (conv_trunc)
         fused_l2_argmin_2cta_kernel<true, 0, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
@@ -2284,8 +2278,8 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     if (p.fold)
       tm_cn = make_map_2d(cen.cnp.get(), 8, cen.k_pad, 8 * sizeof(float), 8, b_box_rows, CU_TENSOR_MAP_SWIZZLE_32B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-    static bool solo_attr = false;
-    if (!solo_attr) {
+    static PerDeviceOnce solo_attr;
+    solo_attr.run(h.device, [&] {
       CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, 0, false>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
       CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<false, 0, false>,
@@ -2294,8 +2288,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
       CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, 0, false, true>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
-      solo_attr = true;
-    }
+    });
     if (cen.bf16c && !dist) {
       CUtensorMap tm_hb = make_map_2d(cen.hb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
                                       b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -2318,12 +2311,11 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     else if (dist && dist_pair_store) fused_l2_argmin_kernel<2><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
     else if (dist) fused_l2_argmin_kernel<1><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
     else if (use_epi_rowown() && p.k_tiles == 1 && t.bn <= TILE_M && !dbg_dots) {   // opt-in row-owner epilogue
-      static bool ro_attr = false;
-      if (!ro_attr) {
+      static PerDeviceOnce ro_attr;
+      ro_attr.run(h.device, [&] {
         CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       static_cast<int>(h.smem_optin)));
-        ro_attr = true;
-      }
+      });
       fused_l2_argmin_kernel<0, true><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
     } else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
   }

@@ -12,15 +12,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 inline EncodeTiledFn encode_tiled_fn()
 {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
+  // resolved once (thread-safe initialisation of a function-local static)
+  static const EncodeTiledFn fn = [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
     CB2_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
     if (!p || q != cudaDriverEntryPointSuccess)
       throw Error(CUML_B200_CUDA_ERROR, "cuTensorMapEncodeTiled is not available from the CUDA driver");
-    fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
   return fn;
 }
 

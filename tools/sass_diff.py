@@ -33,11 +33,19 @@ def kernels(path):
 
 def main():
     old, new = kernels(sys.argv[1]), kernels(sys.argv[2])
-    same = reordered = changed = 0
+    same = reordered = changed = renamed = 0
     for name, ins in old.items():
         short = name if len(name) < 150 else name[:147] + "..."
         if name not in new:
-            print("ONLY OLD  ", short)
+            # a template parameter list that grew renames the instantiation: look for the same instruction stream
+            # under a name only the new build has
+            twin = next((m for m, o in new.items() if m not in old and o == ins), None) or next(
+                (m for m, o in new.items() if m not in old and collections.Counter(o) == collections.Counter(ins)), None)
+            if twin:
+                renamed += 1
+                print("RENAMED   ", len(ins), short, "->", twin[:100], "(identical)" if new[twin] == ins else "(reordered)")
+            else:
+                print("ONLY OLD  ", short)
             continue
         other = new[name]
         if ins == other:
@@ -51,7 +59,7 @@ def main():
     for name in new:
         if name not in old:
             print("ONLY NEW  ", len(new[name]), name if len(name) < 150 else name[:147] + "...")
-    print(f"identical {same}, reordered {reordered}, changed {changed}, old {len(old)}, new {len(new)}")
+    print(f"identical {same}, reordered {reordered}, renamed {renamed}, changed {changed}, old {len(old)}, new {len(new)}")
 
 
 if __name__ == "__main__":
