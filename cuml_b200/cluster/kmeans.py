@@ -431,7 +431,7 @@ class KMeans:
 
     # ---- sklearn interop (reference kmeans.pyx:604-689, internals/interop.py:206-257) ----------
     def as_sklearn(self):
-        from sklearn.cluster import KMeans as SkKMeans
+        from sklearn.cluster._kmeans import KMeans as SkKMeans   # the real class even when accel.install() swapped the public name
         init = self.init
         if not isinstance(init, str):
             init = _as_device_matrix(init).t.cpu().numpy()

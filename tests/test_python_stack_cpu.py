@@ -66,6 +66,8 @@ def test_bodies_of_estimator_level_gpu_tests(fake):
     test_kmeans_gpu.test_doctest_kat_and_empty_cluster_rule()
     test_callers.test_kmeans_bin_edges_gpu()
     test_callers.test_kmeans_sampling_gpu()
+    test_callers.test_spectral_label_assignment_gpu()
+    test_callers.test_accel_proxy_under_sklearn_code_gpu()
     import glob
     import os
     for path in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "sk_*.npz"))):

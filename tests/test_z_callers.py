@@ -114,3 +114,92 @@ def test_kmeans_sampling_gpu():
         assert sorted(dist.argmin(1).tolist()) == list(range(k)) and dist.min(1).max() < 1.5
     plain = kmeans_sampling(X, k, round_values=False, random_state=0)
     assert plain.shape == (k, d)
+
+
+# ---- spectral clustering's label assignment (reference cluster/spectral_clustering.pyx:113,337-349) -----------
+@pytest.mark.gpu
+def test_spectral_label_assignment_gpu():
+    from sklearn.metrics import adjusted_rand_score
+    from cuml_b200.cluster import assign_labels_kmeans
+    rng = np.random.default_rng(5)
+    k, per = 4, 300
+    # what a spectral embedding of k well-separated groups looks like: rows near k points of R^k, small spread
+    anchors = np.eye(k, dtype=np.float32) * 0.5 + 0.1
+    true = np.repeat(np.arange(k), per)
+    emb = (anchors[true] + rng.normal(0, 0.01, size=(k * per, k))).astype(np.float32)
+    perm = rng.permutation(len(emb))
+    labels = assign_labels_kmeans(emb[perm], n_clusters=k, n_init=10, random_state=42)
+    assert labels.dtype == np.int32 and labels.shape == (k * per,)
+    assert adjusted_rand_score(true[perm], labels) == 1.0
+    assert np.array_equal(labels, assign_labels_kmeans(emb[perm], n_clusters=k, n_init=10, random_state=42))
+
+
+# ---- the scikit-learn-facing proxy (reference accel/_overrides/sklearn/cluster.py:12-21) --------------------------
+def test_accel_proxy_parameter_translation_and_sklearn_plumbing():
+    from sklearn.base import clone
+    from sklearn.exceptions import NotFittedError
+    from sklearn.utils.validation import check_is_fitted
+    from cuml_b200.accel import KMeans, UnsupportedOnGPU
+    km = KMeans(5, init="k-means++", n_init=3, max_iter=17, tol=1e-3, random_state=4, algorithm="elkan")
+    p = km._engine_params()
+    assert p["init"] == "scalable-k-means++" and (p["n_clusters"], p["n_init"], p["max_iter"], p["tol"]) == (5, 3, 17, 1e-3)
+    assert KMeans(init="random")._engine_params()["init"] == "random"
+    arr = np.zeros((8, 2))
+    assert KMeans(init=arr)._engine_params()["init"] is arr
+    with pytest.raises(UnsupportedOnGPU):
+        KMeans(init=lambda X, k, rs: X[:k])._engine_params()     # no CPU fallback: unsupported means an error
+    with pytest.raises(UnsupportedOnGPU):
+        KMeans(init="pca")._engine_params()
+    twin = clone(km)
+    assert twin is not km and twin.get_params() == km.get_params()
+    assert km.set_params(n_clusters=6).n_clusters == 6
+    with pytest.raises(NotFittedError):
+        check_is_fitted(km)
+    with pytest.raises(NotFittedError):
+        km.predict(np.zeros((2, 2), np.float32))
+    # same constructor parameters, in the same order, as the scikit-learn class it stands in for
+    import inspect
+    from sklearn.cluster._kmeans import KMeans as SkKMeans
+    assert list(inspect.signature(KMeans.__init__).parameters) == list(inspect.signature(SkKMeans.__init__).parameters)
+
+
+@pytest.mark.gpu
+def test_accel_proxy_under_sklearn_code_gpu():
+    """unmodified scikit-learn code -- Pipeline, GridSearchCV, clone, pickle -- on the proxy"""
+    import pickle
+    import sklearn.cluster
+    from sklearn.metrics import adjusted_rand_score
+    from sklearn.model_selection import GridSearchCV
+    from sklearn.pipeline import make_pipeline
+    from sklearn.preprocessing import StandardScaler
+    from sklearn.utils.validation import check_is_fitted
+    from cuml_b200 import accel
+    from oracle import blobs
+    n, d, k = 4000, 8, 4
+    X, centres, true = blobs.make_blobs(n, d, k)
+    real = sklearn.cluster.KMeans
+    try:
+        assert accel.install() is accel.KMeans and sklearn.cluster.KMeans is accel.KMeans
+        from sklearn.cluster import KMeans                      # user code, unchanged
+        pipe = make_pipeline(StandardScaler(), KMeans(n_clusters=k, random_state=0, n_init=3))
+        labels = pipe.fit_predict(X)
+        km = pipe[-1]
+        check_is_fitted(km)
+        assert adjusted_rand_score(true, labels) >= 0.99
+        assert km.cluster_centers_.shape == (k, d) and isinstance(km.cluster_centers_, np.ndarray)
+        assert km.labels_.dtype == np.int32 and km.n_features_in_ == d and km.n_iter_ >= 1
+        Xs = pipe[0].transform(X)
+        assert np.array_equal(pipe.predict(X), km.predict(Xs)) and np.array_equal(km.predict(Xs), labels)
+        D = pipe.transform(X[:50])
+        assert D.shape == (50, k) and np.array_equal(D.argmin(1), labels[:50])
+        assert abs(-km.score(Xs) - km.inertia_) / km.inertia_ < 1e-5
+        assert km.get_feature_names_out().tolist() == [f"kmeans{i}" for i in range(k)]
+        gs = GridSearchCV(KMeans(random_state=0, n_init=1), {"n_clusters": [2, k]}, cv=2).fit(X)   # clone + score
+        assert gs.best_params_ == {"n_clusters": k}
+        km2 = pickle.loads(pickle.dumps(km))
+        assert np.array_equal(km2.predict(Xs), labels)
+        sk = km.as_sklearn()                                     # hand-over to the real scikit-learn class
+        assert type(sk) is real and (sk.predict(Xs) == labels).mean() >= 0.9999   # its own fp32 E-step: near-ties may differ
+    finally:
+        accel.uninstall()
+    assert sklearn.cluster.KMeans is real
