@@ -54,11 +54,11 @@ def dots_tf32_bf16(X, C):
 def half_norm_pieces(C):
     """-1/2 ||c||^2 (fp32) as three tf32-exact pieces (11 + 11 + 2 mantissa bits) folded into the accumulator by a
     ones x pieces MMA; returns (pieces [k, 3] fp32, the fp32 value they represent)"""
-    hn = (-0.5 * (C.astype(np.float32) ** 2).sum(1, dtype=np.float32)).astype(np.float32)
+    hn = (-(0.5 * (C.astype(np.float64) ** 2).sum(1)).astype(np.float32)).astype(np.float32)   # fp64 row sum, rounded once
     p1 = tf32_truncate(hn)
     r1 = (hn - p1).astype(np.float32)
     p2 = tf32_truncate(r1)
-    p3 = tf32_truncate((r1 - p2).astype(np.float32))
+    p3 = (r1 - p2).astype(np.float32)                      # <= 2 significant bits left: already tf32-exact
     return np.stack([p1, p2, p3], axis=1), hn
 
 
