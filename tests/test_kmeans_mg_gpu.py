@@ -121,13 +121,18 @@ def test_distributed_estimator(world):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, q), daemon=True) for r in range(world)]
     for p in procs:
         p.start()
-    outs = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        outs = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:          # a rank that died or hangs must not outlive the test
+            if p.is_alive():
+                p.terminate()
     outs = [o for _, o in outs]
     for o in outs:
         assert o is not None and "crash" not in o, o

@@ -35,7 +35,8 @@ def test_two_threads_two_streams_match_serial_fits():
         except Exception as e:   # surfaced in the main thread
             errs.append(repr(e))
 
-    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    # daemon threads: a worker that never returns fails the assertion below without keeping the interpreter alive
+    threads = [threading.Thread(target=worker, args=(i,), daemon=True) for i in range(2)]
     for t in threads:
         t.start()
     for t in threads:
