@@ -224,7 +224,7 @@ def test_cpp_surface_has_the_reference_signatures(tmp_path):
     assert r.returncode == 0 and "surface ok" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("src", ["kmeans_example.cpp", "kmeans_bench.cpp"])
+@pytest.mark.parametrize("src", ["kmeans_example.cpp", "kmeans_bench.cpp", "kmeans_mg_test.cpp"])
 def test_cpp_surface_compiles_and_links(tmp_path, src):
     # the C++ ML::kmeans::* mirror (include/cuml/cluster/kmeans.hpp) against the built library: every forwarder the
     # examples use resolves to an exported C-ABI symbol (no GPU needed to compile and link)

@@ -93,6 +93,9 @@ run c4_probe_pairst timeout 600 env CUML_B200_DIST_PAIRST=1 python tools/c4_prob
 # 4c. the reference's C++ benchmark shapes through the C++ surface (examples/kmeans_bench.cpp)
 case "$PHASES" in *D*) g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include examples/kmeans_bench.cpp -Lcuml_b200/lib -lcuml_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/cuml_b200/lib -o /tmp/kmeans_bench ;; esac
 run cpp_bench timeout 900 /tmp/kmeans_bench
+# 4c'. the reference's multi-GPU gtest inputs through the C++ surface on a handle with an injected (one-rank) NCCL communicator
+case "$PHASES" in *D*) g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include examples/kmeans_mg_test.cpp -Lcuml_b200/lib -lcuml_b200 -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/cuml_b200/lib -o /tmp/kmeans_mg_test ;; esac
+run cpp_mg_test timeout 600 /tmp/kmeans_mg_test
 
 # 4d. k-means|| seeding with the min-distance updates on the tensor-core kernel: parity, then the C5 init time both ways
 run parity_seed_tc timeout 900 env CUML_B200_SEED_TC=1 python -m pytest tests/test_kmeans_gpu.py tests/test_z_callers.py -m gpu -q -k "seeded or sampling"
