@@ -10,8 +10,6 @@ from __future__ import annotations
 
 import ctypes as C
 
-import numpy as np
-
 from .. import _lib
 from .kmeans import KMeans, _as_device_matrix, _torch
 
