@@ -6,7 +6,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/ab_round2.sh C'   C3 / C2 variants: truncating converter, E-step / M-step overlap
 #   gpurun --timeout 1500 -- 'bash tools/ab_round2.sh D'   transform store pattern, C++ bench shapes, seeding on the tensor cores, C4
 # No argument = all phases.  BUDGET_S (default 1300) stops starting new steps once that much wall-clock has passed.
-# Everything lands in gpurun_out/r2/.  No step depends on another; a failure is logged and the script goes on.
+# Everything lands in gpurun_out/r2/; `python tools/summarize_r2.py` turns the logs into one A/B table.  No step depends on another; a failure is logged and the script goes on.
 set -u
 PHASES=${1:-ABCD}
 BUDGET_S=${BUDGET_S:-1300}
