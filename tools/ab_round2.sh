@@ -5,6 +5,7 @@
 #   gpurun --timeout 1500 -- 'bash tools/ab_round2.sh B'   small-d variants (C5 / C1): solo kernel, row-owner epilogue, lane = column M-step
 #   gpurun --timeout 1500 -- 'bash tools/ab_round2.sh C'   C3 / C2 variants: truncating converter, E-step / M-step overlap
 #   gpurun --timeout 1500 -- 'bash tools/ab_round2.sh D'   transform store pattern, C++ bench shapes, seeding on the tensor cores, C4
+#   gpurun --gpus 2 --timeout 900 -- 'python -m pytest tests/test_kmeans_mg_gpu.py -m gpu -q; ./kmeans_mg_test 2'   the 2-rank tests (skipped on one GPU)
 # No argument = all phases.  BUDGET_S (default 1300) stops starting new steps once that much wall-clock has passed.
 # Everything lands in gpurun_out/r2/; `python tools/summarize_r2.py` turns the logs into one A/B table.  No step depends on another; a failure is logged and the script goes on.
 set -u
