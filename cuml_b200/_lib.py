@@ -43,6 +43,7 @@ EXPORTED_SYMBOLS = [
     "cuml_b200_kmeans_params_default", "cuml_b200_handle_create", "cuml_b200_handle_destroy",
     "cuml_b200_handle_sync", "cuml_b200_handle_stream", "cuml_b200_last_error", "cuml_b200_version",
     "cuml_b200_nccl_unique_id", "cuml_b200_handle_init_comm",
+    "cuml_b200_peer_window_create", "cuml_b200_peer_window_attach",
     "cuml_b200_kmeans_fit_f32_i32", "cuml_b200_kmeans_fit_f64_i32", "cuml_b200_kmeans_fit_f32_i64",
     "cuml_b200_kmeans_fit_f64_i64", "cuml_b200_kmeans_fit_parts_f32", "cuml_b200_kmeans_fit_parts_f64",
     "cuml_b200_kmeans_predict_f32_i32", "cuml_b200_kmeans_predict_f64_i32", "cuml_b200_kmeans_predict_f32_i64",
@@ -86,6 +87,8 @@ def load(build_if_missing=True):
     lib.cuml_b200_handle_sync.argtypes = [vp]
     lib.cuml_b200_nccl_unique_id.argtypes = [vp]
     lib.cuml_b200_handle_init_comm.argtypes = [vp, vp, C.c_int, C.c_int]
+    lib.cuml_b200_peer_window_create.argtypes = [vp, C.c_int, C.c_size_t, vp]
+    lib.cuml_b200_peer_window_attach.argtypes = [vp, vp, C.c_int, C.c_int]
     for t in ("f32", "f64"):
         for ix, it in (("i32", i32), ("i64", i64)):
             getattr(lib, f"cuml_b200_kmeans_fit_{t}_{ix}").argtypes = [vp, P(KMeansParams), vp, it, it, vp, vp, vp, vp]
@@ -132,6 +135,7 @@ class Handle:
         self._h = C.c_void_p()
         check(self._lib.cuml_b200_handle_create(C.byref(self._h), C.c_void_p(stream or 0), None, rank, n_ranks))
         self.rank, self.n_ranks = rank, n_ranks
+        self.comm_kind = None
 
     def getHandle(self):
         return self._h.value
@@ -147,6 +151,22 @@ class Handle:
         buf = C.create_string_buffer(bytes(unique_id), 128)
         check(self._lib.cuml_b200_handle_init_comm(self._h, buf, rank, n_ranks))
         self.rank, self.n_ranks = rank, n_ranks
+        self.comm_kind = "nccl"
+
+    def peer_window_create(self, n_ranks: int, slot_bytes: int = 0) -> bytes:
+        """allocate this rank's exchange window of the peer-memory communicator; returns its 64-byte CUDA IPC handle"""
+        buf = C.create_string_buffer(64)
+        check(self._lib.cuml_b200_peer_window_create(self._h, n_ranks, slot_bytes, buf))
+        return buf.raw
+
+    def peer_window_attach(self, ipc_handles, rank: int, n_ranks: int):
+        """map the windows of all ranks (`ipc_handles`: n_ranks handles in rank order)"""
+        blob = b"".join(bytes(x) for x in ipc_handles)
+        assert len(blob) == 64 * n_ranks
+        buf = C.create_string_buffer(blob, len(blob))
+        check(self._lib.cuml_b200_peer_window_attach(self._h, buf, rank, n_ranks))
+        self.rank, self.n_ranks = rank, n_ranks
+        self.comm_kind = "peer"
 
     @staticmethod
     def nccl_unique_id() -> bytes:

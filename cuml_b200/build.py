@@ -19,7 +19,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIBNAME = "libcuml_b200.so"
 
-SOURCES = ["handle.cu", "distance_simt.cu", "centroid_update.cu", "fused_l2_argmin_sm100.cu", "centroid_update_tma.cu", "seeding.cu",
+SOURCES = ["handle.cu", "peer_comm.cu", "distance_simt.cu", "centroid_update.cu", "fused_l2_argmin_sm100.cu", "centroid_update_tma.cu", "seeding.cu",
            "kmeans_api.cu"]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

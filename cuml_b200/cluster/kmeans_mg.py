@@ -14,18 +14,45 @@ from .. import _lib
 from .kmeans import KMeans, _as_device_matrix, _torch
 
 
-def comms_from_torch_distributed(stream=None):
-    """Create a Handle whose NCCL communicator spans the default torch.distributed group."""
+def comms_from_torch_distributed(stream=None, backend=None):
+    """Create a Handle whose communicator spans the default torch.distributed group.
+
+    backend: "nccl" (an NCCL communicator built from a unique id rank 0 creates) or "peer" (the library's own
+    peer-memory collectives: every rank maps the others' exchange windows through CUDA IPC; one node only).  Default:
+    the CUML_B200_COMM environment variable, else "peer" when two ranks share a device (NCCL refuses that topology),
+    else "nccl".  torch.distributed only ships the rendezvous blobs."""
+    import os
+    import socket
+    import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(), dist.get_world_size()
     if stream is None:
-        import torch
         stream = torch.cuda.current_stream().cuda_stream or 1   # 0x1 = cudaStreamLegacy
     h = _lib.Handle(stream=stream, n_ranks=world, rank=rank)
-    if world > 1:
+    if world <= 1:
+        return h
+    where = [None] * world
+    dist.all_gather_object(where, (socket.gethostname(), str(torch.cuda.get_device_properties(torch.cuda.current_device()).uuid)))
+    one_node = len({w[0] for w in where}) == 1
+    shared_device = len(set(where)) < world
+    if backend is None:
+        backend = os.environ.get("CUML_B200_COMM") or ("peer" if shared_device else "nccl")
+    if backend == "peer":
+        if not one_node:
+            raise ValueError("the peer-memory communicator needs all ranks on one node")
+        mine = h.peer_window_create(world)
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        h.peer_window_attach(handles, rank, world)
+        dist.barrier()          # every rank has mapped every window before the first exchange
+    elif backend == "nccl":
+        if shared_device:
+            raise ValueError("NCCL cannot place two ranks on one device; use backend='peer'")
         box = [_lib.Handle.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         h.init_comm(box[0], rank, world)
+    else:
+        raise ValueError(f"unknown communicator backend {backend!r}")
     return h
 
 

@@ -848,7 +848,7 @@ accumulate_lanecol_kernel(const LaneColParams p)
 // warps whose private tables fit shared memory (0: the kernel does not apply)
 static int lanecol_warps(const Handle& h, int d, int k)
 {
-  static const bool on = std::getenv("CUML_B200_UPD_LANECOL") && std::atoi(std::getenv("CUML_B200_UPD_LANECOL")) != 0;
+  static const bool on = env_flag("CUML_B200_UPD_LANECOL", true);
   if (!on || (d != 4 && d != 8 && d != 16)) return 0;
   const size_t per_warp = (static_cast<size_t>(k) * 32 + static_cast<size_t>(32 / d) * k) * sizeof(float);
   const int warps       = static_cast<int>(std::min<size_t>(16, (h.smem_optin - 1024) / per_warp));

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstdio>
 #include <memory>
 #include <mutex>
@@ -68,12 +69,16 @@ struct EventPair {
   cudaEvent_t a, b;
 };
 
+struct PeerComm;   // peer_comm.cu
+
 // the sliver of raft::handle_t the k-means path uses
 struct Handle {
   cudaStream_t stream = nullptr;
   bool own_stream      = false;
   void* comm           = nullptr;  // ncclComm_t
   bool own_comm        = false;
+  PeerComm* peer       = nullptr;  // peer-memory communicator (peer_comm.cu); used instead of NCCL once attached
+  bool use_peer        = false;
   int rank             = 0;
   int n_ranks          = 1;
   int device           = 0;
@@ -179,6 +184,13 @@ inline bool is_device_pointer(const void* ptr)
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// boolean environment switch with a default (A/B measurement aid; the defaults are the measured best)
+inline bool env_flag(const char* name, bool dflt)
+{
+  const char* e = std::getenv(name);
+  return e ? std::atoi(e) != 0 : dflt;
+}
+
 // ---- NCCL (loaded lazily with dlopen; only the MG path needs it) -------------------------
 namespace nccl {
 void allreduce_sum_f64(Handle& h, double* buf, size_t count);
@@ -189,5 +201,43 @@ void unique_id(void* out128);
 void init_rank(Handle& h, const void* id128, int rank, int n_ranks);
 void destroy(Handle& h);
 }  // namespace nccl
+
+// ---- peer-memory collectives (peer_comm.cu): the library's own kernels over NVLink / same-device IPC ----
+namespace peer {
+void window_create(Handle& h, size_t slot_bytes, int n_ranks, void* ipc_handle_out64);
+void window_attach(Handle& h, const void* all_handles, int rank, int n_ranks);
+void destroy(Handle& h);
+void allreduce_sum_f64(Handle& h, double* buf, size_t count);
+void allreduce_max_f64(Handle& h, double* buf, size_t count);
+void broadcast_bytes(Handle& h, void* buf, size_t bytes, int root);
+void allgather_bytes(Handle& h, const void* send, void* recv, size_t bytes_per_rank);
+// all-reduce of the packed M-step sums fused with the centroid update; false = not applicable (caller falls back)
+template <typename T>
+bool allreduce_finalize(Handle& h, double* packed, size_t count, T* C, int k, int d, double* shift2_out);
+}  // namespace peer
+
+// ---- what the path calls: dispatch on the communicator the handle carries (raft::comms::comms_t role) ----
+namespace comms {
+inline void allreduce_sum_f64(Handle& h, double* buf, size_t count)
+{
+  if (h.n_ranks <= 1) return;
+  h.use_peer ? peer::allreduce_sum_f64(h, buf, count) : nccl::allreduce_sum_f64(h, buf, count);
+}
+inline void allreduce_max_f64(Handle& h, double* buf, size_t count)
+{
+  if (h.n_ranks <= 1) return;
+  h.use_peer ? peer::allreduce_max_f64(h, buf, count) : nccl::allreduce_max_f64(h, buf, count);
+}
+inline void broadcast_bytes(Handle& h, void* buf, size_t bytes, int root)
+{
+  if (h.n_ranks <= 1) return;
+  h.use_peer ? peer::broadcast_bytes(h, buf, bytes, root) : nccl::broadcast_bytes(h, buf, bytes, root);
+}
+inline void allgather_bytes(Handle& h, const void* send, void* recv, size_t bytes_per_rank)
+{
+  if (h.n_ranks > 1 && h.use_peer) return peer::allgather_bytes(h, send, recv, bytes_per_rank);
+  nccl::allgather_bytes(h, send, recv, bytes_per_rank);   // also the 1-rank copy
+}
+}  // namespace comms
 
 }  // namespace cb2

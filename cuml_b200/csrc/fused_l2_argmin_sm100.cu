@@ -923,7 +923,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
       long long w_acc = 0, w_a = 0, w_b = 0, t_start = 0;
       if constexpr (CLK) t_start = clock64();
       if (p.fold && pair < pair_tiles) ptx::mbar_wait_park(ptx::smem_u32(&bars->cn_full), 0u);
-      const uint32_t first_acc = p.fold ? 1u : 0u;   // the fold MMA initialises the accumulator
+      uint32_t last_kind = 0;   // kind of the last MMA issued: 0 tf32, 1 f16 (BF16C issue order, see below)
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs, ra_tile.advance_by(p.kb, p.a_slots)) {
         for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
           const uint32_t acc = racc.slot, pacc = racc.phase;
@@ -931,12 +931,20 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
           Ring ra = p.a_stream ? ra_run : ra_tile;
           CB2_WAIT_CLK(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u, w_acc);
           const uint32_t d_tmem = tmem_base + acc * p.bn;
-          if (p.fold) {
+          // Issue order (BF16C): a change of MMA kind (tf32 <-> f16) costs the tensor pipe ~135 cycles (measured,
+          // tools/micro/mma_rate_pair.cu: 178 cycles per MMA in the alternating mix against 142 / 147 alone), so every
+          // K-block starts with the kind the previous one ended with, and the tf32 fold MMA rides in front of the
+          // accumulator's first tf32 group: one change per K-block instead of two.
+          bool fold_pending = p.fold != 0;
+          uint32_t acc_on   = 0u;     // 0 for the first MMA into this accumulator
+          if (p.fold && !BF16C) {
             ptx::tc_fence_after();
             if (ptx::elect_one())
               ptx::mma_tf32_ss_2cta(d_tmem, ptx::umma_desc_sw32(fold_u32), ptx::umma_desc_sw32(fold_u32 + (1u + nt) * FOLD_TILE),
                                     idesc, 0u);
             __syncwarp();
+            fold_pending = false;
+            acc_on       = 1u;
           }
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sa = ra.slot, pa = ra.phase;
@@ -957,6 +965,8 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
             const uint64_t db_hi = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes);
             const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
             const int nks = min(4, (p.d - kbi * KBLOCK + 7) / 8);
+            const bool tf_first = last_kind == 0;
+            if (BF16C) last_kind ^= 1u;   // every K-block issues both kinds, so it ends on the other one
             if (ptx::elect_one()) {
               if (BF16C) {
                 // corrections first (bf16, K = 16), then the tf32 main term
@@ -966,32 +976,48 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
                 const uint64_t db_hb = ptx::umma_desc_sw64(b_hb), db_lb = ptx::umma_desc_sw64(b_hb + b_half_bytes / 2);
                 const int nk16 = (nks + 1) / 2;
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  if (ks >= nk16 || (p.dbg_skip & 8)) break;
-                  const uint64_t adv = static_cast<uint64_t>(ks * 2);
-                  ptx::mma_f16_ss_2cta(d_tmem, da_lb + adv, db_hb + adv, idesc16, ((kbi | ks) != 0 ? 1u : 0u) | first_acc);
-                  ptx::mma_f16_ss_2cta(d_tmem, da_hb + adv, db_lb + adv, idesc16, 1u);
-                }
+                for (int ph = 0; ph < 2; ++ph) {
+                  if ((ph == 0) == tf_first) {   // tf32 main term (preceded by the fold MMA of a new accumulator)
+                    if (fold_pending) {
+                      ptx::mma_tf32_ss_2cta(d_tmem, ptx::umma_desc_sw32(fold_u32),
+                                            ptx::umma_desc_sw32(fold_u32 + (1u + nt) * FOLD_TILE), idesc, acc_on);
+                      acc_on = 1u;
+                    }
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  if (ks >= nks || (p.dbg_skip & 16)) break;
-                  const uint64_t adv = static_cast<uint64_t>(ks * 2);
-                  ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+                    for (int ks = 0; ks < 4; ++ks) {
+                      if (ks >= nks) break;
+                      const uint64_t adv = static_cast<uint64_t>(ks * 2);
+                      ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_hi + adv, idesc, acc_on);
+                      acc_on = 1u;
+                    }
+                  } else {                        // the two bf16 correction terms (K = 16)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                      if (ks >= nk16) break;
+                      const uint64_t adv = static_cast<uint64_t>(ks * 2);
+                      ptx::mma_f16_ss_2cta(d_tmem, da_lb + adv, db_hb + adv, idesc16, acc_on);
+                      ptx::mma_f16_ss_2cta(d_tmem, da_hb + adv, db_lb + adv, idesc16, 1u);
+                      acc_on = 1u;
+                    }
+                  }
                 }
               } else {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                   if (ks >= nks) break;
                   const uint64_t adv = static_cast<uint64_t>(ks * 2);
-                  ptx::mma_tf32_ss_2cta(d_tmem, da_lo + adv, db_hi + adv, idesc, ((kbi | ks) != 0 ? 1u : 0u) | first_acc);
+                  ptx::mma_tf32_ss_2cta(d_tmem, da_lo + adv, db_hi + adv, idesc, acc_on);
                   ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
                   ptx::mma_tf32_ss_2cta(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+                  acc_on = 1u;
                 }
               }
               if (!p.b_resident) ptx::mma_commit_2cta(ptx::smem_u32(&bars->b_empty[sb]), 3);
               if (nt == p.k_tiles - 1 || p.a_stream) ptx::mma_commit_2cta(ptx::smem_u32(&bars->a_empty[sa]), 3);
             }
             __syncwarp();
+            fold_pending = false;   // issued with the first tf32 group
+            acc_on       = 1u;
           }
           ra_run = ra;
           if (ptx::elect_one()) ptx::mma_commit_2cta(ptx::smem_u32(&bars->acc_full[acc]), 3);
@@ -1244,7 +1270,7 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
       uint32_t b_cnt = 0, acc_cnt = 0;
       Ring ra_tile, ra_run, rb, racc;
       if (p.fold && pair < pair_tiles) ptx::mbar_wait_park(ptx::smem_u32(&bars->cn_full), 0u);
-      const uint32_t first_acc = p.fold ? 1u : 0u;   // the fold MMA initialises the accumulator
+      uint32_t last_kind = 0;   // kind of the last MMA issued: 0 tf32, 1 f16 (issue order as in the pair kernel)
       for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs, ra_tile.advance_by(p.kb, p.a_slots)) {
         for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
           const uint32_t acc = racc.slot, pacc = racc.phase;
@@ -1252,12 +1278,16 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
           Ring ra = p.a_stream ? ra_run : ra_tile;
           ptx::mbar_wait_park(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
           const uint32_t d_tmem = tmem_base + acc * p.bn;
-          if (p.fold) {
+          bool fold_pending = p.fold != 0;
+          uint32_t acc_on   = 0u;     // 0 for the first MMA into this accumulator
+          if (p.fold && !BF16C) {
             ptx::tc_fence_after();
             if (ptx::elect_one())
               ptx::mma_tf32_ss(d_tmem, ptx::umma_desc_sw32(fold_u32), ptx::umma_desc_sw32(fold_u32 + (1u + nt) * FOLD_TILE),
                                     idesc, 0u);
             __syncwarp();
+            fold_pending = false;
+            acc_on       = 1u;
           }
           for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
             const uint32_t sa = ra.slot, pa = ra.phase;
@@ -1278,6 +1308,8 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
             const uint64_t db_hi = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes);
             const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
             const int nks = min(4, (p.d - kbi * KBLOCK + 7) / 8);
+            const bool tf_first = last_kind == 0;
+            if (BF16C) last_kind ^= 1u;
             if (ptx::elect_one()) {
               if (BF16C) {
                 // corrections first (bf16, K = 16), then the tf32 main term
@@ -1287,32 +1319,48 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
                 const uint64_t db_hb = ptx::umma_desc_sw64(b_hb), db_lb = ptx::umma_desc_sw64(b_hb + b_half_bytes / 2);
                 const int nk16 = (nks + 1) / 2;
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                  if (ks >= nk16 || (p.dbg_skip & 8)) break;
-                  const uint64_t adv = static_cast<uint64_t>(ks * 2);
-                  ptx::mma_f16_ss(d_tmem, da_lb + adv, db_hb + adv, idesc16, ((kbi | ks) != 0 ? 1u : 0u) | first_acc);
-                  ptx::mma_f16_ss(d_tmem, da_hb + adv, db_lb + adv, idesc16, 1u);
-                }
+                for (int ph = 0; ph < 2; ++ph) {
+                  if ((ph == 0) == tf_first) {   // tf32 main term (preceded by the fold MMA of a new accumulator)
+                    if (fold_pending) {
+                      ptx::mma_tf32_ss(d_tmem, ptx::umma_desc_sw32(fold_u32), ptx::umma_desc_sw32(fold_u32 + (1u + nt) * FOLD_TILE),
+                                       idesc, acc_on);
+                      acc_on = 1u;
+                    }
 #pragma unroll
-                for (int ks = 0; ks < 4; ++ks) {
-                  if (ks >= nks || (p.dbg_skip & 16)) break;
-                  const uint64_t adv = static_cast<uint64_t>(ks * 2);
-                  ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+                    for (int ks = 0; ks < 4; ++ks) {
+                      if (ks >= nks) break;
+                      const uint64_t adv = static_cast<uint64_t>(ks * 2);
+                      ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_hi + adv, idesc, acc_on);
+                      acc_on = 1u;
+                    }
+                  } else {                        // the two bf16 correction terms (K = 16)
+#pragma unroll
+                    for (int ks = 0; ks < 2; ++ks) {
+                      if (ks >= nk16) break;
+                      const uint64_t adv = static_cast<uint64_t>(ks * 2);
+                      ptx::mma_f16_ss(d_tmem, da_lb + adv, db_hb + adv, idesc16, acc_on);
+                      ptx::mma_f16_ss(d_tmem, da_hb + adv, db_lb + adv, idesc16, 1u);
+                      acc_on = 1u;
+                    }
+                  }
                 }
               } else {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) {
                   if (ks >= nks) break;
                   const uint64_t adv = static_cast<uint64_t>(ks * 2);
-                  ptx::mma_tf32_ss(d_tmem, da_lo + adv, db_hi + adv, idesc, ((kbi | ks) != 0 ? 1u : 0u) | first_acc);
+                  ptx::mma_tf32_ss(d_tmem, da_lo + adv, db_hi + adv, idesc, acc_on);
                   ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_lo + adv, idesc, 1u);
                   ptx::mma_tf32_ss(d_tmem, da_hi + adv, db_hi + adv, idesc, 1u);
+                  acc_on = 1u;
                 }
               }
               if (!p.b_resident) ptx::mma_commit(ptx::smem_u32(&bars->b_empty[sb]));
               if (nt == p.k_tiles - 1 || p.a_stream) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[sa]));
             }
             __syncwarp();
+            fold_pending = false;
+            acc_on       = 1u;
           }
           ra_run = ra;
           if (ptx::elect_one()) ptx::mma_commit(ptx::smem_u32(&bars->acc_full[acc]));
@@ -1740,15 +1788,13 @@ TilePlan plan_tiles(int d, int k, size_t smem_limit)
 // single-CTA twin of the pair kernel (bf16 corrections + folded norms for k <= 128): opt-in until measured
 bool use_solo_v2()
 {
-  const char* e = std::getenv("CUML_B200_SOLO_V2");
-  return e && std::atoi(e) != 0;
+  return env_flag("CUML_B200_SOLO_V2", true);
 }
 
 // row-owner epilogue of the single-CTA tf32 + bf16 kernel (see epilogue_role_rowown): opt-in until measured
 bool use_epi_rowown()
 {
-  const char* e = std::getenv("CUML_B200_EPI_ROWOWN");
-  return e && std::atoi(e) != 0;
+  return env_flag("CUML_B200_EPI_ROWOWN", true);
 }
 
 // CTA-pair plan: BN = 256 split across the pair (128 centroid rows per CTA), deeper X ring.
@@ -2225,7 +2271,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   });
   // transform only: lane-pair store pattern of the distance-matrix epilogue (DIST = 2 instantiations), opt-in
   static const bool dist_pair_store =
-    std::getenv("CUML_B200_DIST_PAIRST") && std::atoi(std::getenv("CUML_B200_DIST_PAIRST")) != 0;
+    env_flag("CUML_B200_DIST_PAIRST", true);
   EventPair ev{};
   if (h.timing) ev = h.begin_event();
   const long long grid_dbg = pair ? h.sm_count / 2 : h.sm_count;
@@ -2246,7 +2292,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       CUtensorMap tm_lb = make_map_2d(cen.lb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
                                       b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-      static const bool conv_trunc = std::getenv("CUML_B200_CONV_TRUNC") && std::atoi(std::getenv("CUML_B200_CONV_TRUNC")) != 0;
+      static const bool conv_trunc = env_flag("CUML_B200_CONV_TRUNC", true);
       if (best_out) {
         fused_l2_argmin_2cta_kernel<true, 3><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
       } else if (want_clk && !conv_trunc) {   // role-level cycle counters: a separate instantiation, printed below

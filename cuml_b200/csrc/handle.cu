@@ -191,6 +191,7 @@ void free_handle(Handle* h)
   if (h->ev_fwd) cudaEventDestroy(h->ev_fwd);
   if (h->ev_back) cudaEventDestroy(h->ev_back);
   nccl::destroy(*h);
+  peer::destroy(*h);
   for (auto& v : {&h->fused_events, &h->update_events, &h->event_pool})
     for (auto& e : *v) {
       cudaEventDestroy(e.a);

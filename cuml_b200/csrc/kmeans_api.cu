@@ -100,7 +100,7 @@ int64_t allreduce_i64_host(Handle& h, int64_t v)
   DevBuf<double> cell(1, h.stream);
   double dv = static_cast<double>(v);
   CB2_CUDA(cudaMemcpyAsync(cell.get(), &dv, sizeof(double), cudaMemcpyHostToDevice, h.stream));
-  nccl::allreduce_sum_f64(h, cell.get(), 1);
+  comms::allreduce_sum_f64(h, cell.get(), 1);
   CB2_CUDA(cudaMemcpyAsync(&dv, cell.get(), sizeof(double), cudaMemcpyDeviceToHost, h.stream));
   CB2_CUDA(cudaStreamSynchronize(h.stream));
   return static_cast<int64_t>(dv + 0.5);
@@ -112,7 +112,7 @@ int64_t rank_row_offset(Handle& h, int64_t n_local)
   if (h.n_ranks <= 1) return 0;
   DevBuf<int64_t> sb(1, h.stream), rb(h.n_ranks, h.stream);
   CB2_CUDA(cudaMemcpyAsync(sb.get(), &n_local, sizeof(int64_t), cudaMemcpyHostToDevice, h.stream));
-  nccl::allgather_bytes(h, sb.get(), rb.get(), sizeof(int64_t));
+  comms::allgather_bytes(h, sb.get(), rb.get(), sizeof(int64_t));
   std::vector<int64_t> cnt(h.n_ranks);
   CB2_CUDA(cudaMemcpyAsync(cnt.data(), rb.get(), sizeof(int64_t) * h.n_ranks, cudaMemcpyDeviceToHost, h.stream));
   CB2_CUDA(cudaStreamSynchronize(h.stream));
@@ -158,7 +158,7 @@ bool fit_streamed(Handle& h, const cuml_b200_kmeans_params_t& params, const T* c
     if (h.n_ranks > 1) {
       DevBuf<double> cell(1, h.stream);
       CB2_CUDA(cudaMemcpyAsync(cell.get(), &ws, sizeof(double), cudaMemcpyHostToDevice, h.stream));
-      nccl::allreduce_sum_f64(h, cell.get(), 1);
+      comms::allreduce_sum_f64(h, cell.get(), 1);
       CB2_CUDA(cudaMemcpyAsync(&ws, cell.get(), sizeof(double), cudaMemcpyDeviceToHost, h.stream));
       CB2_CUDA(cudaStreamSynchronize(h.stream));
     }
@@ -240,8 +240,7 @@ bool fit_streamed(Handle& h, const cuml_b200_kmeans_params_t& params, const T* c
         solver.accumulate(C, false, !first);
         first = false;
       });
-      nccl::allreduce_sum_f64(h, packed, count);
-      finalize_centroids<T>(h, packed, C, k, di, packed + count);
+      exchange_and_finalize<T>(h, packed, count, C, k, di);
       ++iters;
       if (params.tol > 0.0) {
         CB2_CUDA(cudaMemcpyAsync(h.pinned, packed + count, sizeof(double), cudaMemcpyDeviceToHost, h.stream));
@@ -260,7 +259,7 @@ bool fit_streamed(Handle& h, const cuml_b200_kmeans_params_t& params, const T* c
       first = false;
     });
     double* cell = packed + count - 1;
-    nccl::allreduce_sum_f64(h, cell, 1);
+    comms::allreduce_sum_f64(h, cell, 1);
     CB2_CUDA(cudaMemcpyAsync(h.pinned, cell, sizeof(double), cudaMemcpyDeviceToHost, h.stream));
     CB2_CUDA(cudaStreamSynchronize(h.stream));
     const double inertia = h.pinned[0] * wscale;
@@ -318,7 +317,7 @@ void fit_parts_impl(Handle& h, const cuml_b200_kmeans_params_t& params, const T*
     if (h.n_ranks > 1) {
       DevBuf<double> cell(1, h.stream);
       CB2_CUDA(cudaMemcpyAsync(cell.get(), &ws, sizeof(double), cudaMemcpyHostToDevice, h.stream));
-      nccl::allreduce_sum_f64(h, cell.get(), 1);
+      comms::allreduce_sum_f64(h, cell.get(), 1);
       CB2_CUDA(cudaMemcpyAsync(&ws, cell.get(), sizeof(double), cudaMemcpyDeviceToHost, h.stream));
       CB2_CUDA(cudaStreamSynchronize(h.stream));
     }
@@ -498,6 +497,21 @@ int cuml_b200_handle_init_comm(cuml_b200_handle_t* h, const void* id, int rank, 
     CB2_EXPECTS(h && id, "null handle or id");
     CB2_EXPECTS(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "invalid rank / n_ranks");
     nccl::init_rank(*reinterpret_cast<Handle*>(h), id, rank, n_ranks);
+  });
+}
+
+int cuml_b200_peer_window_create(cuml_b200_handle_t* h, int n_ranks, size_t slot_bytes, void* ipc_handle_out_64_bytes)
+{
+  return guarded([&] {
+    CB2_EXPECTS(h && ipc_handle_out_64_bytes, "null handle or output buffer");
+    peer::window_create(*reinterpret_cast<Handle*>(h), slot_bytes, n_ranks, ipc_handle_out_64_bytes);
+  });
+}
+int cuml_b200_peer_window_attach(cuml_b200_handle_t* h, const void* all_ipc_handles, int rank, int n_ranks)
+{
+  return guarded([&] {
+    CB2_EXPECTS(h && all_ipc_handles, "null handle or handle list");
+    peer::window_attach(*reinterpret_cast<Handle*>(h), all_ipc_handles, rank, n_ranks);
   });
 }
 

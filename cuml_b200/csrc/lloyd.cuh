@@ -50,6 +50,17 @@ inline OverlapCfg overlap_from_env()
   return c;
 }
 
+// Cross-rank sum of the packed M-step result followed by the centroid update.  With the peer-memory communicator the
+// two are one exchange: push kernel + a finalize kernel that waits for the peers' slots (peer_comm.cu); otherwise
+// ncclAllReduce + finalize.
+template <typename T>
+inline void exchange_and_finalize(Handle& h, double* packed, size_t count, T* C, int k, int d)
+{
+  if (h.n_ranks > 1 && h.use_peer && peer::allreduce_finalize<T>(h, packed, count, C, k, d, packed + count)) return;
+  comms::allreduce_sum_f64(h, packed, count);
+  finalize_centroids<T>(h, packed, C, k, d, packed + count);
+}
+
 // One object per (dataset, k): owns labels, operand buffers and the M-step workspace.
 template <typename T>
 class LloydSolver {
@@ -225,8 +236,7 @@ class LloydSolver {
       CB2_CUDA(cudaEventRecord(h_.ev_back, h_.aux_stream));
       CB2_CUDA(cudaStreamWaitEvent(h_.stream, h_.ev_back, 0));
       CB2_CUDA(cudaMemsetAsync(packed_.get() + packed_count() - 1, 0, sizeof(double), h_.stream));
-      nccl::allreduce_sum_f64(h_, packed_.get(), packed_count());
-      finalize_centroids<T>(h_, packed_.get(), C, k_, d_, packed_.get() + packed_count());
+      exchange_and_finalize<T>(h_, packed_.get(), packed_count(), C, k_, d_);
       return true;
     }
   }
@@ -237,8 +247,7 @@ class LloydSolver {
     if (!with_inertia && step_overlapped(C)) return;
     assign(C);
     accumulate(C, with_inertia);
-    nccl::allreduce_sum_f64(h_, packed_.get(), packed_count());
-    finalize_centroids<T>(h_, packed_.get(), C, k_, d_, packed_.get() + packed_count());
+    exchange_and_finalize<T>(h_, packed_.get(), packed_count(), C, k_, d_);
   }
 
   // inertia of the current labelling wrt C (exact difference form), all ranks; host result
@@ -246,7 +255,7 @@ class LloydSolver {
   {
     inertia_only(C);
     double* cell = packed_.get() + packed_count() - 1;
-    nccl::allreduce_sum_f64(h_, cell, 1);
+    comms::allreduce_sum_f64(h_, cell, 1);
     CB2_CUDA(cudaMemcpyAsync(h_.pinned, cell, sizeof(double), cudaMemcpyDeviceToHost, h_.stream));
     CB2_CUDA(cudaStreamSynchronize(h_.stream));
     return h_.pinned[0];

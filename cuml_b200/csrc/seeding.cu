@@ -199,7 +199,7 @@ double allreduce_host(Handle& h, double v)
   if (h.n_ranks <= 1) return v;
   DevBuf<double> cell(1, h.stream);
   CB2_CUDA(cudaMemcpyAsync(cell.get(), &v, sizeof(double), cudaMemcpyHostToDevice, h.stream));
-  nccl::allreduce_sum_f64(h, cell.get(), 1);
+  comms::allreduce_sum_f64(h, cell.get(), 1);
   CB2_CUDA(cudaMemcpyAsync(&v, cell.get(), sizeof(double), cudaMemcpyDeviceToHost, h.stream));
   CB2_CUDA(cudaStreamSynchronize(h.stream));
   return v;
@@ -258,7 +258,7 @@ void init_random(SeedContext<T>& ctx, int k, T* C)
     return;
   }
   DevBuf<T> recv(static_cast<size_t>(m_max) * ctx.d * G, h.stream);
-  nccl::allgather_bytes(h, send.get(), recv.get(), sizeof(T) * m_max * ctx.d);
+  comms::allgather_bytes(h, send.get(), recv.get(), sizeof(T) * m_max * ctx.d);
   int out = 0;
   for (int r = 0; r < S; ++r) {
     const int cnt = per + (r == 0 ? rem : 0);
@@ -364,7 +364,7 @@ void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params,
     if (h.n_ranks > 1) {
       DevBuf<int64_t> sendb(1, h.stream), recvb(h.n_ranks, h.stream);
       CB2_CUDA(cudaMemcpyAsync(sendb.get(), &ctx.n_local, sizeof(int64_t), cudaMemcpyHostToDevice, h.stream));
-      nccl::allgather_bytes(h, sendb.get(), recvb.get(), sizeof(int64_t));
+      comms::allgather_bytes(h, sendb.get(), recvb.get(), sizeof(int64_t));
       std::vector<int64_t> cnt(h.n_ranks);
       CB2_CUDA(cudaMemcpyAsync(cnt.data(), recvb.get(), sizeof(int64_t) * h.n_ranks, cudaMemcpyDeviceToHost, h.stream));
       CB2_CUDA(cudaStreamSynchronize(h.stream));
@@ -377,7 +377,7 @@ void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params,
     if (owner == h.rank)
       CB2_CUDA(cudaMemcpyAsync(cand.get(), local_row(ctx.parts, d, g0 - offs[owner]), sizeof(T) * d,
                                cudaMemcpyDeviceToDevice, h.stream));
-    nccl::broadcast_bytes(h, cand.get(), sizeof(T) * d, owner);
+    comms::broadcast_bytes(h, cand.get(), sizeof(T) * d, owner);
     m = 1;
   }
 
@@ -390,7 +390,7 @@ void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params,
   std::vector<DevBuf<int32_t>> lab_tc;
   TcCentroids cen_tc;
   if constexpr (std::is_same<T, float>::value) {
-    static const bool env_on = std::getenv("CUML_B200_SEED_TC") && std::atoi(std::getenv("CUML_B200_SEED_TC")) != 0;
+    static const bool env_on = env_flag("CUML_B200_SEED_TC", true);
     seed_tc = env_on && h.cc_major == 10 && engine_from_env(ctx.engine) != ENGINE_SIMT;
     for (auto& pt : ctx.parts)
       if (pt.n > 0 && reinterpret_cast<uintptr_t>(pt.X) % 16 != 0) seed_tc = false;
@@ -494,7 +494,7 @@ void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params,
     if (h.n_ranks > 1) {
       DevBuf<int> sb(1, h.stream), rb(h.n_ranks, h.stream);
       CB2_CUDA(cudaMemcpyAsync(sb.get(), &my_cnt, sizeof(int), cudaMemcpyHostToDevice, h.stream));
-      nccl::allgather_bytes(h, sb.get(), rb.get(), sizeof(int));
+      comms::allgather_bytes(h, sb.get(), rb.get(), sizeof(int));
       CB2_CUDA(cudaMemcpyAsync(counts.data(), rb.get(), sizeof(int) * h.n_ranks, cudaMemcpyDeviceToHost, h.stream));
       CB2_CUDA(cudaStreamSynchronize(h.stream));
     }
@@ -519,7 +519,7 @@ void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params,
       DevBuf<T> recvb(static_cast<size_t>(std::max(mx, 1)) * d * h.n_ranks, h.stream);
       CB2_CUDA(cudaMemsetAsync(sendb.get(), 0, sendb.n * sizeof(T), h.stream));
       gather_local(h, ctx.parts, d, rows, sendb.get());
-      nccl::allgather_bytes(h, sendb.get(), recvb.get(), sizeof(T) * mx * d);
+      comms::allgather_bytes(h, sendb.get(), recvb.get(), sizeof(T) * mx * d);
       int out = m;
       for (int r = 0; r < h.n_ranks; ++r) {
         if (counts[r])
@@ -557,7 +557,7 @@ void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params,
     all.assign(cand.get());
     for (size_t pi = 0; pi < ctx.parts.size(); ++pi)
       weighted_histogram<T>(h, all.labels(pi), ctx.parts[pi].w, ctx.parts[pi].n, m, cw64.get());
-    nccl::allreduce_sum_f64(h, cw64.get(), m);
+    comms::allreduce_sum_f64(h, cw64.get(), m);
   }
   std::vector<double> cw_h(m);
   CB2_CUDA(cudaMemcpyAsync(cw_h.data(), cw64.get(), sizeof(double) * m, cudaMemcpyDeviceToHost, h.stream));
@@ -576,7 +576,7 @@ void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params,
     small.run(C, std::max(1, params.max_iter), params.tol);
   }
   // identical centroids on every rank by construction of the inputs; broadcast rank 0's to be safe
-  nccl::broadcast_bytes(h, C, sizeof(T) * k * d, 0);
+  comms::broadcast_bytes(h, C, sizeof(T) * k * d, 0);
   CB2_CUDA(cudaStreamSynchronize(h.stream));
 }
 

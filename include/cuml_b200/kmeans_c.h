@@ -93,6 +93,17 @@ CUML_B200_API int cuml_b200_nccl_unique_id(void* id_out_128_bytes);
 CUML_B200_API int cuml_b200_handle_init_comm(cuml_b200_handle_t* h, const void* id_128_bytes,
                                              int rank, int n_ranks);
 
+/* Peer-memory communicator: the library's own collectives over NVLink / NVSwitch peer mappings (or CUDA IPC on one
+ * device) instead of NCCL -- the same raft::comms role (allreduce / allgather / bcast as the reference's multi-GPU
+ * fit uses them, cpp/include/cuml/cluster/kmeans.hpp:86-90), with the per-iteration all-reduce fused into the centroid
+ * update.  Every rank (one process per rank) creates its exchange window and gets a 64-byte CUDA IPC handle; the host
+ * side gathers the n_ranks handles in rank order by any means and every rank attaches.  slot_bytes = 0 picks the
+ * default (2 MiB per rank and parity).  After attach the handle's collectives no longer use NCCL.                  */
+CUML_B200_API int cuml_b200_peer_window_create(cuml_b200_handle_t* h, int n_ranks, size_t slot_bytes,
+                                               void* ipc_handle_out_64_bytes);
+CUML_B200_API int cuml_b200_peer_window_attach(cuml_b200_handle_t* h, const void* all_ipc_handles_n_ranks_x_64_bytes,
+                                               int rank, int n_ranks);
+
 /* ---- fit: single array.  X [n,d] row-major host or device (auto-detected like
  * ML::is_device_or_managed_type, reference cpp/src/ml_cuda_utils.h:21-33), sample_weight [n] or
  * NULL (same residency), centroids [k,d] DEVICE in/out.

@@ -1,4 +1,8 @@
-"""Multi-GPU (NCCL) test of the row-sharded fit: skipped unless >= 2 GPUs are visible."""
+"""Multi-rank tests of the row-sharded fit (reference contract: the multi-GPU model equals the single-GPU one,
+cpp/tests/mg/kmeans_test.cu:116-137,167-193; python/cuml/tests/dask/test_dask_kmeans.py:54-126).
+
+Topologies: "shared" = two ranks (two processes) on device 0 over the library's peer-memory communicator -- runs on a
+one-GPU box; "peer" / "nccl" = one rank per device over the peer-memory communicator / NCCL, needs >= 2 GPUs."""
 import os
 import socket
 
@@ -14,19 +18,38 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, q, init_kind):
+TOPOLOGIES = ["shared", "peer", "nccl"]
+
+
+def _need(topology, world):
+    import torch
+    have = torch.cuda.device_count()
+    if topology != "shared" and have < world:
+        pytest.skip(f"topology {topology!r} needs {world} GPUs, {have} visible")
+
+
+def _device_of(rank, topology):
+    return 0 if topology == "shared" else rank
+
+
+def _backend_of(topology):
+    return "peer" if topology == "shared" else topology
+
+
+def _worker(rank, world, port, q, init_kind, topology="nccl"):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
+    torch.cuda.set_device(_device_of(rank, topology))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from cuml_b200.cluster.kmeans_mg import KMeansMG, comms_from_torch_distributed, shard_bounds
     from oracle import blobs
     n, d, k = 40000, 32, 16
     X, centres, _ = blobs.make_blobs(n, d, k)
     lo, hi = shard_bounds(n, rank, world)
-    h = comms_from_torch_distributed()
+    h = comms_from_torch_distributed(backend=_backend_of(topology))
+    assert h.comm_kind == _backend_of(topology)
     init = blobs.parity_init(centres) if init_kind == "array" else init_kind
     km = KMeansMG(handle=h, n_clusters=k, init=init, max_iter=10 if init_kind == "array" else 50,
                   tol=0.0 if init_kind == "array" else 1e-6, random_state=5,
@@ -40,11 +63,10 @@ def _worker(rank, world, port, q, init_kind):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("topology", TOPOLOGIES)
 @pytest.mark.parametrize("init_kind", ["array", "k-means||", "random"])
-def test_two_rank_fit_matches_single_gpu(init_kind):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def test_two_rank_fit_matches_single_gpu(init_kind, topology):
+    _need(topology, 2)
     import torch.multiprocessing as mp
     from cuml_b200.cluster import KMeans
     from oracle import blobs, lloyd
@@ -52,13 +74,18 @@ def test_two_rank_fit_matches_single_gpu(init_kind):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, init_kind)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, init_kind, topology), daemon=True) for r in range(2)]
     for p in procs:
         p.start()
-    outs = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        outs = sorted([q.get(timeout=240) for _ in procs], key=lambda t: t[0])
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:          # a rank that died or hangs must not outlive the test
+            if p.is_alive():
+                p.kill()
     n, d, k = 40000, 32, 16
     X, centres, true = blobs.make_blobs(n, d, k)
     assert np.array_equal(outs[0][1], outs[1][1])  # identical centroids on every rank
@@ -78,12 +105,13 @@ def test_two_rank_fit_matches_single_gpu(init_kind):
 
 
 # ---- cuml_b200.distributed.KMeans: the orchestration that stands in for cuml.dask.cluster.KMeans -----------------
-def _dist_worker(rank, world, port, q):
+def _dist_worker(rank, world, port, q, topology="nccl"):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
-    torch.cuda.set_device(rank)
+    os.environ["CUML_B200_COMM"] = _backend_of(topology)
+    torch.cuda.set_device(_device_of(rank, topology))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     out = None
     try:
@@ -110,29 +138,27 @@ def _dist_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [1, 2])
-def test_distributed_estimator(world):
-    import torch
-    if torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
+@pytest.mark.parametrize("world,topology", [(1, "nccl"), (2, "shared"), (2, "peer"), (2, "nccl")])
+def test_distributed_estimator(world, topology):
+    _need(topology, world)
     import torch.multiprocessing as mp
     from cuml_b200.cluster.kmeans_mg import shard_bounds
     from oracle import blobs, lloyd
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, q), daemon=True) for r in range(world)]
+    procs = [ctx.Process(target=_dist_worker, args=(r, world, port, q, topology), daemon=True) for r in range(world)]
     for p in procs:
         p.start()
     try:
-        outs = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
+        outs = sorted([q.get(timeout=240) for _ in procs], key=lambda t: t[0])
         for p in procs:
             p.join(timeout=60)
             assert p.exitcode == 0
     finally:
         for p in procs:          # a rank that died or hangs must not outlive the test
             if p.is_alive():
-                p.terminate()
+                p.kill()
     outs = [o for _, o in outs]
     for o in outs:
         assert o is not None and "crash" not in o, o
