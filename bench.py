@@ -36,9 +36,12 @@ WORKLOADS = {
     "C4": (50_000_000, 256, 4096, "KMeans predict n=50M d=256 k=4096 fp32 (fused distance+argmin inference)"),
     "C5": (200_000_000, 16, 64, "KMeans fit n=200M d=16 k=64 fp32 row-sharded"),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant (fused) kernel at the full
-# workload, from the committed `ncu --set full` captures (profiles/r01_ncu_full_c3.txt, r01_ncu_full_c2.txt)
-TRAFFIC_NCU = {"C3": 25.602643e9 + 0.401213e9, "C2": 5.121371e9 + 0.042751e9}
+# roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant (fused) kernel at the
+# full single-GPU workload, taken from the committed `ncu --set full` captures (bytes cannot be counted inside a timed
+# run); roofline.traffic_source names the file.  Absent capture => null.
+TRAFFIC_NCU = {"C3": (25.602643e9 + 0.401213e9, "profiles/r01_ncu_full_c3.txt"),
+               "C2": (5.121371e9 + 0.042751e9, "profiles/r01_ncu_full_c2.txt"),
+               "C5": (12.800976e9 + 0.748216e9, "profiles/r02_ncu_full_c5_before.txt")}
 METRIC = "kmeans_lloyd_iters_per_sec"
 UNIT = "Lloyd iter/s"
 
@@ -125,92 +128,261 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def gen_blobs_device(torch, n_local, d, k, row_offset, seed=1234, chunk=1 << 22):
-    """isotropic blobs, centres ~ U(-10,10)^d, sigma 1, generated shard-locally on device"""
+GEN_CHUNK = 1 << 20   # rows per generator chunk (global row index // GEN_CHUNK keys the stream)
+
+
+def blob_centres(torch, d, k, seed=1234):
     g = torch.Generator(device="cuda").manual_seed(seed)
-    centres = torch.rand((k, d), device="cuda", generator=g) * 20.0 - 10.0   # same on every rank
-    X = torch.empty((n_local, d), dtype=torch.float32, device="cuda")
-    gs = torch.Generator(device="cuda").manual_seed(seed * 7919 + 1 + row_offset % (2**31))
-    for s in range(0, n_local, chunk):
-        e = min(n_local, s + chunk)
-        lab = torch.randint(0, k, (e - s,), device="cuda", generator=gs)
-        X[s:e] = centres[lab]
-        X[s:e] += torch.randn((e - s, d), device="cuda", generator=gs)
+    return torch.rand((k, d), device="cuda", generator=g) * 20.0 - 10.0
+
+
+def gen_blobs_device(torch, lo, hi, d, k, seed=1234):
+    """rows [lo, hi) of the synthetic matrix: isotropic blobs, centres ~ U(-10,10)^d, sigma 1.
+    The generator is keyed by the GLOBAL row index (chunk c = rows [c*2^20, (c+1)*2^20) has its own seeded stream), so
+    every sharding of the rows -- N = 1, 2, 4, 8 ranks -- sees the same matrix."""
+    centres = blob_centres(torch, d, k, seed)
+    X = torch.empty((hi - lo, d), dtype=torch.float32, device="cuda")
+    gs = torch.Generator(device="cuda")
+    for c in range(lo // GEN_CHUNK, (max(hi, lo + 1) - 1) // GEN_CHUNK + 1):
+        gs.manual_seed(seed * 7919 + 1 + c)
+        lab = torch.randint(0, k, (GEN_CHUNK,), device="cuda", generator=gs)
+        blk = centres[lab]
+        blk += torch.randn((GEN_CHUNK, d), device="cuda", generator=gs)
+        g0 = c * GEN_CHUNK
+        a, b = max(lo, g0), min(hi, g0 + GEN_CHUNK)
+        if b > a:
+            X[a - lo:b - lo] = blk[a - g0:b - g0]
+        del blk, lab
     return X, centres
 
 
-def cpu_reference_rate(n_full, d, k, budget_rows=None, iters=3):
-    """reference CPU execution path (sklearn KMeans, cuML's _cpu_class_path) on a bounded sample of
-    the workload; returns (full-workload iter/s, cores, sample description)."""
+def throughput_init(torch, n, d, k, seed=42):
+    """k distinct data rows among the first min(n, 2^20) global rows: every rank regenerates chunk 0 and picks the
+    same rows (a poor start: every implementation runs all the iterations; not for centroid parity)"""
+    head, _ = gen_blobs_device(torch, 0, min(n, GEN_CHUNK), d, k)
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return head[torch.randperm(head.shape[0], device="cuda", generator=g)[:k]].clone()
+
+
+def parity_init(torch, centres, seed=42, jitter=0.5):
+    """true centres + N(0, 0.5^2): one centroid per blob, unique stable fixed point (SURVEY 8c regime 1)"""
+    g = torch.Generator(device="cuda").manual_seed(seed + 1)
+    return (centres + jitter * torch.randn(centres.shape, device="cuda", generator=g)).contiguous()
+
+
+def all_host_threads():
+    """every host core for the CPU arm at every N: torchrun exports OMP_NUM_THREADS=1 to its workers, which made round
+    1's N > 1 reference lines single-threaded.  Must run before numpy / scikit-learn are imported."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[v] = str(n)
+    return n
+
+
+def host_blobs(n_rows, d, k):
+    """the first n_rows rows of the synthetic matrix on the HOST (numpy) + the throughput init.  On a GPU box they come
+    from the same device generator as our arm (identical blobs); without a GPU (build container) from numpy."""
     import numpy as np
-    from oracle import sklearn_ref
-    cores = sklearn_ref.n_threads()
-    # ~10-30 s of CPU work: n_s * k * d * 2 flop * iters at ~5 GFLOP/s/core
-    if budget_rows is None:
-        target_flop = 15.0 * 5e9 * max(cores, 1)
-        budget_rows = int(max(50_000, min(n_full, target_flop / (2.0 * k * d * (iters + 1)))))
+    try:
+        import torch
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        have_gpu = False
+    if have_gpu:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        X = np.empty((n_rows, d), dtype=np.float32)
+        step = 8 * GEN_CHUNK
+        for lo in range(0, n_rows, step):
+            hi = min(n_rows, lo + step)
+            Xd, _ = gen_blobs_device(torch, lo, hi, d, k)
+            X[lo:hi] = Xd.cpu().numpy()
+            del Xd
+        init = throughput_init(torch, n_rows, d, k).cpu().numpy()
+        torch.cuda.empty_cache()
+        return X, init, "device generator (same rows as the GPU arm)"
     rng = np.random.default_rng(1234)
     centres = rng.uniform(-10, 10, size=(k, d)).astype(np.float32)
-    lab = rng.integers(0, k, size=budget_rows)
-    X = centres[lab] + rng.standard_normal((budget_rows, d), dtype=np.float32)
-    init = X[rng.choice(budget_rows, size=k, replace=False)].copy()   # throughput init: runs all iters
-    # marginal cost per Lloyd iteration: t(1+iters) - t(1), so sklearn's fixed overhead (validation,
-    # mean-centring, final E-step) is not charged to the iterations
-    t1, n1 = sklearn_ref.time_fit(X, init, max_iter=1, reps=2)
-    t2, n2 = sklearn_ref.time_fit(X, init, max_iter=1 + iters, reps=2)
-    if n2 > n1 and t2 > t1:
-        rate_sample = (n2 - n1) / (t2 - t1)
+    X = np.empty((n_rows, d), dtype=np.float32)
+    for lo in range(0, n_rows, GEN_CHUNK):
+        hi = min(n_rows, lo + GEN_CHUNK)
+        X[lo:hi] = centres[rng.integers(0, k, size=hi - lo)] + rng.standard_normal((hi - lo, d), dtype=np.float32)
+    init = X[rng.choice(min(n_rows, GEN_CHUNK), size=k, replace=False)].copy()
+    return X, init, "numpy generator (no GPU visible)"
+
+
+def cpu_reference_rate(n_full, d, k, budget_s=90.0, warm_iters=1, timed_iters=2, max_timed=2):
+    """reference CPU execution path (sklearn KMeans, cuML's _cpu_class_path, kmeans.pyx:604) with all host cores.
+    Marginal Lloyd-iteration rate: t(fit, max_iter = warm + timed) - t(fit, max_iter = warm), so sklearn's fixed work
+    (validation, centring, the final labelling pass) is not charged to the iterations.  Runs on ALL n_full rows when a
+    short calibration says that fits `budget_s` and host memory; otherwise on the largest row prefix that does, scaled
+    by the row ratio and labelled an estimate.  Returns (full-workload iter/s, cores, sample text, rows, timed iters)."""
+    import numpy as np
+    from threadpoolctl import threadpool_limits
+    from oracle import sklearn_ref
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    with threadpool_limits(limits=cores):
+        cores_eff = min(cores, sklearn_ref.n_threads())
+        # calibration: seconds per row and iteration on a small prefix
+        n_cal = int(min(n_full, max(20 * k, 200_000)))
+        Xc, initc, _ = host_blobs(n_cal, d, k)
+        sklearn_ref.time_fit(Xc, initc, max_iter=1, reps=1)
+        t1, _ = sklearn_ref.time_fit(Xc, initc, max_iter=1, reps=1)
+        t3, _ = sklearn_ref.time_fit(Xc, initc, max_iter=3, reps=1)
+        per_row_iter = max((t3 - t1) / 2.0, 1e-9) / n_cal
+        per_row_fixed = max(t1 - (t3 - t1) / 2.0, 0.0) / n_cal
+        del Xc
+        # two fits: warm and warm + timed iterations, each with its fixed part
+        cost_per_row = per_row_iter * (2 * warm_iters + timed_iters) + 2 * per_row_fixed
+        rows = int(min(n_full, max(20 * k, budget_s / max(cost_per_row, 1e-12))))
+        try:
+            import psutil
+            avail = psutil.virtual_memory().available
+            rows = int(min(rows, max(20 * k, 0.4 * avail / (4.0 * d))))   # X + sklearn's working copies
+        except Exception:
+            pass
+        if rows >= 0.97 * n_full:
+            rows = n_full
+        # cheap workloads: time more iterations (up to the requested steps) so the difference of two fits is not noise
+        timed_iters = int(max(timed_iters, min(max_timed, 4.0 / max(per_row_iter * rows, 1e-9))))
+        X, init, how = host_blobs(rows, d, k)
+        big = X.nbytes > (2 << 30)      # no second host copy of a multi-GB matrix (sklearn then centres X in place)
+        ta, na = sklearn_ref.time_fit(X, init, max_iter=warm_iters, reps=1, copy_x=not big)
+        tb, nb = sklearn_ref.time_fit(X, init, max_iter=warm_iters + timed_iters, reps=1, copy_x=not big)
+    if nb > na and tb > ta:
+        rate_rows, timed = (nb - na) / (tb - ta), nb - na
     else:
-        rate_sample = n2 / t2
-    rate_full = rate_sample * (budget_rows / n_full)
-    sample = (f"sklearn {__import__('sklearn').__version__} KMeans(init=array, lloyd, tol=0) on "
-              f"{budget_rows} of {n_full} rows (same d={d}, k={k}); marginal rate (t[{1 + iters} iters]-t[1 iter]), "
-              f"best of 2 each; full-size rate = sample rate x rows ratio")
-    return rate_full, cores, sample
+        rate_rows, timed = nb / tb, nb
+    rate_full = rate_rows * (rows / n_full)
+    import sklearn
+    sample = (f"sklearn {sklearn.__version__} KMeans(init=array (k data rows), lloyd, tol=0, n_init=1), {cores_eff} threads, on "
+              f"{rows} of {n_full} rows ({how}); marginal rate (t[max_iter={warm_iters + timed_iters}] - "
+              f"t[max_iter={warm_iters}] = {tb - ta:.2f} s for {timed} iterations, one fit each)"
+              + ("" if rows == n_full else "; ESTIMATED: full-size rate = sample rate x rows ratio"))
+    return rate_full, cores_eff, sample, rows, timed
 
 
-def cpu_reference_predict_rate(n_full, d, k):
-    """reference CPU path's predict on a bounded row sample -> (full-workload passes/s, cores, sample)"""
+def cpu_reference_predict_rate(n_full, d, k, budget_s=30.0):
+    """reference CPU path's predict on a bounded row prefix -> (full-workload passes/s, cores, sample, rows)"""
     import numpy as np
+    from threadpoolctl import threadpool_limits
     from oracle import sklearn_ref
-    cores = sklearn_ref.n_threads()
-    target_flop = 5.0 * 5e9 * max(cores, 1)                    # ~5 s per repetition, 3 repetitions
-    rows = int(max(4 * k, min(n_full, target_flop / (2.0 * k * d))))
-    rng = np.random.default_rng(1234)
-    centres = rng.uniform(-10, 10, size=(k, d)).astype(np.float32)
-    X = centres[rng.integers(0, k, size=rows)] + rng.standard_normal((rows, d), dtype=np.float32)
-    t = sklearn_ref.time_predict(X, centres, reps=3)
-    sample = (f"sklearn {__import__('sklearn').__version__} KMeans.predict on {rows} of {n_full} rows (same d={d}, "
-              f"k={k}), best of 3; full-size rate = sample rate x rows ratio")
-    return (1.0 / t) * (rows / n_full), cores, sample
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    with threadpool_limits(limits=cores):
+        cores_eff = min(cores, sklearn_ref.n_threads())
+        n_cal = int(min(n_full, 50_000))
+        Xc, _, _ = host_blobs(n_cal, d, k)
+        centres = Xc[:k].copy()
+        tc = sklearn_ref.time_predict(Xc, centres, reps=2)
+        rows = int(min(n_full, max(4 * k, (budget_s / 3.0) / max(tc / n_cal, 1e-12))))
+        X, _, how = host_blobs(rows, d, k)
+        t = sklearn_ref.time_predict(X, centres, reps=2)
+    import sklearn
+    sample = (f"sklearn {sklearn.__version__} KMeans.predict, {cores_eff} threads, on {rows} of {n_full} rows ({how}), best of 2"
+              + ("" if rows == n_full else "; ESTIMATED: full-size rate = sample rate x rows ratio"))
+    return (1.0 / t) * (rows / n_full), cores_eff, sample, rows
+
+
+def workload_config(workload, n, d, k):
+    """the `config` object: identical in both arms (it names the workload, not how an arm runs it)"""
+    return {"workload": f"{workload}: {WORKLOADS[workload][3]}", "n": n, "d": d, "k": k, "l2": "inputs_exceed_l2",
+            "init": "array (k data rows)", "data_seed": 1234}
 
 
 def run_reference(args):
+    """`--impl reference`: the reference's own CPU implementation of the path (sklearn, kmeans.pyx:604) on this box's host
+    cores.  Under torchrun only rank 0 works; the line reports the steps it really ran."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n, d, k, desc = WORKLOADS[args.workload]
     if args.n:
         n = args.n
-    rates = []
-    for _ in range(max(1, min(args.steps, 3))):
-        if args.workload == "C4":
-            rate, cores, sample = cpu_reference_predict_rate(n, d, k)
-        else:
-            rate, cores, sample = cpu_reference_rate(n, d, k, iters=3)
-        rates.append(rate)
-    rate = max(rates)
     metric, unit = metric_unit(args.workload)
+    if args.workload == "C4":
+        rate, cores, sample, rows = cpu_reference_predict_rate(n, d, k, budget_s=args.cpu_budget or 60.0)
+        warm, timed = 0, 2
+    else:
+        rate, cores, sample, rows, timed = cpu_reference_rate(n, d, k, budget_s=args.cpu_budget or 110.0,
+                                                              max_timed=max(2, args.steps))
+        warm = 1
     line = {
-        "impl": "reference", "metric": metric, "value": rate, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": metric, "value": rate, "unit": unit, "n_gpus": args.gpus,
+        "steps": timed, "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "ms_per_step": 1e3 / rate, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {desc}", "n": n, "d": d, "k": k},
+        "config": workload_config(args.workload, n, d, k),
         "dists_per_sec": rate * n * k,
+        "estimated": rows != n,
         "cpu_baseline": {"value": rate, "unit": unit, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": rate, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def parity_fit(torch, dist, _lib, lib, h, args, n, d, k, lo, hi, world, rank, stream, barrier):
+    """The multi-GPU contract of the reference (cpp/tests/mg/kmeans_test.cu:116-137, test_dask_kmeans.py:54-126): the
+    model fitted on N row shards equals the one fitted on one GPU.  All ranks fit their shards of the SAME matrix from
+    the parity init (one centroid per blob: stable fixed point) through the C-ABI; at N > 1 rank 0 then regenerates the
+    whole matrix and repeats the fit alone on a communicator-less handle.  Bars: inertia 1e-5, centroids 1e-4."""
+    iters = max(1, min(args.steps, 10))
+    Xs, centres = gen_blobs_device(torch, lo, hi, d, k)
+    Cp = parity_init(torch, centres)
+
+    def fit(handle, Xt, rows):
+        p = _lib.default_params()
+        p.n_clusters, p.init, p.max_iter, p.tol, p.n_init = k, _lib.INIT_ARRAY, iters, 0.0, 1
+        Cf = Cp.clone()
+        inertia, n_iter = C.c_float(), C.c_int64()
+        xp = (C.c_void_p * 1)(Xt.data_ptr())
+        rows_a = (C.c_int64 * 1)(rows)
+        _lib.check(lib.cuml_b200_kmeans_fit_parts_f32(handle.ptr, C.byref(p), xp, rows_a, 1, d, None, Cf.data_ptr(),
+                                                      C.byref(inertia), C.byref(n_iter)))
+        torch.cuda.synchronize()
+        return Cf, float(inertia.value)
+
+    C_n, in_n = fit(h, Xs, hi - lo)
+    out = {"init": "true centres + N(0, 0.5^2)", "iters": iters, "inertia": in_n,
+           "centroid_abs_sum": float(C_n.double().abs().sum().item())}
+    del Xs
+    torch.cuda.empty_cache()
+    if world > 1:
+        if rank == 0:
+            h1 = _lib.Handle(stream=stream.cuda_stream)
+            Xf, _ = gen_blobs_device(torch, 0, n, d, k)
+            C_1, in_1 = fit(h1, Xf, n)
+            h1.close()
+            del Xf
+            torch.cuda.empty_cache()
+            cerr = float(((C_n - C_1).abs().max() / C_1.abs().max()).item())
+            irel = abs(in_n - in_1) / abs(in_1)
+            out["vs_n1"] = {"inertia_n1": in_1, "inertia_rel": irel, "centroid_err_max_over_max": cerr,
+                            "ok": bool(irel <= 1e-5 and cerr <= 1e-4),
+                            "how": "rank 0 refits the whole matrix alone after the timed regions"}
+        barrier()
+    return out
+
+
+def bind_to_gpu_numa_node(torch, local_rank):
+    """pin this rank's host threads (and therefore the pages of the pinned buffers it allocates next) to the CPUs NVML
+    reports as local to its GPU.  Round 1's 8-rank end-to-end runs copied at 21 GB/s per rank against 53 GB/s alone: all
+    eight pinned buffers had been allocated from wherever the launcher happened to run."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(local_rank)
+        bus = "%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        hdl = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} CPUs local to GPU {bus} ({cpus[0]}-{cpus[-1]})"
+    except Exception as e:   # NVML absent or affinity not permitted: placement stays as launched
+        return f"not bound ({type(e).__name__})"
+    return "not bound"
 
 
 def run_ours(args):
@@ -224,6 +396,7 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else "single rank: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, d, k, desc = WORKLOADS[args.workload]
@@ -236,18 +409,14 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     assert stream.cuda_stream != 0
     if world > 1:
-        h = comms_from_torch_distributed(stream=stream.cuda_stream)
+        h = comms_from_torch_distributed(stream=stream.cuda_stream, backend=args.comm)
     else:
         h = _lib.Handle(stream=stream.cuda_stream)
 
     lo, hi = shard_bounds(n, rank, world)
     n_local = hi - lo
-    X, centres = gen_blobs_device(torch, n_local, d, k, lo)
-    # throughput init = k data rows of rank 0's shard, identical on all ranks
-    g = torch.Generator(device="cuda").manual_seed(42)
-    C0 = X[torch.randperm(min(n_local, 1 << 20), device="cuda", generator=g)[:k]].clone()
-    if world > 1:
-        dist.broadcast(C0, src=0)
+    X, centres = gen_blobs_device(torch, lo, hi, d, k)
+    C0 = throughput_init(torch, n, d, k)     # identical on all ranks by construction
     Cd = C0.clone()
     labels = torch.zeros(n_local, dtype=torch.int32, device="cuda")
     engine = {"auto": 0, "simt": 1, "tc": 2}[args.engine]
@@ -413,6 +582,13 @@ def run_ours(args):
                "inertia": float(inertia.value)}
         del Xh
 
+    parity = None
+    if not predict_only and not args.no_parity:
+        if "X" in dir():
+            del X
+        torch.cuda.empty_cache()
+        parity = parity_fit(torch, dist, _lib, lib, h, args, n, d, k, lo, hi, world, rank, stream, barrier)
+
     if rank == 0:
         peaks = measured_peaks()
         fused_ms = f_ms.value / max(1, f_n.value)
@@ -440,7 +616,9 @@ def run_ours(args):
                         3: "tcgen05 CTA-pair tf32 + 2 bf16 correction terms", 4: "tcgen05 A-in-TMEM 3xTF32",
                         5: "tcgen05 1-CTA tf32 + 2 bf16 correction terms"}[variant]
         roof.update({
-            "traffic": TRAFFIC_NCU.get(args.workload) if world == 1 and not args.n else None,
+            "traffic": TRAFFIC_NCU[args.workload][0] if (args.workload in TRAFFIC_NCU and world == 1 and not args.n) else None,
+            "traffic_source": (TRAFFIC_NCU[args.workload][1] + " (ncu --set full, one launch; not measured in this run)")
+                              if (args.workload in TRAFFIC_NCU and world == 1 and not args.n) else None,
             "kernel": f"fused_l2_argmin ({variant_name}: distance + argmin)", "kernel_ms": fused_ms,
             "algorithmic_flops_per_launch": flop, "algorithmic_bytes_per_launch": fused_bytes,
             "algorithmic_tflops": tf_achieved,
@@ -461,10 +639,11 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32 (split-precision tensor-core contraction: tf32 + bf16 corrections or 3xTF32; fp32/fp64 reductions)",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {desc}", "n": n, "d": d, "k": k, "rows_per_gpu": n_local,
-                       "parallelism": (f"row-sharded x{world}, rank-local predict (no collective)" if predict_only else
-                                       f"row-sharded x{world}, 1 allreduce of (k*d+k+1) f64 per iteration"),
-                       "l2": "inputs_exceed_l2", "engine": args.engine, "init": "array (k data rows)"},
+            "config": workload_config(args.workload, n, d, k),
+            "run": {"rows_per_gpu": n_local, "engine": args.engine, "communicator": getattr(h, "comm_kind", None),
+                    "host_threads": numa, "e2e_host_memory": "pinned (cudaHostAlloc through torch)",
+                    "parallelism": (f"row-sharded x{world}, rank-local predict (no collective)" if predict_only else
+                                    f"row-sharded x{world}, 1 all-reduce of (k*d+k+1) f64 per iteration")},
             "dists_per_sec": value * n * k,
             "gpu_launches": launches,
             "clocks": clocks,
@@ -473,14 +652,22 @@ def run_ours(args):
         }
         if init_info is not None:
             line["init"] = init_info
+        if parity is not None:
+            line["parity_fit"] = parity
         if world == 1 and not args.no_cpu:
-            rate, cores, sample = (cpu_reference_predict_rate if predict_only else cpu_reference_rate)(n, d, k)
+            if predict_only:
+                rate, cores, sample, _ = cpu_reference_predict_rate(n, d, k, budget_s=args.cpu_budget or 20.0)
+            else:
+                rate, cores, sample, _, _ = cpu_reference_rate(n, d, k, budget_s=args.cpu_budget or 25.0)
             line["cpu_baseline"] = {"value": rate, "unit": unit, "cores": cores, "kind": "reference", "sample": sample}
         print(json.dumps(line), flush=True)
     h.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and parity and not parity.get("vs_n1", {}).get("ok", True):
+        print("bench.py: the N-rank fit does not match the 1-rank fit: %r" % (parity["vs_n1"],), file=sys.stderr)
+        sys.exit(3)
 
 
 def main():
@@ -494,10 +681,14 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-rank vs 1-rank parity fit")
+    ap.add_argument("--cpu-budget", type=float, default=0.0, help="seconds of CPU work for the sklearn arm (0 = default)")
+    ap.add_argument("--comm", default=None, choices=["nccl", "peer"], help="communicator of the N > 1 runs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
+        all_host_threads()
         run_reference(args)
     else:
         run_ours(args)

@@ -46,6 +46,7 @@ EXPORTED_SYMBOLS = [
     "cuml_b200_peer_window_create", "cuml_b200_peer_window_attach",
     "cuml_b200_kmeans_fit_f32_i32", "cuml_b200_kmeans_fit_f64_i32", "cuml_b200_kmeans_fit_f32_i64",
     "cuml_b200_kmeans_fit_f64_i64", "cuml_b200_kmeans_fit_parts_f32", "cuml_b200_kmeans_fit_parts_f64",
+    "cuml_b200_kmeans_fit_parts_labels_f32", "cuml_b200_kmeans_fit_parts_labels_f64",
     "cuml_b200_kmeans_predict_f32_i32", "cuml_b200_kmeans_predict_f64_i32", "cuml_b200_kmeans_predict_f32_i64",
     "cuml_b200_kmeans_predict_f64_i64", "cuml_b200_kmeans_transform_f32_i32", "cuml_b200_kmeans_transform_f64_i32",
     "cuml_b200_kmeans_transform_f32_i64", "cuml_b200_kmeans_transform_f64_i64",
@@ -96,6 +97,8 @@ def load(build_if_missing=True):
                                                                            C.c_int, vp, vp]
             getattr(lib, f"cuml_b200_kmeans_transform_{t}_{ix}").argtypes = [vp, P(KMeansParams), vp, vp, it, it, vp]
         getattr(lib, f"cuml_b200_kmeans_fit_parts_{t}").argtypes = [vp, P(KMeansParams), vp, vp, i64, i64, vp, vp, vp, vp]
+        getattr(lib, f"cuml_b200_kmeans_fit_parts_labels_{t}").argtypes = [vp, P(KMeansParams), vp, vp, i64, i64, vp, vp,
+                                                                           vp, vp, vp]
     lib.cuml_b200_kmeans_lloyd_step_f32.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp, vp, vp, C.c_int]
     lib.cuml_b200_kmeans_assign_f32.argtypes = [vp, vp, i64, i64, i32, vp, vp, C.c_int]
     lib.cuml_b200_kmeans_debug_dots_f32.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp, P(i64)]

@@ -145,7 +145,12 @@ class KMeans:
         p.n_clusters = int(self.n_clusters)
         p.max_iter = int(self.max_iter)
         p.tol = float(self.tol)
-        p.verbosity = 4 if self.verbose else 3
+        # reference internals/logger.pyx:30-37 (_verbose_to_level): True -> debug, False -> info, int v -> level 6 - v
+        # in rapids_logger's numbering (trace 0, debug 1, info 2, warn 3, error 4, critical 5, off 6)
+        if isinstance(self.verbose, bool):
+            p.verbosity = 1 if self.verbose else 2
+        else:
+            p.verbosity = min(max(6 - int(self.verbose), 0), 6)
         p.metric = _lib.L2_EXPANDED
         p.batch_samples = int(self.max_samples_per_batch)
         p.init_size = int(self.init_size)
@@ -252,8 +257,10 @@ class KMeans:
         centers = self._prepare_centers(Xd)
         handle = self.handle if self._multi_gpu else get_handle()
         params = self._c_params()
-        n_iter = self._c_fit(handle, params, Xd, wd, centers)
-        labels, inertia = self._c_predict(handle, params, Xd, wd, centers, normalize_weights=True)
+        # one library call: fit + the labels / inertia of its own final assignment pass (the reference runs a second,
+        # redundant E-step here, kmeans.pyx:803-812)
+        n_iter, labels, inertia = self._c_fit_labels(handle, params, Xd.data_ptr(), n_rows, n_cols,
+                                                     wd.data_ptr() if wd is not None else None, centers)
         handle.sync()
         self._centers = centers
         self._labels = labels
@@ -290,27 +297,38 @@ class KMeans:
         handle = get_handle()
         params = self._c_params()
         f32 = Xh.dtype == np.float32
-        fn = getattr(lib, "cuml_b200_kmeans_fit_%s_i64" % ("f32" if f32 else "f64"))
-        inertia = (C.c_float if f32 else C.c_double)()
-        n_iter = C.c_int64()
         torch.cuda.synchronize()
-        _lib.check(fn(handle.ptr, C.byref(params), Xh.ctypes.data, n_rows, n_cols,
-                      wh.ctypes.data if wh is not None else None, centers.data_ptr(), C.byref(inertia),
-                      C.byref(n_iter)))
-        # labels: predict batch by batch (they do not depend on the weights)
-        buf = int(self.device_buffer_samples)
-        labels = torch.empty(n_rows, dtype=torch.int32, device=centers.device)
-        for s0 in range(0, n_rows, buf):
-            xb = torch.from_numpy(Xh[s0:s0 + buf]).to(centers.device)
-            lb, _ = self._c_predict(handle, params, xb, None, centers, normalize_weights=True)
-            labels[s0:s0 + xb.shape[0]] = lb.to(torch.int32)
+        # the library streams the host rows itself and hands back the labels of its final pass
+        n_iter, labels, inertia = self._c_fit_labels(handle, params, Xh.ctypes.data, n_rows, n_cols,
+                                                     wh.ctypes.data if wh is not None else None, centers)
         handle.sync()
         self._centers = centers
         self._labels = labels
         self._in_kind = "numpy"
-        self.inertia_ = float(inertia.value)
-        self.n_iter_ = int(n_iter.value)
+        self.inertia_ = inertia
+        self.n_iter_ = n_iter
         return self
+
+    def _c_fit_labels(self, handle, params, x_ptr, n, d, w_ptr, centers):
+        """cuml_b200_kmeans_fit_parts_labels_*: (n_iter, labels [n] on the centres' device, inertia).  x_ptr / w_ptr may
+        be host or device addresses (the library probes the residency like ML::is_device_or_managed_type)."""
+        torch = _torch()
+        lib = _lib.load()
+        f32 = centers.dtype == torch.float32
+        k = centers.shape[0]
+        labels = torch.zeros(n, dtype=torch.int32, device=centers.device)
+        fn = lib.cuml_b200_kmeans_fit_parts_labels_f32 if f32 else lib.cuml_b200_kmeans_fit_parts_labels_f64
+        inertia = (C.c_float if f32 else C.c_double)()
+        n_iter = C.c_int64()
+        xp = (C.c_void_p * 1)(x_ptr)
+        rows = (C.c_int64 * 1)(n)
+        wp = (C.c_void_p * 1)(w_ptr) if w_ptr is not None else None
+        lp = (C.c_void_p * 1)(labels.data_ptr())
+        _lib.check(fn(handle.ptr, C.byref(params), xp, rows, 1, d, wp, centers.data_ptr(), C.byref(inertia),
+                      C.byref(n_iter), lp))
+        if not (_indices_i32(n, d) and _indices_i32(k, d)):     # reference kmeans.pyx:277-281: int64 labels then
+            labels = labels.to(torch.int64)
+        return int(n_iter.value), labels, float(inertia.value)
 
     def _c_fit(self, handle, params, X, w, centers):
         lib = _lib.load()
@@ -407,7 +425,10 @@ class KMeans:
         self._check_is_fitted()
         xin = _as_device_matrix(X, dtype=self._centers.dtype, device=self._centers.device)
         n, d = xin.t.shape
-        k = int(self.n_clusters)
+        if d != self._centers.shape[1]:
+            raise ValueError(f"X has {d} features, but KMeans is expecting "
+                             f"{self._centers.shape[1]} features as input.")
+        k = int(self._centers.shape[0])
         if not _indices_i32(n, k):
             raise NotImplementedError("KMeans.transform does not currently support output shapes "
                                       f"that require int64 indexing. Got output shape ({n}, {k}).")
@@ -418,6 +439,7 @@ class KMeans:
         fn = getattr(lib, "cuml_b200_kmeans_transform_%s_%s" % ("f32" if f32 else "f64", "i32" if i32 else "i64"))
         handle = get_handle()
         params = self._c_params()
+        params.n_clusters = k
         _lib.check(fn(handle.ptr, C.byref(params), self._centers.data_ptr(), xin.t.data_ptr(), n, d, out.data_ptr()))
         handle.sync()
         return self._out(out, xin.kind)

@@ -326,14 +326,20 @@ __global__ void reduce_partials_kernel(const T* __restrict__ partial_S, const T*
   }
 }
 
+// C_new = S / W (W > 0) else C_old; shift2 = sum (C_new - C_old)^2.  Multi-block (round 1's single 1024-thread block
+// took 20.8 us at k*d = 16 384, a fifth of the non-kernel tail of an 8-GPU iteration): every block writes its partial of
+// the squared shift, the last block to finish adds the partials in block order -- deterministic, no float atomics.
 template <typename T>
-__global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict__ packed, T* __restrict__ C, int k,
-                                                        int d, double* __restrict__ shift2_out)
+__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ packed, T* __restrict__ C, int k,
+                                                       int d, double* __restrict__ shift2_out,
+                                                       double* __restrict__ block_shift, unsigned* __restrict__ done)
 {
-  __shared__ double red[32];
-  const int64_t kd = static_cast<int64_t>(k) * d;
-  double acc       = 0.0;
-  for (int64_t e = threadIdx.x; e < kd; e += blockDim.x) {
+  __shared__ double red[8];
+  __shared__ bool last;
+  const int64_t kd   = static_cast<int64_t>(k) * d;
+  const int64_t step = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  double acc         = 0.0;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < kd; e += step) {
     int j      = static_cast<int>(e / d);
     double wj  = packed[kd + j];
     T old      = C[e];
@@ -349,8 +355,18 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict
   __syncthreads();
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int i = 0; i < blockDim.x / 32; ++i) s += red[i];
+    for (int i = 0; i < static_cast<int>(blockDim.x) / 32; ++i) s += red[i];
+    block_shift[blockIdx.x] = s;
+    __threadfence();
+    last = atomicAdd(done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double s = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) s += __ldcg(block_shift + b);
     if (shift2_out) *shift2_out = s;
+    *done = 0;   // the next finalize on this stream starts after this kernel
   }
 }
 
@@ -520,7 +536,10 @@ void compute_inertia(Handle& h, const T* X, int64_t n, int d, const int32_t* lab
 template <typename T>
 void finalize_centroids(Handle& h, const double* packed, T* C, int k, int d, double* shift2_out)
 {
-  finalize_kernel<T><<<1, 1024, 0, h.stream>>>(packed, C, k, d, shift2_out);
+  const int64_t kd      = static_cast<int64_t>(k) * d;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(Handle::FIN_BLOCKS, std::max<int64_t>(1, kd / 512)));
+  finalize_kernel<T><<<blocks, 256, 0, h.stream>>>(packed, C, k, d, shift2_out, h.fin_scratch,
+                                                   reinterpret_cast<unsigned*>(h.fin_scratch + Handle::FIN_BLOCKS));
   CB2_CHECK_LAUNCH();
 }
 

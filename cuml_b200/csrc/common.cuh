@@ -1,6 +1,7 @@
 // cuml_b200 internal: error handling, handle, device buffers, launch accounting.
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdint>
 #include <cstdlib>
@@ -91,11 +92,13 @@ struct Handle {
   std::vector<EventPair> event_pool;
   // pinned scalar mailbox for per-iteration convergence read-back
   double* pinned = nullptr;
+  // device scratch of the multi-block centroid update: FIN_BLOCKS shift partials + the block arrival counter
+  static constexpr int FIN_BLOCKS = 64;
+  double* fin_scratch = nullptr;
   // solver cached by the lloyd_step measurement hook (freed with the handle)
   std::shared_ptr<void> step_cache;
-  // second stream + hand-off events of the opt-in E-step / M-step overlap (CUML_B200_OVERLAP), created on first use
+  // copy stream of the double-buffered host -> device pipelines (out-of-core fit, chunked staging), created on first use
   cudaStream_t aux_stream = nullptr;
-  cudaEvent_t ev_fwd = nullptr, ev_back = nullptr;
 
   EventPair begin_event();
   void end_event(EventPair ev, bool fused);
@@ -181,6 +184,15 @@ inline bool is_device_pointer(const void* ptr)
   }
   return att.type == cudaMemoryTypeDevice || att.type == cudaMemoryTypeManaged;
 }
+
+// NVTX range per phase of a fit / predict / transform (the reference wraps every estimator method in an NVTX range,
+// python/cuml/cuml/internals/base.py:126-128,267-285).  Header-only NVTX3: free unless a profiler is attached.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&)            = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -176,6 +176,8 @@ Handle* make_handle(void* stream, void* comm, int rank, int n_ranks)
     cudaGetLastError();
   }
   CB2_CUDA(cudaMallocHost(reinterpret_cast<void**>(&h->pinned), 64 * sizeof(double)));
+  CB2_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->fin_scratch), (Handle::FIN_BLOCKS + 2) * sizeof(double)));
+  CB2_CUDA(cudaMemset(h->fin_scratch, 0, (Handle::FIN_BLOCKS + 2) * sizeof(double)));
   return h.release();
 }
 
@@ -188,8 +190,6 @@ void free_handle(Handle* h)
     cudaStreamSynchronize(h->aux_stream);
     cudaStreamDestroy(h->aux_stream);
   }
-  if (h->ev_fwd) cudaEventDestroy(h->ev_fwd);
-  if (h->ev_back) cudaEventDestroy(h->ev_back);
   nccl::destroy(*h);
   peer::destroy(*h);
   for (auto& v : {&h->fused_events, &h->update_events, &h->event_pool})
@@ -198,6 +198,7 @@ void free_handle(Handle* h)
       cudaEventDestroy(e.b);
     }
   if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->fin_scratch) cudaFree(h->fin_scratch);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
 }

@@ -30,26 +30,6 @@ inline int engine_from_env(int engine)
   return ENGINE_AUTO;
 }
 
-// Opt-in experiment (CUML_B200_OVERLAP="<chunks>:<m_sms>", e.g. "8:24"; not yet measured): the rows are cut into
-// chunks; the E-step of chunk c+1 runs on sm_count - m_sms SMs while the M-step of chunk c runs on a second stream
-// on the remaining m_sms SMs (the E-step is tensor-bound and leaves HBM idle, the M-step is HBM-bound).  Results are
-// those of the plain step up to the fp32 summation order of the per-CTA tables.
-struct OverlapCfg {
-  int chunks = 0, m_sms = 0;
-};
-inline OverlapCfg overlap_from_env()
-{
-  OverlapCfg c;
-  const char* e = std::getenv("CUML_B200_OVERLAP");
-  if (!e) return c;
-  int a = 0, b = 0;
-  if (std::sscanf(e, "%d:%d", &a, &b) == 2 && a >= 2 && a <= 64 && b >= 2) {
-    c.chunks = a;
-    c.m_sms  = b & ~1;
-  }
-  return c;
-}
-
 // Cross-rank sum of the packed M-step result followed by the centroid update.  With the peer-memory communicator the
 // two are one exchange: push kernel + a finalize kernel that waits for the peers' slots (peer_comm.cu); otherwise
 // ncclAllReduce + finalize.
@@ -184,67 +164,17 @@ class LloydSolver {
   }
 
   // out-of-core use: the single partition is a device staging buffer whose fill level changes per batch
-  // (n must not exceed the row count the solver was built with)
-  void set_rows(int64_t n)
+  // and which alternates between two buffers (n must not exceed the row count the solver was built with)
+  void set_part(const T* X, const T* w, int64_t n)
   {
-    CB2_EXPECTS(parts_.size() == 1 && n >= 0 && n <= capacity_, "set_rows: single-partition solver, n within capacity");
-    parts_[0].n = n;
-    n_local_    = n;
-  }
-
-  // E-step of chunk c+1 (main stream, sm_count - m_sms SMs) overlapped with the M-step of chunk c (second stream,
-  // m_sms SMs); see OverlapCfg.  Only for the fp32 tensor-core + TMA-update path over one partition.
-  bool step_overlapped(T* C)
-  {
-    if constexpr (!std::is_same<T, float>::value) {
-      return false;
-    } else {
-      static const OverlapCfg cfg = overlap_from_env();
-      if (cfg.chunks == 0 || !use_tc_ || !use_tma_update_ || parts_.size() != 1) return false;
-      if (cfg.m_sms > h_.sm_count - 2 || parts_[0].n < static_cast<int64_t>(cfg.chunks) * 65536) return false;
-      if (!h_.aux_stream) {
-        CB2_CUDA(cudaStreamCreateWithFlags(&h_.aux_stream, cudaStreamNonBlocking));
-        CB2_CUDA(cudaEventCreateWithFlags(&h_.ev_fwd, cudaEventDisableTiming));
-        CB2_CUDA(cudaEventCreateWithFlags(&h_.ev_back, cudaEventDisableTiming));
-      }
-      const Part<T>& pt = parts_[0];
-      prepare(C);
-      const uint8_t* cls_map = nullptr;
-      if (have_weights_) cls_map = tma_update_balance(h_, packed_.get() + static_cast<size_t>(k_) * d_, d_, k_, cls_map_);
-      // views of the handle: same device state, fewer SMs each, the M-step on the second stream
-      Handle e_view = h_, m_view = h_;
-      e_view.sm_count = (h_.sm_count - cfg.m_sms) & ~1;
-      e_view.timing   = false;
-      m_view.sm_count = cfg.m_sms;
-      m_view.stream   = h_.aux_stream;
-      m_view.timing   = false;
-      // the second stream must not start before what the main stream has queued so far (operand buffers, class map,
-      // the previous finalize reading packed)
-      CB2_CUDA(cudaEventRecord(h_.ev_fwd, h_.stream));
-      CB2_CUDA(cudaStreamWaitEvent(h_.aux_stream, h_.ev_fwd, 0));
-      const int64_t per = ((ceil_div(pt.n, cfg.chunks) + 255) / 256) * 256;   // keeps X and label chunks 16-byte aligned
-      int c = 0;
-      for (int64_t off = 0; off < pt.n; off += per, ++c) {
-        const int64_t nc = std::min<int64_t>(per, pt.n - off);
-        tc_assign(e_view, pt.X + off * d_, nc, d_, k_, tc_, labels(0) + off);
-        CB2_CUDA(cudaEventRecord(h_.ev_fwd, h_.stream));
-        CB2_CUDA(cudaStreamWaitEvent(h_.aux_stream, h_.ev_fwd, 0));
-        tma_update_accumulate(m_view, pt.X + off * d_, nc, d_, labels(0) + off, pt.w ? pt.w + off : nullptr, k_, tma_S_,
-                              tma_W_, packed_.get(), c != 0, cls_map);
-      }
-      have_weights_ = true;
-      CB2_CUDA(cudaEventRecord(h_.ev_back, h_.aux_stream));
-      CB2_CUDA(cudaStreamWaitEvent(h_.stream, h_.ev_back, 0));
-      CB2_CUDA(cudaMemsetAsync(packed_.get() + packed_count() - 1, 0, sizeof(double), h_.stream));
-      exchange_and_finalize<T>(h_, packed_.get(), packed_count(), C, k_, d_);
-      return true;
-    }
+    CB2_EXPECTS(parts_.size() == 1 && n >= 0 && n <= capacity_, "set_part: single-partition solver, n within capacity");
+    parts_[0] = Part<T>{X, n, w};
+    n_local_  = n;
   }
 
   // One full Lloyd iteration, centroids updated in place; squared shift left at packed[count]
   void step(T* C, bool with_inertia = false)
   {
-    if (!with_inertia && step_overlapped(C)) return;
     assign(C);
     accumulate(C, with_inertia);
     exchange_and_finalize<T>(h_, packed_.get(), packed_count(), C, k_, d_);

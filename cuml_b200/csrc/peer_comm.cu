@@ -202,8 +202,6 @@ struct PeerComm {
   bool attached = false;
   uint64_t epoch = 0;
   DevBuf<char> stage;          // 16-byte padded copy of odd-sized contributions
-  double* block_shift = nullptr;
-  unsigned* done = nullptr;
 };
 
 namespace peer {
@@ -223,7 +221,7 @@ void window_create(Handle& h, size_t slot_bytes, int n_ranks, void* ipc_handle_o
   slot_bytes = (slot_bytes + 255) & ~size_t(255);
   CB2_CUDA(cudaSetDevice(h.device));
   auto p   = std::make_unique<PeerComm>();
-  p->bytes = window_bytes(n_ranks, slot_bytes) + 8 * 1024 + 64;   // + shift partials and the done counter
+  p->bytes = window_bytes(n_ranks, slot_bytes);
   CB2_CUDA(cudaMalloc(&p->window, p->bytes));
   CB2_CUDA(cudaMemset(p->window, 0, p->bytes));
   CB2_CUDA(cudaDeviceSynchronize());   // zeroed before any peer can learn the handle
@@ -253,9 +251,6 @@ void window_attach(Handle& h, const void* all_handles, int rank, int n_ranks)
     CB2_CUDA(cudaIpcOpenMemHandle(&q, ipc, cudaIpcMemLazyEnablePeerAccess));
     p.view.win[r] = static_cast<char*>(q);
   }
-  char* tail    = static_cast<char*>(p.window) + window_bytes(n_ranks, p.view.slot_bytes);
-  p.block_shift = reinterpret_cast<double*>(tail);
-  p.done        = reinterpret_cast<unsigned*>(tail + 8 * 1024);
   p.attached    = true;
   h.use_peer    = true;
   h.rank        = rank;
@@ -360,9 +355,10 @@ bool allreduce_finalize(Handle& h, double* packed, size_t count, T* C, int k, in
   int parity;
   uint64_t epoch;
   push(h, p, packed, count * sizeof(double), parity, epoch);
-  const unsigned blocks = static_cast<unsigned>(std::min<size_t>(64, std::max<size_t>(1, count / 512)));
-  peer_finalize_kernel<T><<<blocks, 256, 0, h.stream>>>(p.view, packed, C, k, d, shift2_out, p.block_shift, p.done, parity,
-                                                        epoch);
+  const unsigned blocks = static_cast<unsigned>(std::min<size_t>(Handle::FIN_BLOCKS, std::max<size_t>(1, count / 512)));
+  peer_finalize_kernel<T><<<blocks, 256, 0, h.stream>>>(p.view, packed, C, k, d, shift2_out, h.fin_scratch,
+                                                        reinterpret_cast<unsigned*>(h.fin_scratch + Handle::FIN_BLOCKS),
+                                                        parity, epoch);
   CB2_CHECK_LAUNCH();
   return true;
 }

@@ -276,6 +276,8 @@ template <typename T>
 static void kmeans_pp_array(Handle& h, const T* X, const T* w, int64_t n, int d, int k, uint64_t seed, T* C)
 {
   CB2_EXPECTS(n >= k, "k-means++ needs at least n_clusters rows");
+  // the sampling kernel packs (float key, 32-bit row index) into one 64-bit atomicMin word
+  CB2_EXPECTS(n < (int64_t(1) << 32), "sequential k-means++ supports fewer than 2^32 rows per array; use init='k-means||'");
   const int trials = 2 + static_cast<int>(std::floor(std::log(static_cast<double>(k))));
   DevBuf<T> mind(n, h.stream);
   fill_kernel<T><<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, h.stream>>>(mind.get(), n, T(1));
@@ -459,7 +461,7 @@ void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params,
   // 2. over-sampling rounds
   int rounds = 0;
   if (phi > 0.0) rounds = std::max(0, std::min(8, static_cast<int>(std::ceil(std::log(phi)))));
-  const int sel_cap = static_cast<int>(std::min<double>(4.0 * ell + 4096.0, 1 << 24));
+  int sel_cap = static_cast<int>(std::min<double>(4.0 * ell + 4096.0, 1 << 24));
   DevBuf<int64_t> sel(sel_cap, h.stream);
   DevBuf<int> sel_count(1, h.stream);
   for (int round = 0; round < rounds && phi > 0.0; ++round) {
@@ -469,15 +471,21 @@ void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params,
     for (size_t p = 0; p < ctx.parts.size(); ++p) {
       auto& pt = ctx.parts[p];
       if (pt.n > 0) {
-        CB2_CUDA(cudaMemsetAsync(sel_count.get(), 0, sizeof(int), h.stream));
-        bernoulli_select_kernel<T><<<static_cast<unsigned>(ceil_div(pt.n, 256)), 256, 0, h.stream>>>(
-          mind[p].get(), pt.w, pt.n, ctx.row_offset + base, ctx.seed, 0x1000ull + round, ell / phi, sel.get(),
-          sel_count.get(), sel_cap);
-        CB2_CHECK_LAUNCH();
         int cnt = 0;
-        CB2_CUDA(cudaMemcpyAsync(&cnt, sel_count.get(), sizeof(int), cudaMemcpyDeviceToHost, h.stream));
-        CB2_CUDA(cudaStreamSynchronize(h.stream));
-        cnt = std::min(cnt, sel_cap);
+        for (;;) {
+          CB2_CUDA(cudaMemsetAsync(sel_count.get(), 0, sizeof(int), h.stream));
+          bernoulli_select_kernel<T><<<static_cast<unsigned>(ceil_div(pt.n, 256)), 256, 0, h.stream>>>(
+            mind[p].get(), pt.w, pt.n, ctx.row_offset + base, ctx.seed, 0x1000ull + round, ell / phi, sel.get(),
+            sel_count.get(), sel_cap);
+          CB2_CHECK_LAUNCH();
+          CB2_CUDA(cudaMemcpyAsync(&cnt, sel_count.get(), sizeof(int), cudaMemcpyDeviceToHost, h.stream));
+          CB2_CUDA(cudaStreamSynchronize(h.stream));
+          if (cnt <= sel_cap) break;
+          // more picks than slots: which ones were dropped depends on the atomic order, so grow the list and redo the
+          // draw (same Philox counters => same picks) instead of keeping an arbitrary subset
+          sel_cap = cnt;
+          sel.alloc(static_cast<size_t>(sel_cap), h.stream);
+        }
         std::vector<int64_t> part_rows(cnt);
         if (cnt) {
           CB2_CUDA(cudaMemcpyAsync(part_rows.data(), sel.get(), sizeof(int64_t) * cnt, cudaMemcpyDeviceToHost, h.stream));
@@ -537,11 +545,24 @@ void init_scalable(SeedContext<T>& ctx, const cuml_b200_kmeans_params_t& params,
   // 3. reduce the candidates to k
   if (m < k) {
     // too few candidates (tiny / degenerate data): top up with random rows
+    // (k distinct rows are drawn; those that coincide with a candidate already chosen are skipped while others remain)
     DevBuf<T> extra(static_cast<size_t>(k) * d, h.stream);
     init_random<T>(ctx, k, extra.get());
+    std::vector<T> hc(static_cast<size_t>(m) * d), he(static_cast<size_t>(k) * d);
+    if (m) CB2_CUDA(cudaMemcpyAsync(hc.data(), cand.get(), sizeof(T) * m * d, cudaMemcpyDeviceToHost, h.stream));
+    CB2_CUDA(cudaMemcpyAsync(he.data(), extra.get(), sizeof(T) * k * d, cudaMemcpyDeviceToHost, h.stream));
+    CB2_CUDA(cudaStreamSynchronize(h.stream));
+    std::vector<int> fresh, dup;
+    for (int e = 0; e < k; ++e) {
+      bool same = false;
+      for (int c = 0; c < m && !same; ++c) same = std::memcmp(&he[static_cast<size_t>(e) * d], &hc[static_cast<size_t>(c) * d], sizeof(T) * d) == 0;
+      (same ? dup : fresh).push_back(e);
+    }
+    fresh.insert(fresh.end(), dup.begin(), dup.end());   // duplicates only when nothing else is left
     CB2_CUDA(cudaMemcpyAsync(C, cand.get(), sizeof(T) * m * d, cudaMemcpyDeviceToDevice, h.stream));
-    CB2_CUDA(cudaMemcpyAsync(C + static_cast<size_t>(m) * d, extra.get(), sizeof(T) * (k - m) * d,
-                             cudaMemcpyDeviceToDevice, h.stream));
+    for (int j = 0; j < k - m; ++j)
+      CB2_CUDA(cudaMemcpyAsync(C + static_cast<size_t>(m + j) * d, extra.get() + static_cast<size_t>(fresh[j]) * d,
+                               sizeof(T) * d, cudaMemcpyDeviceToDevice, h.stream));
     CB2_CUDA(cudaStreamSynchronize(h.stream));
     return;
   }

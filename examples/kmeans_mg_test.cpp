@@ -5,6 +5,9 @@
 // generating labels (:144-156, :186-189).  Like the reference's test the default run injects a ONE-rank communicator
 // (ncclCommInitAll(&comm, 1, {0}) there, cuml_b200_handle_init_comm(id, 0, 1) here); `kmeans_mg_test N` (N >= 2)
 // additionally runs N rank processes, one GPU each, on contiguous row shards of the same inputs.
+// `kmeans_mg_test N peer` does the same over the library's peer-memory communicator (CUDA IPC windows instead of NCCL;
+// the IPC handles travel through files like the unique id), `kmeans_mg_test N shared` puts all N ranks on device 0
+// (peer-memory communicator; NCCL refuses two ranks on one device) -- the multi-rank run a one-GPU box can do.
 //   g++ -O2 -std=c++17 -Iinclude -I/usr/local/cuda/include examples/kmeans_mg_test.cpp -Lcuml_b200/lib -lcuml_b200
 //       -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,$PWD/cuml_b200/lib -o kmeans_mg_test        (one command line)
 #include <cuda_runtime.h>
@@ -115,10 +118,59 @@ static double run_case(const raft::handle_t& handle, const Inputs& in, int rank,
   return score;
 }
 
-// all inputs, float and double, on rank `rank` of `n_ranks`; the unique id comes from `id_path` (written by rank 0)
-static int run_rank(int rank, int n_ranks, const std::string& id_path)
+// publish `bytes` atomically at `path`: write a temporary, then rename
+static bool put_file(const std::string& path, const void* data, size_t bytes)
 {
-  CHECK(cudaSetDevice(rank));
+  const std::string tmp = path + ".tmp";
+  FILE* f = std::fopen(tmp.c_str(), "wb");
+  if (!f || std::fwrite(data, 1, bytes, f) != bytes) return false;
+  std::fclose(f);
+  return std::rename(tmp.c_str(), path.c_str()) == 0;
+}
+static bool get_file(const std::string& path, void* data, size_t bytes)
+{
+  FILE* f = nullptr;
+  for (int tries = 0; tries < 600 && !(f = std::fopen(path.c_str(), "rb")); ++tries)
+    std::this_thread::sleep_for(std::chrono::milliseconds(100));
+  if (!f || std::fread(data, 1, bytes, f) != bytes) return false;
+  std::fclose(f);
+  return true;
+}
+
+// all inputs, float and double, on rank `rank` of `n_ranks`; the unique id comes from `id_path` (written by rank 0).
+// mode: "nccl" (one device per rank), "peer" (one device per rank, peer-memory communicator), "shared" (all on device 0)
+static int run_rank(int rank, int n_ranks, const std::string& id_path, const std::string& mode = "nccl")
+{
+  CHECK(cudaSetDevice(mode == "shared" ? 0 : rank));
+  if (mode != "nccl" && n_ranks > 1) {
+    int failed = 0;
+    try {
+      raft::handle_t handle;
+      unsigned char mine[64];
+      std::vector<unsigned char> all(static_cast<size_t>(64) * n_ranks);
+      handle.peer_window_create(n_ranks, mine);
+      if (!put_file(id_path + ".ipc" + std::to_string(rank), mine, 64)) return 2;
+      for (int r = 0; r < n_ranks; ++r)
+        if (!get_file(id_path + ".ipc" + std::to_string(r), all.data() + static_cast<size_t>(64) * r, 64)) return 2;
+      handle.peer_window_attach(all.data(), rank, n_ranks);
+      // every rank has mapped every window before anyone starts exchanging
+      if (!put_file(id_path + ".att" + std::to_string(rank), mine, 1)) return 2;
+      unsigned char one;
+      for (int r = 0; r < n_ranks; ++r)
+        if (!get_file(id_path + ".att" + std::to_string(r), &one, 1)) return 2;
+      for (const Inputs& in : kInputs) {
+        const double sf = run_case<float>(handle, in, rank, n_ranks);
+        const double sd = run_case<double>(handle, in, rank, n_ranks);
+        std::printf("[rank %d/%d %s] %5d x %3d k %2d %-10s ARI float %.4f double %.4f\n", rank, n_ranks, mode.c_str(),
+                    in.n_row, in.n_col, in.n_clusters, in.weighted ? "weighted" : "unweighted", sf, sd);
+        if (!(sf >= 0.99) || !(sd >= 0.99)) ++failed;
+      }
+    } catch (const std::exception& e) {
+      std::fprintf(stderr, "[rank %d] exception: %s\n", rank, e.what());
+      return 2;
+    }
+    return failed ? 1 : 0;
+  }
   unsigned char id[128];
   if (rank == 0) {
     if (cuml_b200_nccl_unique_id(id) != CUML_B200_SUCCESS) {
@@ -160,8 +212,9 @@ static int run_rank(int rank, int n_ranks, const std::string& id_path)
 int main(int argc, char** argv)
 {
   if (argc >= 5 && std::strcmp(argv[1], "--rank") == 0)   // a rank process started by the launcher below
-    return run_rank(std::atoi(argv[2]), std::atoi(argv[3]), argv[4]);
-  const int n_ranks = argc > 1 ? std::atoi(argv[1]) : 1;
+    return run_rank(std::atoi(argv[2]), std::atoi(argv[3]), argv[4], argc >= 6 ? argv[5] : "nccl");
+  const int n_ranks      = argc > 1 ? std::atoi(argv[1]) : 1;
+  const std::string mode = argc > 2 ? argv[2] : "nccl";
   if (n_ranks <= 1) {
     const int rc = run_rank(0, 1, "");
     std::printf(rc == 0 ? "PASSED\n" : "FAILED\n");
@@ -174,7 +227,7 @@ int main(int argc, char** argv)
     const pid_t pid = fork();
     if (pid == 0) {
       const std::string rs = std::to_string(r), ns = std::to_string(n_ranks);
-      execl(argv[0], argv[0], "--rank", rs.c_str(), ns.c_str(), id_path.c_str(), static_cast<char*>(nullptr));
+      execl(argv[0], argv[0], "--rank", rs.c_str(), ns.c_str(), id_path.c_str(), mode.c_str(), static_cast<char*>(nullptr));
       std::perror("execl");
       _exit(127);
     }
@@ -187,6 +240,10 @@ int main(int argc, char** argv)
     if (!WIFEXITED(status) || WEXITSTATUS(status) != 0) ++bad;
   }
   std::remove(id_path.c_str());
+  for (int r = 0; r < n_ranks; ++r) {
+    std::remove((id_path + ".ipc" + std::to_string(r)).c_str());
+    std::remove((id_path + ".att" + std::to_string(r)).c_str());
+  }
   std::printf(bad == 0 ? "PASSED\n" : "FAILED\n");
   return bad == 0 ? 0 : 1;
 }

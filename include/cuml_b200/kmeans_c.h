@@ -58,7 +58,7 @@ typedef struct cuml_b200_kmeans_params {
   int32_t  init;                  /* = CUML_B200_INIT_KMeansPlusPlus                         */
   int32_t  max_iter;              /* = 300                                                   */
   double   tol;                   /* = 1e-4; raw sum ||dc||^2 < tol; tol <= 0 never stops    */
-  int32_t  verbosity;             /* = 3 (rapids_logger::level_enum::info)                   */
+  int32_t  verbosity;             /* = 2 (rapids_logger::level_enum::info; <= 1 logs every iteration) */
   uint64_t rng_seed;              /* = 0   raft::random::RngState::seed                      */
   uint64_t rng_base_subsequence;  /* = 0   raft::random::RngState::base_subsequence          */
   int32_t  rng_type;              /* = 0   GenPhilox (only Philox is implemented)            */
@@ -66,7 +66,7 @@ typedef struct cuml_b200_kmeans_params {
   double   oversampling_factor;   /* = 2.0; 0 => sequential k-means++                        */
   int32_t  batch_samples;         /* = 1<<15 (accepted; tiling is chosen by the engine)      */
   int32_t  batch_centroids;       /* = 0                                                     */
-  int64_t  init_size;             /* = 0                                                     */
+  int64_t  init_size;             /* = 0; out-of-core path: rows sampled for seeding (0 => min(3k, n)) */
   int64_t  device_buffer_samples; /* = 0; > 0: host partitions with more rows are streamed in batches this big */
 } cuml_b200_kmeans_params_t;
 
@@ -130,6 +130,19 @@ CUML_B200_API int cuml_b200_kmeans_fit_parts_f32(cuml_b200_handle_t*, const cuml
 CUML_B200_API int cuml_b200_kmeans_fit_parts_f64(cuml_b200_handle_t*, const cuml_b200_kmeans_params_t*,
     const double* const* X_parts, const int64_t* n_samples_parts, int64_t n_parts, int64_t n_features,
     const double* const* sample_weight_parts, double* centroids, double* inertia, int64_t* n_iter);
+
+/* fit + the labels of its own final assignment pass: labels_parts[i] (DEVICE int32 [n_samples_parts[i]], entries may be
+ * NULL) receives partition i's labels.  The reference's estimator runs a second, redundant E-step after every fit to
+ * obtain labels_ (python/cuml/cuml/cluster/kmeans.pyx:803-812); the fit already computed them for the inertia.
+ * `inertia` is the fit's inertia with weights normalised to sum(w) = n_samples, as for the calls above.             */
+CUML_B200_API int cuml_b200_kmeans_fit_parts_labels_f32(cuml_b200_handle_t*, const cuml_b200_kmeans_params_t*,
+    const float* const* X_parts, const int64_t* n_samples_parts, int64_t n_parts, int64_t n_features,
+    const float* const* sample_weight_parts, float* centroids, float* inertia, int64_t* n_iter,
+    int32_t* const* labels_parts);
+CUML_B200_API int cuml_b200_kmeans_fit_parts_labels_f64(cuml_b200_handle_t*, const cuml_b200_kmeans_params_t*,
+    const double* const* X_parts, const int64_t* n_samples_parts, int64_t n_parts, int64_t n_features,
+    const double* const* sample_weight_parts, double* centroids, double* inertia, int64_t* n_iter,
+    int32_t* const* labels_parts);
 
 /* ---- predict: nearest centroid + weighted inertia.  All pointers DEVICE; labels dtype = index
  * type.  Replaces reference kmeans.hpp:154-195 (impl kmeans_predict.cu:19-135).              */

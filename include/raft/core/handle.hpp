@@ -34,6 +34,18 @@ class handle_t {
     if (cuml_b200_handle_init_comm(h_, unique_id_128_bytes, rank, n_ranks) != CUML_B200_SUCCESS)
       throw std::runtime_error(cuml_b200_last_error());
   }
+  // the library's peer-memory communicator instead of NCCL: every rank creates its window (64-byte CUDA IPC handle out),
+  // the caller gathers the n_ranks handles in rank order by any means, every rank attaches
+  void peer_window_create(int n_ranks, void* ipc_handle_out_64_bytes)
+  {
+    if (cuml_b200_peer_window_create(h_, n_ranks, 0, ipc_handle_out_64_bytes) != CUML_B200_SUCCESS)
+      throw std::runtime_error(cuml_b200_last_error());
+  }
+  void peer_window_attach(const void* all_handles, int rank, int n_ranks)
+  {
+    if (cuml_b200_peer_window_attach(h_, all_handles, rank, n_ranks) != CUML_B200_SUCCESS)
+      throw std::runtime_error(cuml_b200_last_error());
+  }
   cuml_b200_handle_t* c_handle() const { return h_; }
 
  private:

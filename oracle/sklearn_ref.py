@@ -23,11 +23,12 @@ def n_threads():
         return os.cpu_count() or 1
 
 
-def fit(X, init, max_iter=50, tol=0.0, sample_weight=None, n_init=1):
-    """sklearn KMeans(init=array, algorithm='lloyd'); returns dict like oracle.lloyd.fit."""
+def fit(X, init, max_iter=50, tol=0.0, sample_weight=None, n_init=1, copy_x=True):
+    """sklearn KMeans(init=array, algorithm='lloyd'); returns dict like oracle.lloyd.fit.
+    copy_x=False lets sklearn centre X in place (no second copy of a matrix that fills a quarter of host memory)."""
     from sklearn.cluster import KMeans
     km = KMeans(n_clusters=init.shape[0], init=np.asarray(init), n_init=n_init, max_iter=max_iter,
-                tol=tol, algorithm="lloyd")
+                tol=tol, algorithm="lloyd", copy_x=copy_x)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         t0 = time.perf_counter()
@@ -37,12 +38,12 @@ def fit(X, init, max_iter=50, tol=0.0, sample_weight=None, n_init=1):
                 inertia=float(km.inertia_), n_iter=int(km.n_iter_), seconds=dt, model=km)
 
 
-def time_fit(X, init, max_iter, reps=3):
+def time_fit(X, init, max_iter, reps=3, copy_x=True):
     """best-of-reps wall time (the reference harness convention,
     python/cuml/cuml/benchmark/runners.py:42-64) -> (seconds, n_iter)."""
     best, n_iter = None, 0
     for _ in range(reps):
-        r = fit(X, init, max_iter=max_iter, tol=0.0)
+        r = fit(X, init, max_iter=max_iter, tol=0.0, copy_x=copy_x)
         if best is None or r["seconds"] < best:
             best, n_iter = r["seconds"], r["n_iter"]
     return best, n_iter

@@ -78,6 +78,9 @@ class FakeLib:
         m = re.fullmatch(r"cuml_b200_kmeans_fit_parts_(f32|f64)", name)
         if m:
             return lambda *a: self._fit_parts(name, m.group(1), *a)
+        m = re.fullmatch(r"cuml_b200_kmeans_fit_parts_labels_(f32|f64)", name)
+        if m:
+            return lambda *a: self._fit_parts(name, m.group(1), *a[:-1], labels_parts=a[-1])
         return getattr(self._real, name)
 
     # ---- compute ---------------------------------------------------------------------------------------
@@ -112,7 +115,7 @@ class FakeLib:
         n_iter._obj.value = r["n_iter"]
         return 0
 
-    def _fit_parts(self, name, t, h, params, xp, rows, n_parts, d, wp, centers, inertia, n_iter):
+    def _fit_parts(self, name, t, h, params, xp, rows, n_parts, d, wp, centers, inertia, n_iter, labels_parts=None):
         self.calls.append(name)
         ct, _ = _CT[t]
         p = params._obj
@@ -125,6 +128,12 @@ class FakeLib:
         r = self._lloyd(p, Xa, wa, Ca)
         inertia._obj.value = r["inertia"]
         n_iter._obj.value = r["n_iter"]
+        if labels_parts is not None:
+            off = 0
+            for i in range(n_parts):
+                if _addr(labels_parts[i]):
+                    _array(labels_parts[i], (int(rows[i]),), C.c_int32)[...] = r["labels"][off:off + int(rows[i])]
+                off += int(rows[i])
         return 0
 
     def _predict(self, t, ix, h, params, centers, X, n, d, w, normalize, labels, inertia):

@@ -184,3 +184,26 @@ def test_distributed_estimator(world, topology):
     assert abs(outs[0]["score"] - expect) / abs(expect) <= 1e-5
     To = lloyd.transform(X[:5], ref["centroids"])
     assert np.abs(outs[0]["tr"] - To).max() / To.max() < 1e-5
+
+
+# ---- the reference's multi-GPU gtest inputs through the C++ surface (examples/kmeans_mg_test.cpp) ---------------------
+@pytest.mark.parametrize("mode", ["shared", "peer", "nccl"])
+def test_cpp_mg_gtest_inputs_two_ranks(tmp_path, mode):
+    # cpp/tests/mg/kmeans_test.cu:50-195: eight inputs, float and double, weighted and not, ARI >= 0.99 on every rank's
+    # shard -- here with TWO rank processes ("shared": both on device 0 over the peer-memory communicator)
+    import shutil
+    import subprocess
+    _need(mode, 2)
+    from cuml_b200 import build
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "kmeans_mg_test")
+    libdir = os.path.dirname(build.lib_path())
+    cmd = [gxx, "-O1", "-std=c++17", "-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include",
+           os.path.join(root, "examples", "kmeans_mg_test.cpp"), "-L" + libdir, "-lcuml_b200",
+           "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir, "-o", exe]
+    subprocess.run(cmd, check=True, capture_output=True)
+    r = subprocess.run([exe, "2", mode], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

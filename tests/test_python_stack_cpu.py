@@ -22,8 +22,9 @@ def test_estimator_calls_the_boundary_with_the_reference_dispatch(fake):
     w = np.random.default_rng(0).uniform(0.5, 2.0, len(X)).astype(np.float32)
     km = KMeans(n_clusters=5, init=init, max_iter=7, tol=0.0).fit(X, sample_weight=w)
     ref = lloyd.fit(X, init, max_iter=7, tol=0.0, sample_weight=w)
-    # fit -> predict on the same handle (reference kmeans.pyx:803-812), int32 indices for small inputs (:277-281)
-    assert fake.calls == ["cuml_b200_kmeans_fit_f32_i32", "cuml_b200_kmeans_predict_f32_i32"]
+    # ONE boundary call per fit: the fit hands back the labels / inertia of its own final pass (the reference needs a
+    # second, redundant E-step for them, kmeans.pyx:803-812); int32 labels for small inputs (:277-281)
+    assert fake.calls == ["cuml_b200_kmeans_fit_parts_labels_f32"]
     assert km.cluster_centers_.dtype == np.float32 and km.labels_.dtype == np.int32
     np.testing.assert_allclose(km.cluster_centers_, ref["centroids"], rtol=1e-6, atol=1e-6)
     assert np.array_equal(km.labels_, ref["labels"]) and km.n_iter_ == 7
@@ -34,7 +35,7 @@ def test_estimator_calls_the_boundary_with_the_reference_dispatch(fake):
     assert fake.calls[-1] == "cuml_b200_kmeans_predict_f32_i32" and "cuml_b200_kmeans_transform_f32_i32" in fake.calls
     # fp64 input keeps fp64 through the boundary
     km64 = KMeans(n_clusters=5, init=init.astype(np.float64), max_iter=3, tol=0.0).fit(X.astype(np.float64))
-    assert "cuml_b200_kmeans_fit_f64_i32" in fake.calls and km64.cluster_centers_.dtype == np.float64
+    assert "cuml_b200_kmeans_fit_parts_labels_f64" in fake.calls and km64.cluster_centers_.dtype == np.float64
     # integer input is converted to fp32 (xfail-list.yaml:693-699)
     kmi = KMeans(n_clusters=2, init=np.array([[0, 0], [9, 9]]), max_iter=2, tol=0.0).fit(np.array([[0, 1], [1, 0], [9, 8], [8, 9]]))
     assert kmi.cluster_centers_.dtype == np.float32 and kmi.labels_.tolist() == [0, 0, 1, 1]
