@@ -53,6 +53,7 @@ EXPORTED_SYMBOLS = [
     "cuml_b200_kmeans_lloyd_step_f32", "cuml_b200_kmeans_assign_f32", "cuml_b200_launch_count_reset",
     "cuml_b200_launch_count", "cuml_b200_kernel_timing_enable", "cuml_b200_kernel_timing_read",
     "cuml_b200_kmeans_tc_supported", "cuml_b200_kmeans_debug_dots_f32", "cuml_b200_kmeans_estep_variant",
+    "cuml_b200_kmeans_fused_update",
 ]
 
 
@@ -108,6 +109,7 @@ def load(build_if_missing=True):
     lib.cuml_b200_kernel_timing_read.argtypes = [vp, P(dbl), P(i64), P(dbl), P(i64)]
     lib.cuml_b200_kmeans_tc_supported.argtypes = [i64, i32]
     lib.cuml_b200_kmeans_estep_variant.argtypes = [vp, i64, i32]
+    lib.cuml_b200_kmeans_fused_update.argtypes = [vp, i64, i32]
     _LIB = lib
     return lib
 

@@ -1013,6 +1013,15 @@ const uint8_t* tma_update_balance(Handle& h, const double* W, int d, int k, DevB
   return map.get();
 }
 
+void tma_update_reduce(Handle& h, const float* partial_S, const float* partial_W, int row_blocks, int k, int d,
+                       double* packed, bool accumulate_into)
+{
+  const int64_t total = static_cast<int64_t>(k) * d + k;
+  reduce_partials_f32_kernel<<<static_cast<unsigned>(ceil_div(total, 32)), 256, 0, h.stream>>>(
+    partial_S, partial_W, row_blocks, k, d, packed, accumulate_into ? 1 : 0);
+  CB2_CHECK_LAUNCH();
+}
+
 void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const int32_t* labels_padded, const float* w,
                            int k, DevBuf<float>& partial_S, DevBuf<float>& partial_W, double* packed,
                            bool accumulate_into, const uint8_t* cls_map)

@@ -127,8 +127,28 @@ struct Barriers {
   uint64_t acc_full[MAX_ACC], acc_empty[MAX_ACC];
   uint64_t raw_full[MAX_RAW], raw_empty[MAX_RAW];   // A-in-TMEM variant: raw X ring in shared memory
   uint64_t cn_full;                                 // CTA-pair kernel: folded half-norm tiles have landed
+  uint64_t lab_full[MAX_A_SLOTS];                   // fused M-step: the labels of the tile in X slot s are in shared memory
   uint32_t tmem_base;
 };
+
+// ---- fused M-step of the single-CTA kernel (MSTEP instantiation; row-packed n_features = 16, unweighted) ----------
+// One pass over X per Lloyd iteration for the HBM-bound small-d shapes: the raw fp32 tile is still in its X slot when
+// the row-owner epilogue knows the tile's labels, so four accumulate warps add the rows into warp-private
+// [k_sub x 32] tables (lane = (data row of the packed pair, column): lane l only ever touches bank l) before the slot is
+// released.  The slot's empty barrier then counts the MMA commit and the four accumulate warps.  Labels travel through
+// a per-slot shared-memory buffer (one word per packed row: even-row label | odd-row label << 16); cluster sizes are
+// integer shared-memory counts kept by the epilogue threads (exact).  At the end the CTA folds its tables in a fixed
+// order into the partials format of the M-step kernels (deterministic).  Parameter fields that are idle in this mode
+// carry the outputs (the parameter block keeps its size): dbg_dots -> partial_S [grid][k][16], cnh -> partial_W [grid][k],
+// raw_slots -> true n_clusters.
+constexpr int MS_ACC_WARPS = 4;
+__host__ __device__ inline size_t mstep_smem_bytes(int k_sub)
+{
+  return static_cast<size_t>(MS_ACC_WARPS) * k_sub * 32 * sizeof(float)   // private tables
+         + static_cast<size_t>(k_sub) * 2 * sizeof(int)                   // counts (both packed groups share them)
+         + static_cast<size_t>(MAX_A_SLOTS) * TILE_M * sizeof(uint32_t)   // label words per slot
+         + 128;
+}
 
 // ===================== epilogue role (shared by all kernel variants) ===================================
 // 16 warps: warp e handles TMEM lanes [32*(e&3), +32) (its rows) and column part (e>>2) of every
@@ -366,10 +386,11 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
 // of its row (both packed groups when two data rows share an operand row) and stores the label itself: no merge, no
 // named barriers, and four tiles' epilogues in flight on different accumulator stages (BN <= 128 leaves >= 4 stages).
 // Only 4 warps arrive on an accumulator's empty barrier (the kernel initialises it with 4 in this mode).
-template <bool FOLD1>
+template <bool FOLD1, bool MSTEP = false>
 __device__ __forceinline__ void epilogue_role_rowown(const FusedParams& p, Barriers* bars, float* cn_s,
                                                      uint32_t tmem_base, int64_t first_row, int64_t row_stride,
-                                                     int64_t n_tiles_cta)
+                                                     int64_t n_tiles_cta, uint32_t* ms_labels = nullptr,
+                                                     int* ms_counts = nullptr)
 {
   const int et      = threadIdx.x - 256;      // 0..511
   const int ew      = et >> 5;                // epilogue warp 0..15
@@ -386,11 +407,14 @@ __device__ __forceinline__ void epilogue_role_rowown(const FusedParams& p, Barri
   }
   Ring racc;                  // accumulator stage of tile t: t % n_acc, phase (t / n_acc) & 1 (n_acc >= 4 here)
   racc.slot = static_cast<uint32_t>(group);
+  Ring rslot;                 // MSTEP: X slot of tile t (one K-block per tile): t % a_slots
+  if (MSTEP) rslot.advance_by(static_cast<uint32_t>(group), p.a_slots);
   for (int64_t t = group; t < n_tiles_cta; t += 4, racc.advance_by(4, p.n_acc)) {
     const uint32_t acc = racc.slot, pacc = racc.phase;
     ptx::mbar_wait_park(ptx::smem_u32(&bars->acc_full[acc]), pacc);
     ptx::tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.bn;
+    uint32_t lab_word = 0;
     for (int g = 0; g < p.pack; ++g) {
       float b0 = inf, b1 = inf, b2 = inf, b3 = inf;
       int i0 = 0, i1 = 0, i2 = 0, i3 = 0;
@@ -433,10 +457,20 @@ __device__ __forceinline__ void epilogue_role_rowown(const FusedParams& p, Barri
       if (b2 < b0 || (b2 == b0 && i2 < i0)) { b0 = b2; i0 = i2; }
       const int64_t row = (first_row + t * row_stride + rit) * p.pack + g;
       if (row < p.n) p.labels[row] = i0;
+      if (MSTEP) {
+        lab_word |= static_cast<uint32_t>(i0) << (16 * g);
+        if (row < p.n) atomicAdd(ms_counts + i0, 1);   // integer: exact and order-independent
+      }
     }
     ptx::tc_fence_before();
     __syncwarp();
     if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->acc_empty[acc]));
+    if (MSTEP) {
+      ms_labels[rslot.slot * TILE_M + rit] = lab_word;
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->lab_full[rslot.slot]));   // release: the words above are visible
+      rslot.advance_by(4, p.a_slots);
+    }
   }
 }
 
@@ -1047,7 +1081,9 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
 // Single-CTA twin of the CTA-pair kernel (opt-in, CUML_B200_SOLO_V2=1; NOT yet validated on hardware): the same
 // roles, bf16 correction terms and folded half norms for k <= 128, with cta_group::1 instructions and local
 // barriers.  Generated from the pair kernel's source; once measured it is meant to replace fused_l2_argmin_kernel.
-template <bool BF16C, int DIST = 0, bool TRUNC = false, bool ROWOWN = false>
+// MSTEP (with ROWOWN, BF16C, TRUNC; row-packed n_features = 16): the M-step rides on the E-step's tile, see above.
+// The converter then has 4 warps (4..7) and warps 24..27 accumulate.
+template <bool BF16C, int DIST = 0, bool TRUNC = false, bool ROWOWN = false, bool MSTEP = false>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                             const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_lb,
@@ -1078,6 +1114,11 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   float* mrg_v           = cn_s + 2 * p.bn;                              // [128] epilogue half merge
   int* mrg_i             = reinterpret_cast<int*>(mrg_v + 3 * TILE_M);   // [3][128]
   Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 6u * TILE_M * 4u);
+  // fused M-step region (after the barriers): tables | counts | label words
+  float* ms_tab          = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ((sizeof(Barriers) + 127) & ~size_t(127)));
+  int* ms_counts         = reinterpret_cast<int*>(ms_tab + static_cast<size_t>(MS_ACC_WARPS) * p.k_sub * 32);
+  uint32_t* ms_labels    = reinterpret_cast<uint32_t*>(ms_counts + 2 * p.k_sub);
+  constexpr int NCONV    = MSTEP ? 128 : 256;   // converter threads
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -1085,8 +1126,9 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   if (threadIdx.x == 0) {
     for (int s = 0; s < MAX_A_SLOTS; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->a_raw_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->a_ready[s]), 8);     // 8 converter warps
-      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->a_ready[s]), NCONV / 32);            // converter warps
+      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), MSTEP ? 1 + MS_ACC_WARPS : 1);  // MMA commit (+ accumulate warps)
+      ptx::mbar_init(ptx::smem_u32(&bars->lab_full[s]), 4);                    // the 4 epilogue warps of a tile's group
     }
     for (int s = 0; s < MAX_ACC; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
@@ -1103,6 +1145,9 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     float* ones = reinterpret_cast<float*>(gbase + fold_off);
     for (int i = threadIdx.x; i < TILE_M * 8; i += blockDim.x) ones[i] = 1.0f;
     ptx::fence_proxy_async_smem();
+  }
+  if (MSTEP) {
+    for (int i = threadIdx.x; i < MS_ACC_WARPS * p.k_sub * 32 + 2 * p.k_sub; i += blockDim.x) ms_tab[i] = 0.0f;   // tables + counts
   }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_x);
@@ -1195,10 +1240,51 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
         }
       }
     }
-  } else if ((warp >= 4 && warp < 8) || warp >= 24) {
-    // ===================== converter (8 warps: 4..7 and 24..27) =====================
-    const int ct = warp >= 24 ? threadIdx.x - 768 + 128 : threadIdx.x - 128;   // 0..255
-    // this thread's chunks are ct + 256 i: 32 rows apart, so the logical chunk and the swizzle phases are fixed
+  } else if (MSTEP && warp >= 24) {
+    // ===================== fused M-step: accumulate warps 24..27 (32 packed rows of every tile each) =====================
+    const int aw       = warp - 24;
+    float* tab         = ms_tab + static_cast<size_t>(aw) * p.k_sub * 32 + lane;   // this lane's column of the private table
+    const int half     = lane >> 4;                                                // which data row of the packed pair
+    const uint32_t xch = static_cast<uint32_t>(lane >> 2);                         // logical 16-byte chunk of the lane's float
+    const uint32_t xin = static_cast<uint32_t>(lane & 3) * 4u;
+    Ring ra;
+    for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
+      const uint32_t sa = ra.slot, pa = ra.phase;
+      ra.advance(p.a_slots);
+      ptx::mbar_wait_park(ptx::smem_u32(&bars->a_raw_full[sa]), pa);   // the raw tile (async-proxy writes) is visible
+      ptx::mbar_wait_park(ptx::smem_u32(&bars->lab_full[sa]), pa);     // ... and so are its labels
+      const uint32_t my_word = ms_labels[sa * TILE_M + aw * 32 + lane];
+      const uint8_t* xs      = gbase + sa * A_SLOT_BYTES + static_cast<uint32_t>(aw * 32) * 128u;
+#pragma unroll 1
+      for (int j = 0; j < 32; j += 4) {
+        uint32_t lb[4];
+        float xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t w = __shfl_sync(0xffffffffu, my_word, j + u);
+          lb[u]            = half ? (w >> 16) : (w & 0xffffu);
+          const uint32_t r = static_cast<uint32_t>(j + u);   // row within this warp's 32 (aw * 32 is a multiple of 8)
+          xv[u] = *reinterpret_cast<const float*>(xs + r * 128u + ((xch ^ (r & 7u)) << 4) + xin);
+        }
+        const bool clash = lb[0] == lb[1] || lb[0] == lb[2] || lb[0] == lb[3] || lb[1] == lb[2] || lb[1] == lb[3] || lb[2] == lb[3];
+        if (!__any_sync(0xffffffffu, clash)) {   // four independent read-modify-write chains
+          float tv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) tv[u] = tab[lb[u] * 32u];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) tab[lb[u] * 32u] = tv[u] + xv[u];
+        } else {                                  // two rows of the group share a cluster in some lane: row order
+#pragma unroll
+          for (int u = 0; u < 4; ++u) tab[lb[u] * 32u] += xv[u];
+        }
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->a_empty[sa]));
+    }
+  } else if ((warp >= 4 && warp < 8) || (!MSTEP && warp >= 24)) {
+    // ===================== converter (8 warps: 4..7 and 24..27; MSTEP: 4 warps) =====================
+    const int ct = warp >= 24 ? threadIdx.x - 768 + 128 : threadIdx.x - 128;   // 0..NCONV-1
+    // this thread's chunks are ct + NCONV i: NCONV / 8 rows apart, so the logical chunk and the swizzle phases are fixed
     const int conv_row       = ct >> 3;
     const int conv_lc        = (ct & 7) ^ (conv_row & 7);     // logical 16-byte chunk: features [4 lc, 4 lc + 4)
     const uint32_t conv_off  = static_cast<uint32_t>(conv_row) * 64u +
@@ -1219,15 +1305,15 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
         const int live_chunks = BF16C ? 4 * min(2, (rem_f + 15) / 16) : 2 * min(4, (rem_f + 7) / 8);
         uint8_t* hb = gbase + sa * A_SLOT_BYTES + KBLOCK_BYTES;                    // bf16 hi tile (8 KB)
         uint8_t* lb = hb + KBLOCK_BYTES / 2;                                       // bf16 lo tile (8 KB)
-        constexpr int CPT = KBLOCK_BYTES / 16 / 256;   // 16-byte chunks per thread
+        constexpr int CPT = KBLOCK_BYTES / 16 / NCONV;   // 16-byte chunks per thread
         // all loads first: the chunks are independent, one shared-memory latency instead of CPT
         uint4 v[CPT];
 #pragma unroll
-        for (int i = 0; i < CPT; ++i) v[i] = hi[ct + i * 256];
-        if (conv_lc < live_chunks) {   // chunk ct + 256 i keeps the logical chunk and the swizzle phase of chunk ct
+        for (int i = 0; i < CPT; ++i) v[i] = hi[ct + i * NCONV];
+        if (conv_lc < live_chunks) {   // chunk ct + NCONV i keeps the logical chunk and the swizzle phase of chunk ct
 #pragma unroll
           for (int i = 0; i < CPT; ++i) {
-            const int e = ct + i * 256;
+            const int e = ct + i * NCONV;
             uint4 h, l;
             if (BF16C && !TRUNC) {   // nearest tf32 (ties away from zero): |lo| <= 2^-12 |x|
               h.x = (v[i].x + 0x1000u) & 0xffffe000u;
@@ -1244,7 +1330,7 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
             if (!TRUNC) hi[e] = h;
             if (BF16C) {
               // 4 features -> 8 bytes of the 64-byte bf16 row (64B swizzle: 16-byte chunk ^= (row / 2) % 4)
-              const uint32_t off = conv_off + static_cast<uint32_t>(i) * (32u * 64u);
+              const uint32_t off = conv_off + static_cast<uint32_t>(i) * (static_cast<uint32_t>(NCONV / 8) * 64u);
               const __nv_bfloat162 h01 = __floats2bfloat162_rn(__uint_as_float(h.x), __uint_as_float(h.y));
               const __nv_bfloat162 h23 = __floats2bfloat162_rn(__uint_as_float(h.z), __uint_as_float(h.w));
               const __nv_bfloat162 l01 = __floats2bfloat162_rn(__uint_as_float(l.x), __uint_as_float(l.y));
@@ -1372,7 +1458,7 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     // ===================== epilogue (own 128 rows of the pair tile) =====================
     const int64_t n_mine = (pair_tiles > pair) ? (pair_tiles - pair + n_pairs - 1) / n_pairs : 0;
     if constexpr (ROWOWN)
-      epilogue_role_rowown<true>(p, bars, cn_s, tmem_base, pair * TILE_M, n_pairs * TILE_M, n_mine);
+      epilogue_role_rowown<true, MSTEP>(p, bars, cn_s, tmem_base, pair * TILE_M, n_pairs * TILE_M, n_mine, ms_labels, ms_counts);
     else
       epilogue_role<false, DIST, true>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, pair * TILE_M, n_pairs * TILE_M, n_mine);
   }
@@ -1381,6 +1467,24 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   __syncthreads();
   ptx::tc_fence_after();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  if (MSTEP) {
+    // fold the private tables in a fixed order (accumulate warp 0..3, packed group 0 then 1) into this CTA's partials
+    const int k_true = p.raw_slots;
+    float* out_S     = p.dbg_dots + static_cast<size_t>(blockIdx.x) * k_true * 16;
+    float* out_W     = const_cast<float*>(p.cnh) + static_cast<size_t>(blockIdx.x) * k_true;
+    for (int e = threadIdx.x; e < k_true * 16; e += blockDim.x) {
+      const int j = e >> 4, c = e & 15;
+      float acc = 0.0f;
+#pragma unroll
+      for (int w = 0; w < MS_ACC_WARPS; ++w) {
+        const float* t = ms_tab + (static_cast<size_t>(w) * p.k_sub + j) * 32;
+        acc += t[c];
+        acc += t[16 + c];
+      }
+      out_S[e] = acc;
+    }
+    for (int j = threadIdx.x; j < k_true; j += blockDim.x) out_W[j] = static_cast<float>(ms_counts[j]);
+  }
 }
 
 // =================================================================================================
@@ -2046,9 +2150,34 @@ bool tc_best_supported(const Handle& h, int d, int k)
   return h.cc_major == 10 && tc_supported(d, k) && !use_ts(h, d, k);
 }
 
-void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen, int32_t* labels,
-               float* dbg_dots, const TcDistOut* dist, float* best_out)
+// fused E + M step (see mstep_smem_bytes): the plan of the row-packed single-CTA kernel with room for the tables
+static bool plan_fused_mstep(const Handle& h, int d, int k, TilePlan& t_out, size_t& smem_out)
 {
+  static const bool on = env_flag("CUML_B200_FUSED_MSTEP", true);
+  const int k_sub = pack_k_sub(d, k);
+  if (!on || d != 16 || k_sub == 0 || k_sub > 64 || !use_solo_v2() || !use_bf16_corrections() || !use_epi_rowown() || !use_cn_fold())
+    return false;
+  const int k_pad      = 2 * k_sub;
+  const size_t extra   = mstep_smem_bytes(k_sub) + static_cast<size_t>(2) * TILE_M * 32;   // tables + the fold tiles
+  if (h.smem_optin <= extra) return false;
+  TilePlan t = plan_tiles(2 * d, k_pad, h.smem_optin - extra);
+  if (t.bn != k_pad || t.kb != 1 || t.a_slots < 3 || !t.b_resident || 512 / t.bn < 4) return false;
+  t_out    = t;
+  smem_out = t.smem + extra;
+  return true;
+}
+
+bool tc_fused_update_supported(const Handle& h, int d, int k)
+{
+  TilePlan t;
+  size_t smem;
+  return h.cc_major == 10 && plan_fused_mstep(h, d, k, t, smem);
+}
+
+void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen, int32_t* labels,
+               float* dbg_dots, const TcDistOut* dist, float* best_out, TcMstepOut* mstep)
+{
+  if (mstep) mstep->row_blocks = 0;
   if (n == 0) return;
   CB2_EXPECTS(!best_out || (!dbg_dots && !dist && labels), "best-value output excludes the debug dump and the distance matrix");
   CB2_EXPECTS(!dist || cen.pack == 1, "distance-matrix mode does not support row packing");
@@ -2093,7 +2222,34 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       EventPair ev{};
       if (h.timing) ev = h.begin_event();
       const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
-      if (cen.bf16c && !best_out) {
+      TilePlan tf;
+      size_t smem_f = 0;
+      if (mstep && cen.bf16c && cen.fold && !best_out && (n & 1) == 0 && plan_fused_mstep(h, d, k, tf, smem_f)) {
+        // ---- one pass over X: distance + argmin + centroid sums / counts (fused_l2_argmin_solo_kernel<.., MSTEP>) ----
+        p.a_slots = tf.a_slots; p.b_stages = tf.b_stages; p.b_resident = tf.b_resident;
+        p.fold = 1; p.l2_ahead = 3;
+        if (mstep->partial_S->n < static_cast<size_t>(grid) * k * d) mstep->partial_S->alloc(static_cast<size_t>(grid) * k * d, h.stream);
+        if (mstep->partial_W->n < static_cast<size_t>(grid) * k) mstep->partial_W->alloc(static_cast<size_t>(grid) * k, h.stream);
+        p.dbg_dots  = mstep->partial_S->get();   // idle fields carry the M-step outputs (see mstep_smem_bytes)
+        p.cnh       = mstep->partial_W->get();
+        p.raw_slots = k;
+        CUtensorMap tm_hb = make_map_2d(cen.hb.get(), KBLOCK, cen.k_pad, static_cast<uint64_t>(KBLOCK) * 2, KBLOCK, tf.bn,
+                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        CUtensorMap tm_lb = make_map_2d(cen.lb.get(), KBLOCK, cen.k_pad, static_cast<uint64_t>(KBLOCK) * 2, KBLOCK, tf.bn,
+                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        CUtensorMap tm_cn = make_map_2d(cen.cnp.get(), 8, cen.k_pad, 8 * sizeof(float), 8, tf.bn, CU_TENSOR_MAP_SWIZZLE_32B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        static PerDeviceOnce ms_attr;
+        ms_attr.run(h.device, [&] {
+          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, 0, true, true, true>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
+        });
+        fused_l2_argmin_solo_kernel<true, 0, true, true, true><<<grid, PAIR_THREADS, smem_f, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb,
+                                                                                                        tm_cn, p);
+        mstep->row_blocks = static_cast<int>(grid);
+      } else if (cen.bf16c && !best_out) {
         // opt-in single-CTA tf32 + bf16 kernel (CUML_B200_SOLO_V2=1) on the row-packed operands.  (It has no best-value
         // epilogue; the 3xTF32 kernel below reads the same buffers: hi rounded to nearest is still tf32-exact and
         // lo = c - hi is exact.)

@@ -38,9 +38,19 @@ struct TcDistOut {
   const float* xnorm = nullptr;   // [n] ||x_i||^2
   int sqrt           = 0;
 };
+// fused E + M step (short rows: n_features = 16, k <= 64, unweighted, even row count): the E-step kernel also leaves
+// this partition's centroid sums / counts as per-CTA partials [row_blocks][k][d] / [row_blocks][k]; row_blocks == 0 on
+// return means the shape took the plain kernel and the caller runs the separate M-step
+struct TcMstepOut {
+  DevBuf<float>* partial_S = nullptr;
+  DevBuf<float>* partial_W = nullptr;
+  int row_blocks           = 0;
+};
+bool tc_fused_update_supported(const Handle& h, int d, int k);
 // best_out (optional, [n]): the winning value 1/2||c_label||^2 - x.c per row, i.e. (min distance - ||x||^2) / 2
 void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen,
-               int32_t* labels, float* dbg_dots = nullptr, const TcDistOut* dist = nullptr, float* best_out = nullptr);
+               int32_t* labels, float* dbg_dots = nullptr, const TcDistOut* dist = nullptr, float* best_out = nullptr,
+               TcMstepOut* mstep = nullptr);
 bool tc_best_supported(const Handle& h, int d, int k);
 bool tc_transform_supported(const Handle& h, int64_t d, int k);
 
@@ -73,6 +83,10 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
                            int k, DevBuf<float>& partial_S, DevBuf<float>& partial_W, double* packed,
                            bool accumulate_into, const uint8_t* cls_map = nullptr);
 const uint8_t* tma_update_balance(Handle& h, const double* W, int d, int k, DevBuf<uint8_t>& map);
+// packed[0 .. k*d+k) (+)= fixed-order fp64 sum of per-CTA partials (the tail of every fp32 M-step kernel; also used alone
+// after the fused E + M kernel)
+void tma_update_reduce(Handle& h, const float* partial_S, const float* partial_W, int row_blocks, int k, int d,
+                       double* packed, bool accumulate_into);
 // C_new = S/W (W>0) else C_old; shift2 = sum (C_new-C_old)^2 (deterministic, one block)
 template <typename T>
 void finalize_centroids(Handle& h, const double* packed, T* C, int k, int d, double* shift2_out);

@@ -307,7 +307,6 @@ void fit_streamed(Handle& h, const cuml_b200_kmeans_params_t& params, const T* c
   if (params.init != CUML_B200_INIT_Array) {
     const int64_t want_global = params.init_size > 0 ? params.init_size : std::min<int64_t>(3 * static_cast<int64_t>(k), n_global);
     n_seed = std::min<int64_t>(n_local, ceil_div(want_global * n_local, std::max<int64_t>(n_global, 1)));
-    if (h.n_ranks == 1) n_seed = std::min<int64_t>(n_local, std::max<int64_t>(n_seed, k));
     const std::vector<int64_t> pick = sample_rows(n_local, n_seed, params.rng_seed + static_cast<uint64_t>(h.rank));
     std::vector<T> hx(static_cast<size_t>(n_seed) * d), hw(weighted ? static_cast<size_t>(n_seed) : 0);
     int64_t pi = 0, base = 0;
@@ -903,6 +902,13 @@ int cuml_b200_kernel_timing_read(cuml_b200_handle_t* h, double* fused_ms, int64_
 }
 
 int cuml_b200_kmeans_tc_supported(int64_t d, int32_t k) { return tc_supported(d, k) ? 1 : 0; }
+
+int cuml_b200_kmeans_fused_update(cuml_b200_handle_t* h, int64_t d, int32_t k)
+{
+  if (!h || d <= 0 || d > std::numeric_limits<int>::max() || k <= 0) return 0;
+  Handle& hh = HANDLE(h);
+  return (hh.cc_major == 10 && tc_supported(d, k) && tc_fused_update_supported(hh, static_cast<int>(d), k)) ? 1 : 0;
+}
 
 int cuml_b200_kmeans_estep_variant(cuml_b200_handle_t* h, int64_t d, int32_t k)
 {

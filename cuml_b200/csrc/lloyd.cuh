@@ -172,9 +172,41 @@ class LloydSolver {
     n_local_  = n;
   }
 
+  // E-step and M-step in one pass over X where the fused kernel applies (fp32, n_features = 16, k <= 64, no weights,
+  // even partition sizes): labels + packed sums / weights.  false = not applicable, nothing was launched.
+  bool assign_accumulate_fused(const T* C)
+  {
+    if constexpr (!std::is_same<T, float>::value) {
+      return false;
+    } else {
+      if (!use_tc_ || parts_.empty() || !tc_fused_update_supported(h_, d_, k_)) return false;
+      for (auto& p : parts_)
+        if (p.w != nullptr || (p.n & 1) != 0 || p.n == 0) return false;
+      prepare(C);
+      for (size_t i = 0; i < parts_.size(); ++i) {
+        TcMstepOut ms;
+        ms.partial_S = &tma_S_;
+        ms.partial_W = &tma_W_;
+        tc_assign(h_, parts_[i].X, parts_[i].n, d_, k_, tc_, labels(i), nullptr, nullptr, nullptr, &ms);
+        CB2_EXPECTS(ms.row_blocks > 0, "fused E+M kernel was planned but not launched");
+        EventPair ev{};
+        if (h_.timing) ev = h_.begin_event();
+        tma_update_reduce(h_, tma_S_.get(), tma_W_.get(), ms.row_blocks, k_, d_, packed_.get(), i != 0);
+        if (h_.timing) h_.end_event(ev, false);
+      }
+      CB2_CUDA(cudaMemsetAsync(packed_.get() + packed_count() - 1, 0, sizeof(double), h_.stream));
+      have_weights_ = true;
+      return true;
+    }
+  }
+
   // One full Lloyd iteration, centroids updated in place; squared shift left at packed[count]
   void step(T* C, bool with_inertia = false)
   {
+    if (!with_inertia && assign_accumulate_fused(C)) {
+      exchange_and_finalize<T>(h_, packed_.get(), packed_count(), C, k_, d_);
+      return;
+    }
     assign(C);
     accumulate(C, with_inertia);
     exchange_and_finalize<T>(h_, packed_.get(), packed_count(), C, k_, d_);

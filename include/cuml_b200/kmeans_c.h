@@ -199,6 +199,9 @@ CUML_B200_API int     cuml_b200_kernel_timing_read(cuml_b200_handle_t*, double* 
                                                    int64_t* update_launches);
 /* 1 if the tcgen05 engine supports (n_features, n_clusters) for fp32.                        */
 CUML_B200_API int cuml_b200_kmeans_tc_supported(int64_t n_features, int32_t n_clusters);
+/* 1 if an unweighted fp32 fit of this shape runs the E-step and the M-step as ONE kernel (one pass over X per
+ * iteration: n_features = 16, n_clusters <= 64).  Used by bench.py to label its roofline. */
+CUML_B200_API int cuml_b200_kmeans_fused_update(cuml_b200_handle_t* handle, int64_t n_features, int32_t n_clusters);
 /* Which E-step kernel a fit of this shape takes on the handle's device: 0 CUDA-core fp32, 1 tcgen05 one CTA
  * per tile (3xTF32), 2 tcgen05 CTA pair (3xTF32), 3 tcgen05 CTA pair (tf32 main term + two bf16 correction
  * terms), 4 tcgen05 with the X operand in tensor memory (opt-in), 5 tcgen05 one CTA per tile with the bf16

@@ -112,6 +112,50 @@ def test_baseline_config_shapes_step_and_predict(env, name, n, d, k, init_kind):
     assert abs(inertia.value - ref_in) / ref_in <= 1e-5
 
 
+@pytest.mark.parametrize("n,k", [(100000, 64), (40002, 33), (5000, 8), (131072, 64), (258, 5)])
+@pytest.mark.parametrize("init_kind", ["parity", "throughput"])
+def test_fused_e_m_step_short_rows(env, n, k, init_kind):
+    # n_features = 16, k <= 64, unweighted, even n: ONE kernel does distance + argmin + centroid sums / counts
+    # (fused_l2_argmin_solo_kernel<.., MSTEP>); it is taken when the caller does not ask for the per-step inertia
+    # (sums_out == NULL), as the Lloyd loop of fit does.  Three consecutive steps against the oracle.
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    from oracle import blobs, lloyd
+    d = 16
+    X, centres, _ = blobs.make_blobs(n, d, k)
+    C_o = (blobs.parity_init(centres) if init_kind == "parity" else blobs.throughput_init(X, k)).astype(np.float32)
+    Xd = torch.from_numpy(X).cuda()
+    Cd = torch.from_numpy(C_o.copy()).cuda()
+    labels = torch.zeros(n, dtype=torch.int32, device="cuda")
+    shift = torch.zeros(1, dtype=torch.float64, device="cuda")
+    for _ in range(3):
+        C_in = Cd.cpu().numpy().copy()
+        torch.cuda.synchronize()
+        _lib.check(lib.cuml_b200_kmeans_lloyd_step_f32(h.ptr, Xd.data_ptr(), n, d, None, k, Cd.data_ptr(), labels.data_ptr(),
+                                                       None, shift.data_ptr(), 0))
+        h.sync()
+        lab = labels.cpu().numpy()
+        agree, bad = lloyd.label_disagreements_ok(X, C_in, lab, FP32_GAP_TOL)
+        assert agree >= 0.9999 and bad == 0, (agree, bad)
+        S, W, C_ref = lloyd.m_step(X, lab.astype(np.int64), k, C_old=C_in)
+        got = Cd.cpu().numpy()
+        assert np.abs(got - C_ref).max() / np.abs(C_ref).max() < 1e-6
+        shift_o = float(((C_ref - C_in.astype(np.float64)) ** 2).sum())
+        assert abs(float(shift.item()) - shift_o) <= 1e-4 * max(shift_o, 1e-12)
+
+
+def test_fused_e_m_fit_matches_oracle_d16():
+    # end to end through the estimator at the C5 shape (d = 16, k = 64): the Lloyd loop runs on the fused E + M kernel
+    from cuml_b200.cluster import KMeans
+    from oracle import blobs, lloyd
+    X, centres, _ = blobs.make_blobs(120000, 16, 64)
+    init = blobs.parity_init(centres)
+    km = KMeans(n_clusters=64, init=init, max_iter=8, tol=0.0, n_init=1).fit(X)
+    ref = lloyd.fit(X, init, max_iter=8, tol=0.0)
+    assert (km.labels_ == ref["labels"]).mean() >= 0.9999
+    assert abs(km.inertia_ - ref["inertia"]) / ref["inertia"] <= 1e-5
+    assert np.abs(km.cluster_centers_ - ref["centroids"]).max() / np.abs(ref["centroids"]).max() <= 1e-4
+
+
 @pytest.mark.parametrize("engine", [1, 2])
 def test_regime2_step_matches_oracle(env, engine):
     # throughput init (several centroids per blob): single-step check only
