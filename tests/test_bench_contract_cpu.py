@@ -41,7 +41,10 @@ def test_committed_bench_lines_keep_the_contract(path):
     r = j["roofline"]
     assert r["bound"] in ("hbm", "tensor") and r["unit"] == ("GB/s" if r["bound"] == "hbm" else "TFLOP/s")
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    n, d, k = j["config"]["rows_per_gpu"], j["config"]["d"], j["config"]["k"]
+    # round 1 kept the per-run facts (rows per GPU, engine, communicator) in `config`; since round 2 `config` names the
+    # workload only (same at every N, so the driver's same_config check holds) and the rest lives in `run`
+    rows = j["config"]["rows_per_gpu"] if "rows_per_gpu" in j["config"] else j["run"]["rows_per_gpu"]
+    n, d, k = rows, j["config"]["d"], j["config"]["k"]
     # achieved = algorithmic work per launch (2nkd flop, 4nd + 4n bytes) / measured launch duration
     assert r["algorithmic_flops_per_launch"] == 2.0 * n * k * d and r["algorithmic_bytes_per_launch"] == 4.0 * n * d + 4.0 * n
     work = r["algorithmic_flops_per_launch"] / 1e12 if r["bound"] == "tensor" else r["algorithmic_bytes_per_launch"] / 1e9
@@ -63,7 +66,8 @@ def test_scaling_series_is_whole_job_throughput():
     assert sorted(by_n) == [1, 2, 4, 8]
     for g, j in by_n.items():
         assert j["scaling"] == "strong" and j["config"]["n"] == 100_000_000     # total work fixed as N grows
-        assert j["config"]["rows_per_gpu"] * g >= j["config"]["n"]
+        rows = j["config"]["rows_per_gpu"] if "rows_per_gpu" in j["config"] else j["run"]["rows_per_gpu"]
+        assert rows * g >= j["config"]["n"]
     assert by_n[8]["value"] / by_n[1]["value"] >= 0.85 * 8                       # the north-star scaling bar
 
 
