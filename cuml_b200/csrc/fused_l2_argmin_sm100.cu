@@ -1255,27 +1255,30 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
       ptx::mbar_wait_park(ptx::smem_u32(&bars->lab_full[sa]), pa);     // ... and so are its labels
       const uint32_t my_word = ms_labels[sa * TILE_M + aw * 32 + lane];
       const uint8_t* xs      = gbase + sa * A_SLOT_BYTES + static_cast<uint32_t>(aw * 32) * 128u;
-#pragma unroll 1
+      // the tile's 32 values of this lane first: they do not depend on the labels, and loading them ahead of the
+      // table updates leaves ONE shared-memory latency (table read) per group of four rows instead of two
+      float xv[32];
+#pragma unroll
+      for (int r = 0; r < 32; ++r)
+        xv[r] = *reinterpret_cast<const float*>(xs + static_cast<uint32_t>(r) * 128u + ((xch ^ (static_cast<uint32_t>(r) & 7u)) << 4) + xin);
+#pragma unroll
       for (int j = 0; j < 32; j += 4) {
         uint32_t lb[4];
-        float xv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const uint32_t w = __shfl_sync(0xffffffffu, my_word, j + u);
-          lb[u]            = half ? (w >> 16) : (w & 0xffffu);
-          const uint32_t r = static_cast<uint32_t>(j + u);   // row within this warp's 32 (aw * 32 is a multiple of 8)
-          xv[u] = *reinterpret_cast<const float*>(xs + r * 128u + ((xch ^ (r & 7u)) << 4) + xin);
+          lb[u]            = (half ? (w >> 16) : (w & 0xffffu)) * 32u;
         }
         const bool clash = lb[0] == lb[1] || lb[0] == lb[2] || lb[0] == lb[3] || lb[1] == lb[2] || lb[1] == lb[3] || lb[2] == lb[3];
         if (!__any_sync(0xffffffffu, clash)) {   // four independent read-modify-write chains
           float tv[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) tv[u] = tab[lb[u] * 32u];
+          for (int u = 0; u < 4; ++u) tv[u] = tab[lb[u]];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) tab[lb[u] * 32u] = tv[u] + xv[u];
+          for (int u = 0; u < 4; ++u) tab[lb[u]] = tv[u] + xv[j + u];
         } else {                                  // two rows of the group share a cluster in some lane: row order
 #pragma unroll
-          for (int u = 0; u < 4; ++u) tab[lb[u] * 32u] += xv[u];
+          for (int u = 0; u < 4; ++u) tab[lb[u]] += xv[j + u];
         }
       }
       __syncwarp();
@@ -2153,7 +2156,10 @@ bool tc_best_supported(const Handle& h, int d, int k)
 // fused E + M step (see mstep_smem_bytes): the plan of the row-packed single-CTA kernel with room for the tables
 static bool plan_fused_mstep(const Handle& h, int d, int k, TilePlan& t_out, size_t& smem_out)
 {
-  static const bool on = env_flag("CUML_B200_FUSED_MSTEP", true);
+  // opt-in (CUML_B200_FUSED_MSTEP=1, read per call so that a test can switch it): parity-green, but measured SLOWER than
+  // the two-kernel step at C5 (8.0 ms against 5.1 + 2.1 ms, profiles/README.md): the table updates of the four
+  // accumulate warps add ~48 KB of shared-memory traffic per tile to a kernel that is already bound by it
+  const bool on = env_flag("CUML_B200_FUSED_MSTEP", false);
   const int k_sub = pack_k_sub(d, k);
   if (!on || d != 16 || k_sub == 0 || k_sub > 64 || !use_solo_v2() || !use_bf16_corrections() || !use_epi_rowown() || !use_cn_fold())
     return false;

@@ -114,10 +114,12 @@ def test_baseline_config_shapes_step_and_predict(env, name, n, d, k, init_kind):
 
 @pytest.mark.parametrize("n,k", [(100000, 64), (40002, 33), (5000, 8), (131072, 64), (258, 5)])
 @pytest.mark.parametrize("init_kind", ["parity", "throughput"])
-def test_fused_e_m_step_short_rows(env, n, k, init_kind):
+def test_fused_e_m_step_short_rows(env, n, k, init_kind, monkeypatch):
     # n_features = 16, k <= 64, unweighted, even n: ONE kernel does distance + argmin + centroid sums / counts
     # (fused_l2_argmin_solo_kernel<.., MSTEP>); it is taken when the caller does not ask for the per-step inertia
     # (sums_out == NULL), as the Lloyd loop of fit does.  Three consecutive steps against the oracle.
+    # Opt-in since it measured slower than the two-kernel step (CUML_B200_FUSED_MSTEP is read per call).
+    monkeypatch.setenv("CUML_B200_FUSED_MSTEP", "1")
     torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
     from oracle import blobs, lloyd
     d = 16
@@ -145,8 +147,11 @@ def test_fused_e_m_step_short_rows(env, n, k, init_kind):
         assert abs(float(shift.item()) - shift_o) <= 1e-4 * shift_o + floor
 
 
-def test_fused_e_m_fit_matches_oracle_d16():
-    # end to end through the estimator at the C5 shape (d = 16, k = 64): the Lloyd loop runs on the fused E + M kernel
+@pytest.mark.parametrize("fused", ["0", "1"])
+def test_fused_e_m_fit_matches_oracle_d16(fused, monkeypatch):
+    # end to end through the estimator at the C5 shape (d = 16, k = 64): the Lloyd loop on the two-kernel step (default)
+    # and on the opt-in fused E + M kernel
+    monkeypatch.setenv("CUML_B200_FUSED_MSTEP", fused)
     from cuml_b200.cluster import KMeans
     from oracle import blobs, lloyd
     X, centres, _ = blobs.make_blobs(120000, 16, 64)

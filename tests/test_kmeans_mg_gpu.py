@@ -66,7 +66,18 @@ def _worker(rank, world, port, q, init_kind, topology="nccl"):
 @pytest.mark.parametrize("topology", TOPOLOGIES)
 @pytest.mark.parametrize("init_kind", ["array", "k-means||", "random"])
 def test_two_rank_fit_matches_single_gpu(init_kind, topology):
-    _need(topology, 2)
+    _fit_ranks_match_single_gpu(2, init_kind, topology)
+
+
+@pytest.mark.parametrize("world,topology", [(4, "peer"), (4, "nccl"), (8, "peer"), (8, "nccl")])
+@pytest.mark.parametrize("init_kind", ["array", "k-means||"])
+def test_many_rank_fit_matches_single_gpu(init_kind, world, topology):
+    # the reference's MG gtest runs on however many ranks the communicator has (kmeans_test.cu:116-137); one rank per GPU
+    _fit_ranks_match_single_gpu(world, init_kind, topology)
+
+
+def _fit_ranks_match_single_gpu(world, init_kind, topology):
+    _need(topology, world)
     import torch.multiprocessing as mp
     from cuml_b200.cluster import KMeans
     from oracle import blobs, lloyd
@@ -74,7 +85,8 @@ def test_two_rank_fit_matches_single_gpu(init_kind, topology):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, init_kind, topology), daemon=True) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, init_kind, topology), daemon=True)
+             for r in range(world)]
     for p in procs:
         p.start()
     try:
@@ -88,9 +100,10 @@ def test_two_rank_fit_matches_single_gpu(init_kind, topology):
                 p.kill()
     n, d, k = 40000, 32, 16
     X, centres, true = blobs.make_blobs(n, d, k)
-    assert np.array_equal(outs[0][1], outs[1][1])  # identical centroids on every rank
-    labels = np.concatenate([outs[0][4], outs[1][4]])
-    total_inertia = outs[0][2] + outs[1][2]
+    for o in outs[1:]:
+        assert np.array_equal(outs[0][1], o[1])    # identical centroids on every rank
+    labels = np.concatenate([o[4] for o in outs])
+    total_inertia = sum(o[2] for o in outs)
     assert abs(total_inertia - outs[0][3]) / outs[0][3] < 1e-5
     if init_kind == "array":
         ref = lloyd.fit(X, blobs.parity_init(centres), max_iter=10, tol=0.0)
@@ -138,7 +151,7 @@ def _dist_worker(rank, world, port, q, topology="nccl"):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,topology", [(1, "nccl"), (2, "shared"), (2, "peer"), (2, "nccl")])
+@pytest.mark.parametrize("world,topology", [(1, "nccl"), (2, "shared"), (2, "peer"), (2, "nccl"), (8, "peer"), (8, "nccl")])
 def test_distributed_estimator(world, topology):
     _need(topology, world)
     import torch.multiprocessing as mp
@@ -187,13 +200,13 @@ def test_distributed_estimator(world, topology):
 
 
 # ---- the reference's multi-GPU gtest inputs through the C++ surface (examples/kmeans_mg_test.cpp) ---------------------
-@pytest.mark.parametrize("mode", ["shared", "peer", "nccl"])
-def test_cpp_mg_gtest_inputs_two_ranks(tmp_path, mode):
+@pytest.mark.parametrize("ranks,mode", [(2, "shared"), (2, "peer"), (2, "nccl"), (8, "peer"), (8, "nccl")])
+def test_cpp_mg_gtest_inputs_rank_processes(tmp_path, ranks, mode):
     # cpp/tests/mg/kmeans_test.cu:50-195: eight inputs, float and double, weighted and not, ARI >= 0.99 on every rank's
-    # shard -- here with TWO rank processes ("shared": both on device 0 over the peer-memory communicator)
+    # shard -- here with 2 or 8 rank processes ("shared": both on device 0 over the peer-memory communicator)
     import shutil
     import subprocess
-    _need(mode, 2)
+    _need(mode, ranks)
     from cuml_b200 import build
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     gxx = shutil.which("g++")
@@ -205,5 +218,5 @@ def test_cpp_mg_gtest_inputs_two_ranks(tmp_path, mode):
            os.path.join(root, "examples", "kmeans_mg_test.cpp"), "-L" + libdir, "-lcuml_b200",
            "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + libdir, "-o", exe]
     subprocess.run(cmd, check=True, capture_output=True)
-    r = subprocess.run([exe, "2", mode], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([exe, str(ranks), mode], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
