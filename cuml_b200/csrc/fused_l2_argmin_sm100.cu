@@ -142,9 +142,17 @@ struct Barriers {
 // carry the outputs (the parameter block keeps its size): dbg_dots -> partial_S [grid][k][16], cnh -> partial_W [grid][k],
 // raw_slots -> true n_clusters.
 constexpr int MS_ACC_WARPS = 4;
+constexpr int TSP_ACC_WARPS = 8;   // A-in-TMEM kernel: warps 20..27 accumulate (the row-owner epilogue then has 3 groups)
+__host__ __device__ inline size_t tsp_mstep_smem_bytes(int k_sub)
+{
+  return static_cast<size_t>(TSP_ACC_WARPS) * (k_sub + 1) * 32 * sizeof(float)   // private tables (+ a dummy row each)
+         + static_cast<size_t>(k_sub) * 2 * sizeof(int)                           // counts
+         + static_cast<size_t>(MAX_A_SLOTS) * TILE_M * sizeof(uint32_t)           // label words per X slot
+         + 128;
+}
 __host__ __device__ inline size_t mstep_smem_bytes(int k_sub)
 {
-  return static_cast<size_t>(MS_ACC_WARPS) * k_sub * 32 * sizeof(float)   // private tables
+  return static_cast<size_t>(MS_ACC_WARPS) * (k_sub + 1) * 32 * sizeof(float)   // private tables (+ a dummy row each)
          + static_cast<size_t>(k_sub) * 2 * sizeof(int)                   // counts (both packed groups share them)
          + static_cast<size_t>(MAX_A_SLOTS) * TILE_M * sizeof(uint32_t)   // label words per slot
          + 128;
@@ -390,7 +398,7 @@ template <bool FOLD1, bool MSTEP = false>
 __device__ __forceinline__ void epilogue_role_rowown(const FusedParams& p, Barriers* bars, float* cn_s,
                                                      uint32_t tmem_base, int64_t first_row, int64_t row_stride,
                                                      int64_t n_tiles_cta, uint32_t* ms_labels = nullptr,
-                                                     int* ms_counts = nullptr)
+                                                     int* ms_counts = nullptr, int x_slots = 0, int lab_shift = 0)
 {
   const int et      = threadIdx.x - 256;      // 0..511
   const int ew      = et >> 5;                // epilogue warp 0..15
@@ -405,11 +413,17 @@ __device__ __forceinline__ void epilogue_role_rowown(const FusedParams& p, Barri
     if (et < p.bn) cn_s[et] = __ldg(p.cnh + et);
     ptx::named_bar_sync(1, EPI_THREADS);
   }
-  Ring racc;                  // accumulator stage of tile t: t % n_acc, phase (t / n_acc) & 1 (n_acc >= 4 here)
-  racc.slot = static_cast<uint32_t>(group);
-  Ring rslot;                 // MSTEP: X slot of tile t (one K-block per tile): t % a_slots
-  if (MSTEP) rslot.advance_by(static_cast<uint32_t>(group), p.a_slots);
-  for (int64_t t = group; t < n_tiles_cta; t += 4, racc.advance_by(4, p.n_acc)) {
+  // A group must see EVERY phase of an accumulator barrier it waits on (a parity wait cannot tell phase k from k + 2),
+  // so the number of groups divides the ring: 4 groups when n_acc >= 4 (a multiple of 4 or exactly 4..8 stages walked
+  // with stride 4 -- n_acc is then 4 or 8), otherwise one group per accumulator stage and the remaining warps idle
+  const int n_groups = p.n_acc >= 4 ? 4 : p.n_acc;
+  if (group >= n_groups) return;
+  Ring racc;                  // accumulator stage of tile t: t % n_acc, phase (t / n_acc) & 1
+  racc.advance_by(static_cast<uint32_t>(group), p.n_acc);
+  const uint32_t xs_n = static_cast<uint32_t>(x_slots > 0 ? x_slots : p.a_slots);
+  Ring rslot;                 // MSTEP: X slot of tile t (one K-block per tile): t % (X ring depth)
+  if (MSTEP) rslot.advance_by(static_cast<uint32_t>(group), xs_n);
+  for (int64_t t = group; t < n_tiles_cta; t += n_groups, racc.advance_by(n_groups, p.n_acc)) {
     const uint32_t acc = racc.slot, pacc = racc.phase;
     ptx::mbar_wait_park(ptx::smem_u32(&bars->acc_full[acc]), pacc);
     ptx::tc_fence_after();
@@ -458,7 +472,7 @@ __device__ __forceinline__ void epilogue_role_rowown(const FusedParams& p, Barri
       const int64_t row = (first_row + t * row_stride + rit) * p.pack + g;
       if (row < p.n) p.labels[row] = i0;
       if (MSTEP) {
-        lab_word |= static_cast<uint32_t>(i0) << (16 * g);
+        lab_word |= (static_cast<uint32_t>(i0) << lab_shift) << (16 * g);   // label, or its table-row byte offset
         if (row < p.n) atomicAdd(ms_counts + i0, 1);   // integer: exact and order-independent
       }
     }
@@ -469,7 +483,7 @@ __device__ __forceinline__ void epilogue_role_rowown(const FusedParams& p, Barri
       ms_labels[rslot.slot * TILE_M + rit] = lab_word;
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->lab_full[rslot.slot]));   // release: the words above are visible
-      rslot.advance_by(4, p.a_slots);
+      rslot.advance_by(n_groups, xs_n);
     }
   }
 }
@@ -1745,6 +1759,283 @@ fused_l2_argmin_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
   }
 }
 
+// =================================================================================================
+// Row-packed small-d kernel with the X operand in tensor memory (n_features = 16: two data rows per operand row,
+// block-diagonal centroid operands, one accumulator tile of BN = 2 k_sub <= 128 columns, centroids resident).
+// Why: the shared-memory twin above is bound by shared-memory bandwidth at this shape (profiles/
+// r02_role_skip_experiments.txt) -- per 256-data-row tile its nine MMAs fetch 72 KB of operands and the converter
+// writes 16 KB of bf16 tiles next to the 16 KB TMA writes and the 16 KB converter reads.  Here the converter (thread =
+// operand row, one warp per TMEM lane quarter) writes the raw fp32 words (the tensor core truncates them to tf32) and
+// the bf16 hi / lo pairs of its row straight into 64 TMEM columns (tcgen05.st), the eight data MMAs read A from
+// tensor memory (N/2-cycle floor instead of 43 + N/2, tools/micro/mma_rate.cu) and only B (4 KB each) from shared
+// memory; the -1/2||c||^2 fold stays a shared-memory MMA of the ones tile.  The raw X tiles ride a deep ring of 16 KB
+// slots.  TMEM: n_acc accumulators of BN columns, then two 64-column operand stages [raw 32 | bf16 hi 16 | bf16 lo 16].
+// MSTEP: the fused M-step of the twin (accumulate warps 24..27 add the raw tile into private tables once the
+// row-owner epilogue has published the tile's labels; the slot's empty barrier counts converter and accumulate warps).
+// In MSTEP mode idle parameter fields carry the outputs: dbg_dots -> partial_S, cnh -> partial_W, a_stream -> true k.
+template <bool MSTEP>
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+fused_l2_argmin_tsp_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
+                           const __grid_constant__ CUtensorMap tm_hb, const __grid_constant__ CUtensorMap tm_lb,
+                           const __grid_constant__ CUtensorMap tm_cn, const FusedParams p)
+{
+  extern __shared__ uint8_t smem_dyn[];
+  const uint32_t raw_base = ptx::smem_u32(smem_dyn);
+  const uint32_t base     = (raw_base + 1023u) & ~1023u;
+  uint8_t* gbase          = smem_dyn + (base - raw_base);
+
+  const int64_t cta    = blockIdx.x;
+  const int64_t n_ctas = gridDim.x;
+  const int64_t tiles  = p.m_tiles;                                      // tiles of 128 operand rows (256 data rows)
+
+  const uint32_t x_base   = base;                                        // raw ring, 16 KB slots
+  const uint32_t b_off    = static_cast<uint32_t>(p.raw_slots) * KBLOCK_BYTES;
+  const uint32_t b_base   = base + b_off;                                // tf32 hi [bn x 128 B] | bf16 hi [bn x 64 B] | bf16 lo
+  const uint32_t b_hi_sz  = static_cast<uint32_t>(p.bn) * 128u;
+  constexpr uint32_t FOLD_TILE = TILE_M * 32u;                           // ones [128 x 8 tf32], then the half-norm pieces
+  const uint32_t fold_off = b_off + 2u * b_hi_sz;
+  const uint32_t fold_u32 = base + fold_off;
+  Barriers* bars          = reinterpret_cast<Barriers*>(gbase + fold_off + 2u * FOLD_TILE);
+  float* ms_tab           = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ((sizeof(Barriers) + 127) & ~size_t(127)));
+  const int ms_rows       = p.k_sub + 1;   // private table rows per accumulate warp: k_sub clusters + one dummy row
+  int* ms_counts          = reinterpret_cast<int*>(ms_tab + static_cast<size_t>(TSP_ACC_WARPS) * ms_rows * 32);
+  uint32_t* ms_labels     = reinterpret_cast<uint32_t*>(ms_counts + 2 * p.k_sub);
+
+  const int warp = threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < MAX_RAW; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->raw_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->raw_empty[s]), MSTEP ? 4 + TSP_ACC_WARPS : 4);   // converter (+ accumulate) warps
+    }
+    for (int s = 0; s < MAX_A_SLOTS; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->a_ready[s]), 4);                  // the 4 converter warps
+      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), 1);                  // MMA commit
+      ptx::mbar_init(ptx::smem_u32(&bars->lab_full[s]), 4);                 // the 4 epilogue warps of a tile's group
+    }
+    for (int s = 0; s < MAX_ACC; ++s) {
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 4);               // row-owner epilogue: 4 warps per tile
+    }
+    ptx::mbar_init(ptx::smem_u32(&bars->b_full[0]), 1);
+    ptx::mbar_init(ptx::smem_u32(&bars->cn_full), 1);
+    ptx::fence_barrier_init();
+  }
+  {   // all-ones A tile of the fold MMA (identical 16-byte chunks: the 32B swizzle does not matter)
+    float* ones = reinterpret_cast<float*>(gbase + fold_off);
+    for (int i = threadIdx.x; i < TILE_M * 8; i += blockDim.x) ones[i] = 1.0f;
+    ptx::fence_proxy_async_smem();
+  }
+  if (MSTEP) {
+    for (int i = threadIdx.x; i < TSP_ACC_WARPS * ms_rows * 32 + 2 * p.k_sub; i += blockDim.x) ms_tab[i] = 0.0f;   // tables + counts
+  }
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tm_x);
+    ptx::prefetch_tmap(&tm_hi);
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== raw X producer =====================
+    Ring rr;
+    for (int64_t t = cta; t < tiles; t += n_ctas) {
+      const int32_t row0 = static_cast<int32_t>(t * TILE_M);
+      const uint32_t rs = rr.slot, rp = rr.phase;
+      rr.advance(p.raw_slots);
+      ptx::mbar_wait_park(ptx::smem_u32(&bars->raw_empty[rs]), rp ^ 1u);
+      if (ptx::elect_one()) {
+        const uint32_t full = ptx::smem_u32(&bars->raw_full[rs]);
+        ptx::mbar_arrive_expect_tx(full, KBLOCK_BYTES);
+        ptx::tma_load_2d_hint(x_base + rs * KBLOCK_BYTES, &tm_x, 0, row0, full, ptx::kEvictFirst);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 2) {
+    // ===================== centroid operands + half-norm pieces: once, resident =====================
+    if (cta < tiles && ptx::elect_one()) {
+      const uint32_t bfull = ptx::smem_u32(&bars->b_full[0]);
+      ptx::mbar_arrive_expect_tx(bfull, 2u * b_hi_sz);
+      ptx::tma_load_2d_hint(b_base, &tm_hi, 0, 0, bfull, ptx::kEvictLast);
+      ptx::tma_load_2d_hint(b_base + b_hi_sz, &tm_hb, 0, 0, bfull, ptx::kEvictLast);
+      ptx::tma_load_2d_hint(b_base + b_hi_sz + b_hi_sz / 2, &tm_lb, 0, 0, bfull, ptx::kEvictLast);
+      const uint32_t cfull = ptx::smem_u32(&bars->cn_full);
+      ptx::mbar_arrive_expect_tx(cfull, static_cast<uint32_t>(p.bn) * 32u);
+      ptx::tma_load_2d_hint(fold_u32 + FOLD_TILE, &tm_cn, 0, 0, cfull, ptx::kEvictLast);
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== converter: operand row (shared) -> raw | bf16 hi | bf16 lo columns (tensor memory) ======
+    const int quarter        = warp & 3;
+    const int row            = quarter * 32 + lane;                     // operand row of the tile == TMEM lane
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    Ring rr, ra;
+    for (int64_t t = cta; t < tiles; t += n_ctas) {
+      const uint32_t rs = rr.slot, rp = rr.phase;
+      rr.advance(p.raw_slots);
+      const uint32_t as = ra.slot, ap = ra.phase;
+      ra.advance(p.a_slots);
+      ptx::mbar_wait_park(ptx::smem_u32(&bars->raw_full[rs]), rp);
+      ptx::mbar_wait_park(ptx::smem_u32(&bars->a_empty[as]), ap ^ 1u);   // the MMAs that read this operand stage retired
+      ptx::tc_fence_after();
+      const uint4* src    = reinterpret_cast<const uint4*>(gbase + rs * KBLOCK_BYTES + row * 128);
+      const uint32_t acol = tmem_base + lane_addr + p.a_col0 + as * 64;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {   // 16 features (one data row of the packed pair) at a time: registers
+        uint32_t w[16], hb[8], lb[8];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 v = src[(hf * 4 + c) ^ (row & 7)];                  // 128B swizzle: chunk ^= row & 7
+          w[c * 4 + 0] = v.x; w[c * 4 + 1] = v.y; w[c * 4 + 2] = v.z; w[c * 4 + 3] = v.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float x0 = __uint_as_float(w[2 * e]), x1 = __uint_as_float(w[2 * e + 1]);
+          const float h0 = __uint_as_float(w[2 * e] & 0xffffe000u), h1 = __uint_as_float(w[2 * e + 1] & 0xffffe000u);
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);        // .x (low half) = the lower k
+          const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+          hb[e] = *reinterpret_cast<const uint32_t*>(&hh);
+          lb[e] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        ptx::tmem_st_32x16(acol + hf * 16, w);
+        ptx::tmem_st_32x8(acol + 32 + hf * 8, hb);
+        ptx::tmem_st_32x8(acol + 48 + hf * 8, lb);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(ptx::smem_u32(&bars->raw_empty[rs]));           // converter is done with the raw slot
+        ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready[as]));
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    const uint32_t idesc   = ptx::umma_idesc_tf32(TILE_M, p.bn);
+    const uint32_t idesc16 = ptx::umma_idesc_bf16(TILE_M, p.bn);
+    const uint64_t db_hi   = ptx::umma_desc_sw128(b_base);
+    const uint64_t db_hb   = ptx::umma_desc_sw64(b_base + b_hi_sz);
+    const uint64_t db_lb   = ptx::umma_desc_sw64(b_base + b_hi_sz + b_hi_sz / 2);
+    const uint64_t d_ones  = ptx::umma_desc_sw32(fold_u32);
+    const uint64_t d_cn    = ptx::umma_desc_sw32(fold_u32 + FOLD_TILE);
+    Ring ra, racc;
+    bool tf_first = true;   // a change of MMA kind costs the tensor pipe: every tile starts with the kind the last one ended on
+    if (cta < tiles) {
+      ptx::mbar_wait_park(ptx::smem_u32(&bars->b_full[0]), 0u);
+      ptx::mbar_wait_park(ptx::smem_u32(&bars->cn_full), 0u);
+    }
+    for (int64_t t = cta; t < tiles; t += n_ctas, tf_first = !tf_first) {
+      const uint32_t acc = racc.slot, pacc = racc.phase;
+      racc.advance(p.n_acc);
+      const uint32_t as = ra.slot, ap = ra.phase;
+      ra.advance(p.a_slots);
+      ptx::mbar_wait_park(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
+      ptx::mbar_wait_park(ptx::smem_u32(&bars->a_ready[as]), ap);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * p.bn;
+      const uint32_t a_raw  = tmem_base + p.a_col0 + as * 64;
+      const uint32_t a_hb   = a_raw + 32, a_lb = a_raw + 48;
+      if (ptx::elect_one()) {
+        uint32_t acc_on = 0u;
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          if ((ph == 0) == tf_first) {   // fold + tf32 main term
+            ptx::mma_tf32_ss(d_tmem, d_ones, d_cn, idesc, acc_on);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              ptx::mma_tf32_ts(d_tmem, a_raw + ks * 8, db_hi + static_cast<uint64_t>(ks * 2), idesc, 1u);
+            acc_on = 1u;
+          } else {                        // the two bf16 correction terms (K = 16: 8 TMEM columns of A, 32 bytes of B)
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+              ptx::mma_f16_ts(d_tmem, a_lb + ks * 8, db_hb + static_cast<uint64_t>(ks * 2), idesc16, acc_on);
+              ptx::mma_f16_ts(d_tmem, a_hb + ks * 8, db_lb + static_cast<uint64_t>(ks * 2), idesc16, 1u);
+              acc_on = 1u;
+            }
+          }
+        }
+        ptx::mma_commit(ptx::smem_u32(&bars->a_empty[as]));
+        ptx::mma_commit(ptx::smem_u32(&bars->acc_full[acc]));
+      }
+      __syncwarp();
+    }
+  } else if (MSTEP && warp >= 20) {
+    // ===================== fused M-step: accumulate warps 20..27 (16 operand rows of every tile each) ===============
+    const int aw         = warp - 20;
+    // lane = (data row of the packed pair, column): lane l only ever touches bank l of its warp's private table
+    uint8_t* tab         = reinterpret_cast<uint8_t*>(ms_tab + static_cast<size_t>(aw) * ms_rows * 32 + lane);
+    const uint32_t sel   = (lane >> 4) ? 0x4432u : 0x4410u;                        // byte_perm selector: this half's 16 bits
+    const uint32_t xch   = static_cast<uint32_t>(lane >> 2);                       // logical 16-byte chunk of the lane's float
+    const uint32_t xin   = static_cast<uint32_t>(lane & 3) * 4u;
+    const uint32_t dummy = static_cast<uint32_t>(p.k_sub) * 128u;                  // byte offset of the row nobody reads
+    Ring rr;
+    for (int64_t t = cta; t < tiles; t += n_ctas) {
+      const uint32_t rs = rr.slot, rp = rr.phase;
+      rr.advance(p.raw_slots);
+      ptx::mbar_wait_park(ptx::smem_u32(&bars->raw_full[rs]), rp);     // the raw tile (async-proxy writes) is visible
+      ptx::mbar_wait_park(ptx::smem_u32(&bars->lab_full[rs]), rp);     // ... and so are its labels
+      const uint32_t* lw = ms_labels + rs * TILE_M + aw * 16;          // (offset of row 2r's cluster | row 2r+1's << 16)
+      const uint8_t* xs  = gbase + rs * KBLOCK_BYTES + static_cast<uint32_t>(aw * 16) * 128u;
+      // Two operand rows per step, branch-free: when both rows (in this lane's half) belong to one cluster the second is
+      // folded into the first in registers and its own update is pointed at the dummy row, so the two table
+      // read-modify-writes of a step never alias (loads, adds, stores; ~10 instructions per row).  The kernel is bound
+      // by instruction issue, so the count matters more than the latency of the chain.
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const uint32_t l0 = __byte_perm(lw[j], 0u, sel), w1 = __byte_perm(lw[j + 1], 0u, sel);   // broadcast loads
+        const uint32_t r0 = static_cast<uint32_t>(j), r1 = r0 + 1u;
+        const float x0 = *reinterpret_cast<const float*>(xs + r0 * 128u + ((xch ^ (r0 & 7u)) << 4) + xin);
+        const float x1 = *reinterpret_cast<const float*>(xs + r1 * 128u + ((xch ^ (r1 & 7u)) << 4) + xin);
+        const bool dup    = w1 == l0;
+        const float a0    = x0 + (dup ? x1 : 0.0f);
+        const uint32_t l1 = dup ? dummy : w1;
+        float* p0 = reinterpret_cast<float*>(tab + l0);
+        float* p1 = reinterpret_cast<float*>(tab + l1);
+        const float t0 = *p0, t1 = *p1;
+        *p0 = t0 + a0;
+        *p1 = t1 + x1;
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->raw_empty[rs]));
+    }
+  } else if (warp >= 8 && warp < 24) {
+    // ===================== row-owner epilogue =====================
+    const int64_t n_mine = (tiles > cta) ? (tiles - cta + n_ctas - 1) / n_ctas : 0;
+    epilogue_role_rowown<true, MSTEP>(p, bars, nullptr, tmem_base, cta * TILE_M, n_ctas * TILE_M, n_mine, ms_labels, ms_counts,
+                                      p.raw_slots, 7);   // label words carry byte offsets of 128-byte table rows
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+  if (MSTEP) {
+    // fold the private tables in a fixed order (accumulate warp 0..7, packed group 0 then 1) into this CTA's partials
+    const int k_true = p.a_stream;
+    float* out_S     = p.dbg_dots + static_cast<size_t>(blockIdx.x) * k_true * 16;
+    float* out_W     = const_cast<float*>(p.cnh) + static_cast<size_t>(blockIdx.x) * k_true;
+    for (int e = threadIdx.x; e < k_true * 16; e += blockDim.x) {
+      const int j = e >> 4, c = e & 15;
+      float acc = 0.0f;
+#pragma unroll
+      for (int w = 0; w < TSP_ACC_WARPS; ++w) {
+        const float* tw = ms_tab + (static_cast<size_t>(w) * ms_rows + j) * 32;
+        acc += tw[c];
+        acc += tw[16 + c];
+      }
+      out_S[e] = acc;
+    }
+    for (int j = threadIdx.x; j < k_true; j += blockDim.x) out_W[j] = static_cast<float>(ms_counts[j]);
+  }
+}
+
 // hi/lo split + half norms of the centroids into padded operand buffers
 __global__ void prepare_centroids_kernel(const float* __restrict__ C, int k, int d, int k_pad, int d_pad,
                                          float* __restrict__ hi, float* __restrict__ lo, float* __restrict__ cnh,
@@ -2153,13 +2444,40 @@ bool tc_best_supported(const Handle& h, int d, int k)
   return h.cc_major == 10 && tc_supported(d, k) && !use_ts(h, d, k);
 }
 
+// ---- row-packed kernel with the X operand in tensor memory (fused_l2_argmin_tsp_kernel) ------------------------------
+// CUML_B200_TSP (read per call so that a test can switch it).
+static bool use_tsp() { return env_flag("CUML_B200_TSP", true); }
+// fused M-step: on by default with the tensor-memory kernel (C5: 4.6 ms per Lloyd step against 3.7 + 2.1 ms for the two
+// kernels); with CUML_B200_TSP=0 the shared-memory twin takes it, where it measured slower (8.0 ms against 5.1 + 2.1 ms)
+static bool fused_mstep_on() { return env_flag("CUML_B200_FUSED_MSTEP", use_tsp()); }
+
+struct TspPlan {
+  int raw_slots, n_acc, a_col0;
+  size_t smem;
+};
+static bool plan_tsp(const Handle& h, int d, int k, bool mstep, TspPlan& out)
+{
+  const int k_sub = pack_k_sub(d, k);
+  if (h.cc_major != 10 || k_sub == 0 || k_sub > 64 || !use_bf16_corrections() || !use_cn_fold()) return false;
+  if (mstep && d != 16) return false;
+  const int bn       = 2 * k_sub;
+  const size_t fixed = static_cast<size_t>(bn) * 256 + 2 * static_cast<size_t>(TILE_M) * 32 +
+                       ((sizeof(Barriers) + 127) & ~size_t(127)) + (mstep ? tsp_mstep_smem_bytes(k_sub) : 0) + 1024;
+  if (h.smem_optin < fixed + 3 * static_cast<size_t>(KBLOCK_BYTES)) return false;
+  out.raw_slots = static_cast<int>(std::min<size_t>(mstep ? MAX_A_SLOTS : MAX_RAW, (h.smem_optin - fixed) / KBLOCK_BYTES));
+  out.n_acc     = std::min(mstep ? 3 : 4, (512 - 128) / bn);   // fused M-step: warps 20..23 accumulate, 3 epilogue groups
+  out.a_col0    = out.n_acc * bn;
+  out.smem      = fixed + static_cast<size_t>(out.raw_slots) * KBLOCK_BYTES;
+  return true;
+}
+
 // fused E + M step (see mstep_smem_bytes): the plan of the row-packed single-CTA kernel with room for the tables
 static bool plan_fused_mstep(const Handle& h, int d, int k, TilePlan& t_out, size_t& smem_out)
 {
-  // opt-in (CUML_B200_FUSED_MSTEP=1, read per call so that a test can switch it): parity-green, but measured SLOWER than
-  // the two-kernel step at C5 (8.0 ms against 5.1 + 2.1 ms, profiles/README.md): the table updates of the four
-  // accumulate warps add ~48 KB of shared-memory traffic per tile to a kernel that is already bound by it
-  const bool on = env_flag("CUML_B200_FUSED_MSTEP", false);
+  // opt-in (CUML_B200_FUSED_MSTEP=1, read per call so that a test can switch it): parity-green, but on the shared-memory
+  // operand kernel measured SLOWER than the two-kernel step at C5 (8.0 ms against 5.1 + 2.1 ms, profiles/README.md): the
+  // table updates of the four accumulate warps add ~48 KB of shared-memory traffic per tile to a kernel already bound by it
+  const bool on = fused_mstep_on();
   const int k_sub = pack_k_sub(d, k);
   if (!on || d != 16 || k_sub == 0 || k_sub > 64 || !use_solo_v2() || !use_bf16_corrections() || !use_epi_rowown() || !use_cn_fold())
     return false;
@@ -2177,6 +2495,8 @@ bool tc_fused_update_supported(const Handle& h, int d, int k)
 {
   TilePlan t;
   size_t smem;
+  TspPlan tp;
+  if (h.cc_major == 10 && fused_mstep_on() && use_tsp() && plan_tsp(h, d, k, true, tp)) return true;
   return h.cc_major == 10 && plan_fused_mstep(h, d, k, t, smem);
 }
 
@@ -2230,7 +2550,41 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
       TilePlan tf;
       size_t smem_f = 0;
-      if (mstep && cen.bf16c && cen.fold && !best_out && (n & 1) == 0 && plan_fused_mstep(h, d, k, tf, smem_f)) {
+      TspPlan tp{};
+      const bool tsp_mstep = mstep && (n & 1) == 0 && fused_mstep_on();
+      if (use_tsp() && cen.bf16c && cen.fold && !best_out && plan_tsp(h, d, k, tsp_mstep, tp)) {
+        // ---- X operand in tensor memory (fused_l2_argmin_tsp_kernel), optionally with the fused M-step ----
+        p.raw_slots = tp.raw_slots; p.a_slots = 2; p.n_acc = tp.n_acc; p.a_col0 = tp.a_col0; p.tmem_cols = 512;
+        p.fold = 1; p.b_resident = 1; p.b_stages = 1;
+        if (tsp_mstep) {
+          if (mstep->partial_S->n < static_cast<size_t>(grid) * k * d) mstep->partial_S->alloc(static_cast<size_t>(grid) * k * d, h.stream);
+          if (mstep->partial_W->n < static_cast<size_t>(grid) * k) mstep->partial_W->alloc(static_cast<size_t>(grid) * k, h.stream);
+          p.dbg_dots = mstep->partial_S->get();   // idle fields carry the M-step outputs (see the kernel's header)
+          p.cnh      = mstep->partial_W->get();
+          p.a_stream = k;
+        }
+        CUtensorMap tm_hb = make_map_2d(cen.hb.get(), KBLOCK, cen.k_pad, static_cast<uint64_t>(KBLOCK) * 2, KBLOCK, t.bn,
+                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        CUtensorMap tm_lb = make_map_2d(cen.lb.get(), KBLOCK, cen.k_pad, static_cast<uint64_t>(KBLOCK) * 2, KBLOCK, t.bn,
+                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+        CUtensorMap tm_cn = make_map_2d(cen.cnp.get(), 8, cen.k_pad, 8 * sizeof(float), 8, t.bn, CU_TENSOR_MAP_SWIZZLE_32B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+        static PerDeviceOnce tsp_attr;
+        tsp_attr.run(h.device, [&] {
+          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_tsp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(h.smem_optin)));
+          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_tsp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(h.smem_optin)));
+        });
+        if (tsp_mstep) {
+          fused_l2_argmin_tsp_kernel<true><<<grid, PAIR_THREADS, tp.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+          mstep->row_blocks = static_cast<int>(grid);
+        } else {
+          fused_l2_argmin_tsp_kernel<false><<<grid, PAIR_THREADS, tp.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+        }
+      } else if (mstep && cen.bf16c && cen.fold && !best_out && (n & 1) == 0 && plan_fused_mstep(h, d, k, tf, smem_f)) {
         // ---- one pass over X: distance + argmin + centroid sums / counts (fused_l2_argmin_solo_kernel<.., MSTEP>) ----
         p.a_slots = tf.a_slots; p.b_stages = tf.b_stages; p.b_resident = tf.b_resident;
         p.fold = 1; p.l2_ahead = 3;
