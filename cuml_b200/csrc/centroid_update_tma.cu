@@ -374,15 +374,13 @@ balance_classes_kernel(const double* __restrict__ W, int k, uint8_t* __restrict_
 //   consumer : owns the table rows of its class.  Walks its perm segment with lane = column: per row one
 //              contiguous table read, add, write; the X segment of the next row and the next list entries are
 //              already in flight.  Two rows per loop iteration (register rotation without moves).
-//   HALF     : n_features == 16 -- a row is 64 bytes, so a warp instruction covers TWO rows of the consumer's
-//              list (lanes 0-15 / 16-31); when both carry the same label the upper half hands its values to
-//              the lower half (one shuffle) and only the lower half updates the table.
-template <int VEC, bool HAS_W, bool HALF = false>
+// (A variant for 64-byte rows -- two list rows per warp instruction -- was parity-green but measured slower than the
+// lane = row kernel at C5, 6.1 against 3.8 ms, and was removed; n_features 4 / 8 / 16 take accumulate_lanecol_kernel.)
+template <int VEC, bool HAS_W>
 __global__ void __launch_bounds__((2 + OWN_NA + OWN_CONS) * 32)
 accumulate_owner_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParams7 p)
 {
-  static_assert(!HALF || VEC == 1, "HALF rows are 16 floats: one float per lane");
-  constexpr int DS        = HALF ? 16 : 32 * VEC;
+  constexpr int DS        = 32 * VEC;
   constexpr uint32_t ROWB = DS * 4;
   extern __shared__ uint8_t smem_dyn[];
   const uint32_t raw  = ptx::smem_u32(smem_dyn);
@@ -571,83 +569,44 @@ accumulate_owner_kernel(const __grid_constant__ CUtensorMap tm_x, const UpdParam
       int j          = (cw & 1) ? static_cast<int>(oo.y) : static_cast<int>(oo.x);
       const int o1   = (cw & 1) ? lds32(offs + cw * 4 + 4) : static_cast<int>(oo.y);
       c_rows += o1 - j;
-      if constexpr (HALF) {
-        // two list entries per instruction: lanes 0-15 take entry j, lanes 16-31 entry j + 1
-        const int half      = lane >> 4;
-        const uint32_t hoff = static_cast<uint32_t>(lane & 15) * 4u;
-        const uint32_t xsh  = base + s * x_bytes + hoff;
-        const uint32_t tabh = tab_u32 + hoff;
-        if (j < o1) {
-          uint32_t e  = static_cast<uint32_t>(lds32(perm + (j + half) * 4));   // past the end: stale, in range
-          float w     = 1.0f;
-          if (HAS_W) w = __int_as_float(lds32(wprm + (j + half) * 4));
-          float x     = __int_as_float(lds32(xsh + (e >> 16) * ROWB));
-          for (; j < o1; j += 2) {
-            const uint32_t en = static_cast<uint32_t>(lds32(perm + (j + 2 + half) * 4));
-            float wn = 1.0f;
-            if (HAS_W) wn = __int_as_float(lds32(wprm + (j + 2 + half) * 4));
-            const float xn = __int_as_float(lds32(xsh + (en >> 16) * ROWB));
-            const bool live   = (j + half) < o1;
-            const uint32_t l  = e & 0xffffu;
-            const uint32_t lo = __shfl_xor_sync(0xffffffffu, l, 16);
-            float v = HAS_W ? x * w : x;
-            const float vo = __shfl_xor_sync(0xffffffffu, v, 16);
-            float wsum = w;
-            if (HAS_W) wsum += __shfl_xor_sync(0xffffffffu, w, 16);
-            const bool same = (j + 1 < o1) && (l == lo);          // both rows of the instruction share a label
-            if (same) v += vo;                                    // (only the lower half stores then)
-            const bool store  = live && !(same && half);
-            const uint32_t ta = tabh + l * ROWB;
-            const float tvv   = __int_as_float(lds32(ta));
-            if (store) asm volatile("st.shared.f32 [%0], %1;" ::"r"(ta), "f"(tvv + v) : "memory");
-            if (HAS_W && counts) {
-              const uint32_t wa = wtab_u32 + l * 4u;
-              const float cur   = __int_as_float(lds32(wa));
-              if (store) asm volatile("st.shared.f32 [%0], %1;" ::"r"(wa), "f"(cur + (same ? wsum : w)) : "memory");
-            }
-            e = en; w = wn; x = xn;
-          }
-        }
-      } else {
-      VecIO<VEC> x0, x1, tv;
-      // apply one row: table row of label (e & 0xffff) += w * x
-      auto apply = [&](uint32_t e, const VecIO<VEC>& x, float w, auto&& between) {
-        const uint32_t l  = e & 0xffffu;
-        const uint32_t ta = tab_me + l * ROWB;
-        tv.load(ta);
-        float cur = 0.0f;
-        if (HAS_W && counts) cur = __int_as_float(lds32(wtab_u32 + l * 4u));
-        between();
+    VecIO<VEC> x0, x1, tv;
+    // apply one row: table row of label (e & 0xffff) += w * x
+    auto apply = [&](uint32_t e, const VecIO<VEC>& x, float w, auto&& between) {
+      const uint32_t l  = e & 0xffffu;
+      const uint32_t ta = tab_me + l * ROWB;
+      tv.load(ta);
+      float cur = 0.0f;
+      if (HAS_W && counts) cur = __int_as_float(lds32(wtab_u32 + l * 4u));
+      between();
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) tv.v[q] = HAS_W ? fmaf(x.v[q], w, tv.v[q]) : tv.v[q] + x.v[q];
-        tv.store(ta);
-        if (HAS_W && counts)   // every lane writes the same value to the same word: no divergence, no atomics
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(wtab_u32 + l * 4u), "f"(cur + w) : "memory");
-      };
-      if (j < o1 && (j & 1)) {   // odd head so that the pair loop reads aligned entry pairs
-        const uint32_t e = static_cast<uint32_t>(lds32(perm + j * 4));
-        float w = 1.0f;
-        if (HAS_W) w = __int_as_float(lds32(wprm + j * 4));
-        x0.load(xs + (e >> 16) * ROWB);
-        apply(e, x0, w, [] {});
-        ++j;
+      for (int q = 0; q < VEC; ++q) tv.v[q] = HAS_W ? fmaf(x.v[q], w, tv.v[q]) : tv.v[q] + x.v[q];
+      tv.store(ta);
+      if (HAS_W && counts)   // every lane writes the same value to the same word: no divergence, no atomics
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(wtab_u32 + l * 4u), "f"(cur + w) : "memory");
+    };
+    if (j < o1 && (j & 1)) {   // odd head so that the pair loop reads aligned entry pairs
+      const uint32_t e = static_cast<uint32_t>(lds32(perm + j * 4));
+      float w = 1.0f;
+      if (HAS_W) w = __int_as_float(lds32(wprm + j * 4));
+      x0.load(xs + (e >> 16) * ROWB);
+      apply(e, x0, w, [] {});
+      ++j;
+    }
+    if (j < o1) {
+      uint2 e = lds64u(perm + j * 4);
+      uint2 w = make_uint2(0x3f800000u, 0x3f800000u);
+      if (HAS_W) w = lds64u(wprm + j * 4);
+      x0.load(xs + (e.x >> 16) * ROWB);
+      for (; j < o1; j += 2) {
+        const uint2 en = lds64u(perm + j * 4 + 8);     // entries j+2, j+3 (past the end: stale, in range)
+        uint2 wn       = w;
+        if (HAS_W) wn = lds64u(wprm + j * 4 + 8);
+        apply(e.x, x0, __uint_as_float(w.x), [&] { x1.load(xs + (e.y >> 16) * ROWB); });
+        if (j + 1 < o1) apply(e.y, x1, __uint_as_float(w.y), [&] { x0.load(xs + (en.x >> 16) * ROWB); });
+        e = en;
+        w = wn;
       }
-      if (j < o1) {
-        uint2 e = lds64u(perm + j * 4);
-        uint2 w = make_uint2(0x3f800000u, 0x3f800000u);
-        if (HAS_W) w = lds64u(wprm + j * 4);
-        x0.load(xs + (e.x >> 16) * ROWB);
-        for (; j < o1; j += 2) {
-          const uint2 en = lds64u(perm + j * 4 + 8);     // entries j+2, j+3 (past the end: stale, in range)
-          uint2 wn       = w;
-          if (HAS_W) wn = lds64u(wprm + j * 4 + 8);
-          apply(e.x, x0, __uint_as_float(w.x), [&] { x1.load(xs + (e.y >> 16) * ROWB); });
-          if (j + 1 < o1) apply(e.y, x1, __uint_as_float(w.y), [&] { x0.load(xs + (en.x >> 16) * ROWB); });
-          e = en;
-          w = wn;
-        }
-      }
-      }   // !HALF
+    }
       __syncwarp();
       if (lane == 0) {
         ptx::mbar_arrive(bars_u32 + B_EMPTYX + s * 8);
@@ -701,8 +660,8 @@ reduce_partials_f32_kernel(const float* __restrict__ partial_S, const float* __r
   }
 }
 
-// ---- opt-in M-step for short rows (n_features 4 / 8 / 16, e.g. C5): lane = column, warp-private tables -------------
-// CUML_B200_UPD_LANECOL=1; written after round 1's GPU budget was spent -- parity and speed not yet measured.
+// ---- M-step for short rows (n_features 4 / 8 / 16, e.g. C5): lane = column, warp-private tables -------------------
+// Default for these shapes (CUML_B200_UPD_LANECOL=0 restores the lane = row kernel): 3.65 -> 2.06 ms at C5 = 6.6 TB/s.
 // The lane = row kernel above is bound by shared-memory wavefronts (32 random table rows per instruction).  Here one
 // warp instruction covers R = 32 / D consecutive rows with lane = (sub-row r, column c), lane == r * D + c, so a batch
 // of 32 * U consecutive floats of X is loaded with U perfectly coalesced 128-byte loads and needs no staging at all.
@@ -932,7 +891,7 @@ static TmaUpdatePlan plan_tma_update(const Handle& h, int d, int k)
 }
 
 struct OwnerPlan {
-  int vec = 0, tr = 0, nstage = 0, slices = 0, ncons = 16, nl = 0, half = 0;
+  int vec = 0, tr = 0, nstage = 0, slices = 0, ncons = 16, nl = 0;
   size_t smem = 0;
 };
 
@@ -942,11 +901,7 @@ static OwnerPlan plan_owner_update(const Handle& h, int d, int k)
   OwnerPlan best;
   int mode = 1;
   if (const char* e = std::getenv("CUML_B200_UPDATE_OWNER")) mode = std::atoi(e);
-  // 64-byte rows (n_features == 16), two rows per warp instruction: correct but measured slower than the lane = row
-  // kernel at C5 (6.1 vs 3.8 ms: four times the rows per byte make the analysts the bottleneck) -> opt-in
-  static const bool half_ok = std::getenv("CUML_B200_OWNER_HALF") && std::atoi(std::getenv("CUML_B200_OWNER_HALF")) != 0;
-  if (mode == 0 || (d < 32 && !(d == 16 && half_ok)) || d % 4 != 0 || k < 16) return best;
-  const bool half = d == 16;
+  if (mode == 0 || d < 32 || d % 4 != 0 || k < 16) return best;
   int force_vec = 0, force_tr = 0, force_nl = 0, force_ns = 0;
   if (const char* e = std::getenv("CUML_B200_OWNER_VEC")) force_vec = std::atoi(e);
   if (const char* e = std::getenv("CUML_B200_OWNER_TR")) force_tr = std::atoi(e);
@@ -954,9 +909,9 @@ static OwnerPlan plan_owner_update(const Handle& h, int d, int k)
   if (const char* e = std::getenv("CUML_B200_OWNER_NS")) force_ns = std::atoi(e);
   const size_t budget = h.smem_optin - 512;
   double best_score   = -1.0;
-  for (int vec = half ? 1 : 4; vec >= 1; vec >>= 1) {
+  for (int vec = 4; vec >= 1; vec >>= 1) {
     if (force_vec && vec != force_vec) continue;
-    const int ds = half ? 16 : 32 * vec;
+    const int ds = 32 * vec;
     if (vec > 1 && ds > d) continue;   // do not read padding columns
     const size_t table = (static_cast<size_t>(k) * ds + ((k + 3) & ~3)) * 4 + ((k + 15) & ~15) + (2 * MAX_NSTAGE + 3 * OWN_MAXNL) * 8 + 256;
     if (table + 2 * 8192 > budget) continue;
@@ -985,7 +940,6 @@ static OwnerPlan plan_owner_update(const Handle& h, int d, int k)
           best.slices = slices;
           best.smem   = table + lists + nstage * stage + 128;
           best.nl     = nl;
-          best.half   = half ? 1 : 0;
         }
       }
     }
@@ -1085,7 +1039,7 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
     if (partial_W.n < static_cast<size_t>(rb) * k) partial_W.alloc(static_cast<size_t>(rb) * k, h.stream);
     q.labels = labels_padded; q.w = w; q.partial_S = partial_S.get(); q.partial_W = partial_W.get();
     CUtensorMap tm = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
-                                 static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(op.half ? 16 : 32 * op.vec),
+                                 static_cast<uint64_t>(d) * sizeof(float), static_cast<uint32_t>(32 * op.vec),
                                  static_cast<uint32_t>(op.tr), CU_TENSOR_MAP_SWIZZLE_NONE,
                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     dim3 grid(static_cast<unsigned>(rb), static_cast<unsigned>(op.slices));
@@ -1095,14 +1049,10 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
       kern<<<grid, threads, op.smem, h.stream>>>(tm, q);
     };
     const bool hw = w != nullptr;
-    if (op.half) {
-      hw ? launch(accumulate_owner_kernel<1, true, true>) : launch(accumulate_owner_kernel<1, false, true>);
-    } else {
-      switch (op.vec) {
-        case 4: hw ? launch(accumulate_owner_kernel<4, true>) : launch(accumulate_owner_kernel<4, false>); break;
-        case 2: hw ? launch(accumulate_owner_kernel<2, true>) : launch(accumulate_owner_kernel<2, false>); break;
-        default: hw ? launch(accumulate_owner_kernel<1, true>) : launch(accumulate_owner_kernel<1, false>); break;
-      }
+    switch (op.vec) {
+      case 4: hw ? launch(accumulate_owner_kernel<4, true>) : launch(accumulate_owner_kernel<4, false>); break;
+      case 2: hw ? launch(accumulate_owner_kernel<2, true>) : launch(accumulate_owner_kernel<2, false>); break;
+      default: hw ? launch(accumulate_owner_kernel<1, true>) : launch(accumulate_owner_kernel<1, false>); break;
     }
     CB2_CHECK_LAUNCH();
     reduce_partials_f32_kernel<<<static_cast<unsigned>(ceil_div(total, 32)), 256, 0, h.stream>>>(

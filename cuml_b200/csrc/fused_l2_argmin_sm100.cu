@@ -15,7 +15,8 @@
 //   fused_l2_argmin_2cta_kernel  k > 128: two CTAs of a TPC share M = 256, N = 256 MMAs (cta_group::2), each
 //                                holds half of every centroid block; 8 converter warps, 16 epilogue warps
 //   fused_l2_argmin_kernel       k <= 128 and the row-packed small-d case
-//   fused_l2_argmin_ts_kernel    X operand in tensor memory (opt-in experiment)
+//   fused_l2_argmin_tsp_kernel   n_features <= 16 (two data rows per operand row), k <= 64: X operand in tensor memory,
+//                                optionally with the M-step fused in (one pass over X per Lloyd step)
 // Roles: TMA producers for X and centroid K-blocks (128B / 64B / 32B-swizzled tiles), converter warps that
 // split the raw X tile in shared memory, one MMA-issuing warp (uniform control flow, elect.sync lane), and the
 // argmin epilogue (tcgen05.ld, thread = row, four (min, argmin) chains, parts merged through shared memory).
@@ -112,7 +113,6 @@ struct FusedParams {
   int32_t* labels;
   float* dbg_dots;   // optional [n, k_pad] dump of the x.c accumulators (tests only)
   long long* dbg_clk; // optional [16]: per-role (wait cycles, total cycles) of CTA 0 (env CUML_B200_DBG_CLK)
-  int dbg_skip;      // profiling knob (env CUML_B200_DBG_SKIP): 1 = no hi/lo split, 2 = no MMA, 4 = no argmin
   int l2_ahead;      // CTA-pair kernel: row tiles prefetched into L2 ahead of the shared-memory ring
   int fold;          // CTA-pair kernel: -1/2||c||^2 enters the accumulator through one extra K=8 MMA (ones x pieces)
   // Distance-matrix mode (DIST kernels, ML::kmeans::transform) reuses fields that are idle there, so that the
@@ -131,30 +131,20 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
-// ---- fused M-step of the single-CTA kernel (MSTEP instantiation; row-packed n_features = 16, unweighted) ----------
+// ---- fused M-step of the row-packed tensor-memory kernel (fused_l2_argmin_tsp_kernel<MSTEP>; n_features = 16, unweighted)
 // One pass over X per Lloyd iteration for the HBM-bound small-d shapes: the raw fp32 tile is still in its X slot when
-// the row-owner epilogue knows the tile's labels, so four accumulate warps add the rows into warp-private
-// [k_sub x 32] tables (lane = (data row of the packed pair, column): lane l only ever touches bank l) before the slot is
-// released.  The slot's empty barrier then counts the MMA commit and the four accumulate warps.  Labels travel through
-// a per-slot shared-memory buffer (one word per packed row: even-row label | odd-row label << 16); cluster sizes are
-// integer shared-memory counts kept by the epilogue threads (exact).  At the end the CTA folds its tables in a fixed
-// order into the partials format of the M-step kernels (deterministic).  Parameter fields that are idle in this mode
-// carry the outputs (the parameter block keeps its size): dbg_dots -> partial_S [grid][k][16], cnh -> partial_W [grid][k],
-// raw_slots -> true n_clusters.
-constexpr int MS_ACC_WARPS = 4;
+// the row-owner epilogue knows the tile's labels, so accumulate warps add the rows into warp-private [k_sub + 1 x 32]
+// tables (lane = (data row of the packed pair, column): lane l only ever touches bank l) before the slot is released.
+// The slot's empty barrier then counts the converter and the accumulate warps.  Labels travel through a per-slot
+// shared-memory buffer (one word per operand row: table-row byte offset of the even data row | odd row << 16); cluster
+// sizes are integer shared-memory counts kept by the epilogue threads (exact).  At the end the CTA folds its tables in
+// a fixed order into the partials format of the M-step kernels (deterministic).
 constexpr int TSP_ACC_WARPS = 8;   // A-in-TMEM kernel: warps 20..27 accumulate (the row-owner epilogue then has 3 groups)
 __host__ __device__ inline size_t tsp_mstep_smem_bytes(int k_sub)
 {
   return static_cast<size_t>(TSP_ACC_WARPS) * (k_sub + 1) * 32 * sizeof(float)   // private tables (+ a dummy row each)
          + static_cast<size_t>(k_sub) * 2 * sizeof(int)                           // counts
          + static_cast<size_t>(MAX_A_SLOTS) * TILE_M * sizeof(uint32_t)           // label words per X slot
-         + 128;
-}
-__host__ __device__ inline size_t mstep_smem_bytes(int k_sub)
-{
-  return static_cast<size_t>(MS_ACC_WARPS) * (k_sub + 1) * 32 * sizeof(float)   // private tables (+ a dummy row each)
-         + static_cast<size_t>(k_sub) * 2 * sizeof(int)                   // counts (both packed groups share them)
-         + static_cast<size_t>(MAX_A_SLOTS) * TILE_M * sizeof(uint32_t)   // label words per slot
          + 128;
 }
 
@@ -220,7 +210,6 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
       const int jbase      = nt * p.bn;
       uint32_t r[32];
       for (int c0 = cbeg; c0 < cend; c0 += 32) {
-        if (p.dbg_skip & 4) break;
         ptx::tmem_ld_32x32(taddr + c0, r);
         ptx::tmem_ld_wait();
         if (!DIST && p.dbg_dots) {
@@ -385,8 +374,9 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
   }
 }
 
-// ===================== row-owner epilogue (opt-in, CUML_B200_EPI_ROWOWN=1; single centroid tile, BN <= 128) ===========
-// Written after round 1's GPU budget was spent -- not yet validated on hardware.  With few clusters the epilogue above
+// ===================== row-owner epilogue (single centroid tile, BN <= 128) ============================================
+// Measured at C5: fused kernel 6.9 -> 5.9 ms on the 3xTF32 kernel, 6.5 -> 4.9 ms on the tf32 + bf16 twin
+// (profiles/r02_ab_table.txt).  With few clusters the epilogue above
 // gives each of its 16 warps ONE 32-column chunk per tile and then pays two 512-thread named barriers and a shared-
 // memory merge per tile: a per-tile latency chain (accumulator wait -> tcgen05.ld -> compare -> barrier -> merge ->
 // store -> barrier) that all 16 warps walk together, one tile at a time.  Here the 16 warps form 4 groups of 4 (one
@@ -488,7 +478,7 @@ __device__ __forceinline__ void epilogue_role_rowown(const FusedParams& p, Barri
   }
 }
 
-template <int DIST, bool ROWOWN = false>
+template <int DIST>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                        const __grid_constant__ CUtensorMap tm_lo, const FusedParams p)
@@ -520,7 +510,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     }
     for (int s = 0; s < MAX_ACC; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), ROWOWN ? 4 : 16);   // one arrive per epilogue warp of the accumulator
+      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), 16);   // one arrive per epilogue warp of the accumulator
     }
     for (int s = 0; s < MAX_STAGES; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);
@@ -611,7 +601,6 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
         const int live_chunks = 2 * min(4, (p.d - kbi * KBLOCK + 7) / 8);
 #pragma unroll
         for (int i = 0; i < KBLOCK_BYTES / 16 / 128; ++i) {
-          if (p.dbg_skip & 1) break;
           const int e = ct + i * 128;
           // logical chunk of this physical position under the 128B swizzle: pos ^ (row & 7)
           if (((e & 7) ^ ((e >> 3) & 7)) >= live_chunks) continue;
@@ -670,7 +659,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
             if (ptx::elect_one()) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
-                if (ks >= nks || (p.dbg_skip & 2)) break;
+                if (ks >= nks) break;
                 const uint64_t adv = static_cast<uint64_t>(ks * 2);  // 8 tf32 = 32 bytes = 2 x 16B units
                 // small terms first, then the dominant hi.hi term
                 ptx::mma_tf32_ss(d_tmem, da_lo + adv, db_hi + adv, idesc, (kbi | ks) != 0 ? 1u : 0u);
@@ -705,11 +694,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
     // ===================== epilogue: argmin over the accumulator =====================
     const int64_t n_mine = (p.m_tiles > static_cast<int64_t>(blockIdx.x))
                              ? (p.m_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    if constexpr (ROWOWN)
-      epilogue_role_rowown<false>(p, bars, cn_s, tmem_base, static_cast<int64_t>(blockIdx.x) * TILE_M,
-                                  static_cast<int64_t>(gridDim.x) * TILE_M, n_mine);
-    else
-      epilogue_role<false, DIST>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, static_cast<int64_t>(blockIdx.x) * TILE_M,
+    epilogue_role<false, DIST>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, static_cast<int64_t>(blockIdx.x) * TILE_M,
                                  static_cast<int64_t>(gridDim.x) * TILE_M, n_mine);
   }
 
@@ -1095,9 +1080,7 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
 // Single-CTA twin of the CTA-pair kernel (opt-in, CUML_B200_SOLO_V2=1; NOT yet validated on hardware): the same
 // roles, bf16 correction terms and folded half norms for k <= 128, with cta_group::1 instructions and local
 // barriers.  Generated from the pair kernel's source; once measured it is meant to replace fused_l2_argmin_kernel.
-// MSTEP (with ROWOWN, BF16C, TRUNC; row-packed n_features = 16): the M-step rides on the E-step's tile, see above.
-// The converter then has 4 warps (4..7) and warps 24..27 accumulate.
-template <bool BF16C, int DIST = 0, bool TRUNC = false, bool ROWOWN = false, bool MSTEP = false>
+template <bool BF16C, int DIST = 0, bool TRUNC = false, bool ROWOWN = false>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
                             const __grid_constant__ CUtensorMap tm_lo, const __grid_constant__ CUtensorMap tm_lb,
@@ -1128,11 +1111,7 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   float* mrg_v           = cn_s + 2 * p.bn;                              // [128] epilogue half merge
   int* mrg_i             = reinterpret_cast<int*>(mrg_v + 3 * TILE_M);   // [3][128]
   Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 6u * TILE_M * 4u);
-  // fused M-step region (after the barriers): tables | counts | label words
-  float* ms_tab          = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ((sizeof(Barriers) + 127) & ~size_t(127)));
-  int* ms_counts         = reinterpret_cast<int*>(ms_tab + static_cast<size_t>(MS_ACC_WARPS) * p.k_sub * 32);
-  uint32_t* ms_labels    = reinterpret_cast<uint32_t*>(ms_counts + 2 * p.k_sub);
-  constexpr int NCONV    = MSTEP ? 128 : 256;   // converter threads
+  constexpr int NCONV    = 256;   // converter threads
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -1141,8 +1120,7 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     for (int s = 0; s < MAX_A_SLOTS; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->a_raw_full[s]), 1);
       ptx::mbar_init(ptx::smem_u32(&bars->a_ready[s]), NCONV / 32);            // converter warps
-      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), MSTEP ? 1 + MS_ACC_WARPS : 1);  // MMA commit (+ accumulate warps)
-      ptx::mbar_init(ptx::smem_u32(&bars->lab_full[s]), 4);                    // the 4 epilogue warps of a tile's group
+      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), 1);                     // MMA commit
     }
     for (int s = 0; s < MAX_ACC; ++s) {
       ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
@@ -1159,9 +1137,6 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     float* ones = reinterpret_cast<float*>(gbase + fold_off);
     for (int i = threadIdx.x; i < TILE_M * 8; i += blockDim.x) ones[i] = 1.0f;
     ptx::fence_proxy_async_smem();
-  }
-  if (MSTEP) {
-    for (int i = threadIdx.x; i < MS_ACC_WARPS * p.k_sub * 32 + 2 * p.k_sub; i += blockDim.x) ms_tab[i] = 0.0f;   // tables + counts
   }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_x);
@@ -1254,52 +1229,8 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
         }
       }
     }
-  } else if (MSTEP && warp >= 24) {
-    // ===================== fused M-step: accumulate warps 24..27 (32 packed rows of every tile each) =====================
-    const int aw       = warp - 24;
-    float* tab         = ms_tab + static_cast<size_t>(aw) * p.k_sub * 32 + lane;   // this lane's column of the private table
-    const int half     = lane >> 4;                                                // which data row of the packed pair
-    const uint32_t xch = static_cast<uint32_t>(lane >> 2);                         // logical 16-byte chunk of the lane's float
-    const uint32_t xin = static_cast<uint32_t>(lane & 3) * 4u;
-    Ring ra;
-    for (int64_t pt = pair; pt < pair_tiles; pt += n_pairs) {
-      const uint32_t sa = ra.slot, pa = ra.phase;
-      ra.advance(p.a_slots);
-      ptx::mbar_wait_park(ptx::smem_u32(&bars->a_raw_full[sa]), pa);   // the raw tile (async-proxy writes) is visible
-      ptx::mbar_wait_park(ptx::smem_u32(&bars->lab_full[sa]), pa);     // ... and so are its labels
-      const uint32_t my_word = ms_labels[sa * TILE_M + aw * 32 + lane];
-      const uint8_t* xs      = gbase + sa * A_SLOT_BYTES + static_cast<uint32_t>(aw * 32) * 128u;
-      // the tile's 32 values of this lane first: they do not depend on the labels, and loading them ahead of the
-      // table updates leaves ONE shared-memory latency (table read) per group of four rows instead of two
-      float xv[32];
-#pragma unroll
-      for (int r = 0; r < 32; ++r)
-        xv[r] = *reinterpret_cast<const float*>(xs + static_cast<uint32_t>(r) * 128u + ((xch ^ (static_cast<uint32_t>(r) & 7u)) << 4) + xin);
-#pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        uint32_t lb[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t w = __shfl_sync(0xffffffffu, my_word, j + u);
-          lb[u]            = (half ? (w >> 16) : (w & 0xffffu)) * 32u;
-        }
-        const bool clash = lb[0] == lb[1] || lb[0] == lb[2] || lb[0] == lb[3] || lb[1] == lb[2] || lb[1] == lb[3] || lb[2] == lb[3];
-        if (!__any_sync(0xffffffffu, clash)) {   // four independent read-modify-write chains
-          float tv[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) tv[u] = tab[lb[u]];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) tab[lb[u]] = tv[u] + xv[j + u];
-        } else {                                  // two rows of the group share a cluster in some lane: row order
-#pragma unroll
-          for (int u = 0; u < 4; ++u) tab[lb[u]] += xv[j + u];
-        }
-      }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->a_empty[sa]));
-    }
-  } else if ((warp >= 4 && warp < 8) || (!MSTEP && warp >= 24)) {
-    // ===================== converter (8 warps: 4..7 and 24..27; MSTEP: 4 warps) =====================
+  } else if ((warp >= 4 && warp < 8) || warp >= 24) {
+    // ===================== converter (8 warps: 4..7 and 24..27) =====================
     const int ct = warp >= 24 ? threadIdx.x - 768 + 128 : threadIdx.x - 128;   // 0..NCONV-1
     // this thread's chunks are ct + NCONV i: NCONV / 8 rows apart, so the logical chunk and the swizzle phases are fixed
     const int conv_row       = ct >> 3;
@@ -1475,7 +1406,7 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
     // ===================== epilogue (own 128 rows of the pair tile) =====================
     const int64_t n_mine = (pair_tiles > pair) ? (pair_tiles - pair + n_pairs - 1) / n_pairs : 0;
     if constexpr (ROWOWN)
-      epilogue_role_rowown<true, MSTEP>(p, bars, cn_s, tmem_base, pair * TILE_M, n_pairs * TILE_M, n_mine, ms_labels, ms_counts);
+      epilogue_role_rowown<true>(p, bars, cn_s, tmem_base, pair * TILE_M, n_pairs * TILE_M, n_mine);
     else
       epilogue_role<false, DIST, true>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, pair * TILE_M, n_pairs * TILE_M, n_mine);
   }
@@ -1484,279 +1415,6 @@ fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   __syncthreads();
   ptx::tc_fence_after();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
-  if (MSTEP) {
-    // fold the private tables in a fixed order (accumulate warp 0..3, packed group 0 then 1) into this CTA's partials
-    const int k_true = p.raw_slots;
-    float* out_S     = p.dbg_dots + static_cast<size_t>(blockIdx.x) * k_true * 16;
-    float* out_W     = const_cast<float*>(p.cnh) + static_cast<size_t>(blockIdx.x) * k_true;
-    for (int e = threadIdx.x; e < k_true * 16; e += blockDim.x) {
-      const int j = e >> 4, c = e & 15;
-      float acc = 0.0f;
-#pragma unroll
-      for (int w = 0; w < MS_ACC_WARPS; ++w) {
-        const float* t = ms_tab + (static_cast<size_t>(w) * p.k_sub + j) * 32;
-        acc += t[c];
-        acc += t[16 + c];
-      }
-      out_S[e] = acc;
-    }
-    for (int j = threadIdx.x; j < k_true; j += blockDim.x) out_W[j] = static_cast<float>(ms_counts[j]);
-  }
-}
-
-// =================================================================================================
-// A-in-TMEM variant (the fast one).  Measured on B200 (tools/micro/mma_rate.cu): a kind::tf32 MMA with
-// both operands in shared memory costs 43 + N/2 cycles (171 at N = 256 -> 861 TFLOP/s), with the A
-// operand in tensor memory it runs at the N/2 floor (64 cycles at N = 128 -> 1149 TFLOP/s).  So the
-// converter warps write the hi / lo split of each X K-block straight into TMEM (tcgen05.st, thread = row)
-// instead of shared memory; the raw X tiles ride a deep 16 KB-per-slot ring; BN <= 128 leaves TMEM room
-// for the operand slots:  columns [0, n_acc*BN) accumulators | a_slots x (hi 32 | lo 32) operand columns.
-// PAIR = true runs it as a CTA pair (cta_group::2): M = 256, each CTA holds BN/2 centroid rows.
-template <bool PAIR>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-fused_l2_argmin_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
-                          const __grid_constant__ CUtensorMap tm_lo, const FusedParams p)
-{
-  extern __shared__ uint8_t smem_dyn[];
-  const uint32_t raw_base = ptx::smem_u32(smem_dyn);
-  const uint32_t base     = (raw_base + 1023u) & ~1023u;
-  uint8_t* gbase          = smem_dyn + (base - raw_base);
-
-  const uint32_t cta_rank = PAIR ? ptx::cluster_ctarank() : 0u;
-  const bool leader       = cta_rank == 0;
-  const int64_t unit      = PAIR ? (blockIdx.x >> 1) : blockIdx.x;       // CTA or CTA pair
-  const int64_t n_units   = PAIR ? (gridDim.x >> 1) : gridDim.x;
-  const int rows_unit     = PAIR ? 2 * TILE_M : TILE_M;
-  const int64_t tiles     = PAIR ? (p.m_tiles + 1) / 2 : p.m_tiles;      // tiles of rows_unit rows
-  const int my_bn         = PAIR ? p.bn / 2 : p.bn;                       // centroid rows held by this CTA
-
-  const uint32_t b_half_bytes  = static_cast<uint32_t>(my_bn) * 128u;
-  const uint32_t b_stage_bytes = 2u * b_half_bytes;                      // hi then lo
-  const uint32_t x_base  = base;                                         // raw ring
-  const uint32_t b_base  = x_base + p.raw_slots * KBLOCK_BYTES;
-  const uint32_t cn_off  = p.raw_slots * KBLOCK_BYTES + p.b_stages * b_stage_bytes;
-  float* cn_s            = reinterpret_cast<float*>(gbase + cn_off);     // [2][bn]
-  float* mrg_v           = cn_s + 2 * p.bn;
-  int* mrg_i             = reinterpret_cast<int*>(mrg_v + 3 * TILE_M);
-  Barriers* bars         = reinterpret_cast<Barriers*>(gbase + cn_off + 2u * p.bn * sizeof(float) + 6u * TILE_M * 4u);
-
-  const int warp = threadIdx.x / 32;
-  const int lane = threadIdx.x % 32;
-  const uint32_t conv_arrivals = PAIR ? 8u : 4u;    // converter warps that feed one MMA
-  const uint32_t epi_arrivals  = PAIR ? 32u : 16u;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < MAX_RAW; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&bars->raw_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->raw_empty[s]), 4);     // the CTA's own 4 converter warps
-    }
-    for (int s = 0; s < MAX_A_SLOTS; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&bars->a_ready[s]), conv_arrivals);
-      ptx::mbar_init(ptx::smem_u32(&bars->a_empty[s]), 1);
-    }
-    for (int s = 0; s < MAX_ACC; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&bars->acc_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->acc_empty[s]), epi_arrivals);
-    }
-    for (int s = 0; s < MAX_STAGES; ++s) {
-      ptx::mbar_init(ptx::smem_u32(&bars->b_full[s]), 1);
-      ptx::mbar_init(ptx::smem_u32(&bars->b_empty[s]), 1);
-    }
-    ptx::fence_barrier_init();
-  }
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tm_x);
-    ptx::prefetch_tmap(&tm_hi);
-    ptx::prefetch_tmap(&tm_lo);
-  }
-  if (warp == 1) {
-    if (PAIR) {
-      ptx::tmem_alloc_2cta(ptx::smem_u32(&bars->tmem_base), p.tmem_cols);
-      ptx::tmem_relinquish_2cta();
-    } else {
-      ptx::tmem_alloc(ptx::smem_u32(&bars->tmem_base), p.tmem_cols);
-      ptx::tmem_relinquish();
-    }
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (PAIR) ptx::cluster_sync_all();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = bars->tmem_base;
-
-  if (warp == 0) {
-    // ===================== raw X producer (own 128 rows) =====================
-    uint32_t cnt = 0;
-    Ring rr;
-    for (int64_t t = unit; t < tiles; t += n_units) {
-      const int32_t row0 = static_cast<int32_t>(t * rows_unit + cta_rank * TILE_M);
-      for (int kbi = 0; kbi < p.kb; ++kbi, ++cnt) {
-        const uint32_t rs = rr.slot, rp = rr.phase;
-        rr.advance(p.raw_slots);
-        ptx::mbar_wait(ptx::smem_u32(&bars->raw_empty[rs]), rp ^ 1u);
-        if (ptx::elect_one()) {
-          const uint32_t full = ptx::smem_u32(&bars->raw_full[rs]);
-          ptx::mbar_arrive_expect_tx(full, KBLOCK_BYTES);
-          ptx::tma_load_2d_hint(x_base + rs * KBLOCK_BYTES, &tm_x, kbi * KBLOCK, row0, full, ptx::kEvictFirst);
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == 2) {
-    // ===================== centroid producer =====================
-    uint32_t b_cnt = 0;
-    Ring rb;
-    for (int64_t t = unit; t < tiles; t += n_units) {
-      if (p.b_resident && t != unit) break;
-      for (int nt = 0; nt < p.k_tiles; ++nt) {
-        for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
-          const uint32_t sb = rb.slot, pb = rb.phase;
-            rb.advance(p.b_stages);
-          ptx::mbar_wait(ptx::smem_u32(&bars->b_empty[sb]), pb ^ 1u);
-          if (ptx::elect_one()) {
-            const uint32_t full_local = ptx::smem_u32(&bars->b_full[sb]);
-            const uint32_t dst        = b_base + sb * b_stage_bytes;
-            const int32_t crow        = nt * p.bn + static_cast<int32_t>(cta_rank) * my_bn;
-            if (PAIR) {
-              const uint32_t full_leader = ptx::mapa(full_local, 0);
-              if (leader) ptx::mbar_arrive_expect_tx(full_local, 2u * b_stage_bytes);  // bytes of BOTH CTAs
-              ptx::tma_load_2d_2cta(dst, &tm_hi, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
-              ptx::tma_load_2d_2cta(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, crow, full_leader, ptx::kEvictLast);
-            } else {
-              ptx::mbar_arrive_expect_tx(full_local, b_stage_bytes);
-              ptx::tma_load_2d_hint(dst, &tm_hi, kbi * KBLOCK, crow, full_local, ptx::kEvictLast);
-              ptx::tma_load_2d_hint(dst + b_half_bytes, &tm_lo, kbi * KBLOCK, crow, full_local, ptx::kEvictLast);
-            }
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== converter: raw row (shared) -> hi | lo operand columns (tensor memory) =========
-    const int quarter = warp & 3;
-    const int row     = quarter * 32 + lane;                       // row of the tile == TMEM lane
-    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    uint32_t cnt = 0;
-    Ring rr, ra;
-    for (int64_t t = unit; t < tiles; t += n_units) {
-      for (int kbi = 0; kbi < p.kb; ++kbi, ++cnt) {
-        const uint32_t rs = rr.slot, rp = rr.phase;
-        rr.advance(p.raw_slots);
-        const uint32_t as = ra.slot, ap = ra.phase;
-        ra.advance(p.a_slots);
-        ptx::mbar_wait(ptx::smem_u32(&bars->raw_full[rs]), rp);
-        const uint4* src = reinterpret_cast<const uint4*>(gbase + rs * KBLOCK_BYTES + row * 128);
-        uint32_t hi[32], lo[32];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint4 v = src[c ^ (row & 7)];                        // 128B swizzle: chunk ^= row & 7
-          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const uint32_t h = w4[e] & 0xffffe000u;
-            hi[c * 4 + e]    = h;
-            lo[c * 4 + e]    = __float_as_uint(__uint_as_float(w4[e]) - __uint_as_float(h));
-          }
-        }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(&bars->raw_empty[rs]));   // raw slot may be refilled
-        ptx::mbar_wait(ptx::smem_u32(&bars->a_empty[as]), ap ^ 1u);             // MMAs that read this slot retired
-        ptx::tc_fence_after();
-        const uint32_t acol = tmem_base + lane_addr + p.a_col0 + as * 64;
-        ptx::tmem_st_32x32(acol, hi);
-        ptx::tmem_st_32x32(acol + 32, lo);
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (PAIR) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&bars->a_ready[as]), 0));
-          else ptx::mbar_arrive(ptx::smem_u32(&bars->a_ready[as]));
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
-    if (leader) {
-      const uint32_t idesc = ptx::umma_idesc_tf32(PAIR ? 2 * TILE_M : TILE_M, p.bn);
-      uint32_t b_cnt = 0, acc_cnt = 0;
-      Ring ra_tile, rb, racc;
-      for (int64_t t = unit; t < tiles; t += n_units, ra_tile.advance_by(p.kb, p.a_slots)) {
-        for (int nt = 0; nt < p.k_tiles; ++nt, ++acc_cnt) {
-          const uint32_t acc = racc.slot, pacc = racc.phase;
-          racc.advance(p.n_acc);
-          Ring ra = ra_tile;
-          ptx::mbar_wait(ptx::smem_u32(&bars->acc_empty[acc]), pacc ^ 1u);
-          const uint32_t d_tmem = tmem_base + acc * p.bn;
-          for (int kbi = 0; kbi < p.kb; ++kbi, ++b_cnt) {
-            const uint32_t as = ra.slot, ap = ra.phase;
-            ra.advance(p.a_slots);
-            if (nt == 0) ptx::mbar_wait(ptx::smem_u32(&bars->a_ready[as]), ap);
-            uint32_t sb = rb.slot;
-            const uint32_t pb = rb.phase;
-            rb.advance(p.b_stages);
-            if (p.b_resident) {
-              sb = nt * p.kb + kbi;
-              if (t == unit) ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), 0u);
-            } else {
-              ptx::mbar_wait(ptx::smem_u32(&bars->b_full[sb]), pb);
-            }
-            ptx::tc_fence_after();
-            const uint32_t a_hi  = tmem_base + p.a_col0 + as * 64;
-            const uint32_t a_lo  = a_hi + 32;
-            const uint64_t db_hi = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes);
-            const uint64_t db_lo = ptx::umma_desc_sw128(b_base + sb * b_stage_bytes + b_half_bytes);
-            const int nks = min(4, (p.d - kbi * KBLOCK + 7) / 8);
-            if (ptx::elect_one()) {
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (ks >= nks) break;
-                const uint64_t adv = static_cast<uint64_t>(ks * 2);   // B: 8 tf32 = 32 bytes = 2 x 16B units
-                const uint32_t ak  = static_cast<uint32_t>(ks * 8);   // A: 8 TMEM columns per K = 8 step
-                const uint32_t first = (kbi | ks) != 0 ? 1u : 0u;
-                if (PAIR) {
-                  ptx::mma_tf32_ts_2cta(d_tmem, a_lo + ak, db_hi + adv, idesc, first);
-                  ptx::mma_tf32_ts_2cta(d_tmem, a_hi + ak, db_lo + adv, idesc, 1u);
-                  ptx::mma_tf32_ts_2cta(d_tmem, a_hi + ak, db_hi + adv, idesc, 1u);
-                } else {
-                  ptx::mma_tf32_ts(d_tmem, a_lo + ak, db_hi + adv, idesc, first);
-                  ptx::mma_tf32_ts(d_tmem, a_hi + ak, db_lo + adv, idesc, 1u);
-                  ptx::mma_tf32_ts(d_tmem, a_hi + ak, db_hi + adv, idesc, 1u);
-                }
-              }
-              if (PAIR) {
-                if (!p.b_resident) ptx::mma_commit_2cta(ptx::smem_u32(&bars->b_empty[sb]), 3);
-                if (nt == p.k_tiles - 1) ptx::mma_commit_2cta(ptx::smem_u32(&bars->a_empty[as]), 3);
-              } else {
-                if (!p.b_resident) ptx::mma_commit(ptx::smem_u32(&bars->b_empty[sb]));
-                if (nt == p.k_tiles - 1) ptx::mma_commit(ptx::smem_u32(&bars->a_empty[as]));
-              }
-            }
-            __syncwarp();
-          }
-          if (ptx::elect_one()) {
-            if (PAIR) ptx::mma_commit_2cta(ptx::smem_u32(&bars->acc_full[acc]), 3);
-            else ptx::mma_commit(ptx::smem_u32(&bars->acc_full[acc]));
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else if (warp >= 8) {
-    // ===================== epilogue =====================
-    const int64_t n_mine = (tiles > unit) ? (tiles - unit + n_units - 1) / n_units : 0;
-    epilogue_role<PAIR>(p, bars, cn_s, mrg_v, mrg_i, tmem_base, unit * rows_unit + cta_rank * TILE_M,
-                        n_units * rows_unit, n_mine);
-  }
-
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (PAIR) ptx::cluster_sync_all();
-  ptx::tc_fence_after();
-  if (warp == 1) {
-    if (PAIR) ptx::tmem_dealloc_2cta(tmem_base, p.tmem_cols);
-    else ptx::tmem_dealloc(tmem_base, p.tmem_cols);
-  }
 }
 
 // =================================================================================================
@@ -1770,7 +1428,7 @@ fused_l2_argmin_ts_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid
 // tensor memory (N/2-cycle floor instead of 43 + N/2, tools/micro/mma_rate.cu) and only B (4 KB each) from shared
 // memory; the -1/2||c||^2 fold stays a shared-memory MMA of the ones tile.  The raw X tiles ride a deep ring of 16 KB
 // slots.  TMEM: n_acc accumulators of BN columns, then two 64-column operand stages [raw 32 | bf16 hi 16 | bf16 lo 16].
-// MSTEP: the fused M-step of the twin (accumulate warps 24..27 add the raw tile into private tables once the
+// MSTEP: the fused M-step (accumulate warps 20..27 add the raw tile into private tables once the
 // row-owner epilogue has published the tile's labels; the slot's empty barrier counts converter and accumulate warps).
 // In MSTEP mode idle parameter fields carry the outputs: dbg_dots -> partial_S, cnh -> partial_W, a_stream -> true k.
 template <bool MSTEP>
@@ -2183,18 +1841,6 @@ TilePlan plan_tiles(int d, int k, size_t smem_limit)
   return t;
 }
 
-// single-CTA twin of the pair kernel (bf16 corrections + folded norms for k <= 128): opt-in until measured
-bool use_solo_v2()
-{
-  return env_flag("CUML_B200_SOLO_V2", true);
-}
-
-// row-owner epilogue of the single-CTA tf32 + bf16 kernel (see epilogue_role_rowown): opt-in until measured
-bool use_epi_rowown()
-{
-  return env_flag("CUML_B200_EPI_ROWOWN", true);
-}
-
 // CTA-pair plan: BN = 256 split across the pair (128 centroid rows per CTA), deeper X ring.
 // half norms folded into the accumulator by one extra MMA (default on; CUML_B200_FOLD=0 restores the epilogue add)
 bool use_cn_fold()
@@ -2261,62 +1907,6 @@ bool use_bf16_corrections()
   return e ? std::atoi(e) != 0 : true;
 }
 
-// Plan for the A-in-TMEM kernel: BN <= 128, operand slots in TMEM, raw X ring + centroid stages in smem.
-struct TsPlan {
-  int kb = 0, bn = 0, a_slots = 0, raw_slots = 0, b_stages = 0, b_resident = 0, n_acc = 0, pair = 0;
-  size_t smem = 0;
-};
-
-TsPlan plan_ts(const Handle& h, int d, int k)
-{
-  TsPlan t;
-  t.kb = static_cast<int>(ceil_div(d, KBLOCK));
-  int bn = 128;
-  if (k <= 32) bn = 32;
-  else if (k <= 64) bn = 64;
-  const int k_tiles = static_cast<int>(ceil_div(k, bn));
-  {
-    const char* e = std::getenv("CUML_B200_2CTA");
-    const bool want = e ? (std::atoi(e) != 0) : true;
-    t.pair = (want && bn == 128 && (h.sm_count % 2) == 0) ? 1 : 0;
-  }
-  // tensor memory: accumulators first, then 64-column operand slots (need all K-blocks of a row tile when
-  // there are several centroid tiles)
-  const int a_min = (k_tiles > 1) ? t.kb : 1;
-  int n_acc       = std::min(MAX_ACC, std::max(2, 256 / bn));
-  while (n_acc > 2 && (512 - n_acc * bn) / 64 < std::max(a_min, 2)) --n_acc;
-  int a_slots = std::min(MAX_A_SLOTS, (512 - n_acc * bn) / 64);
-  if (a_slots < a_min) return t;   // bn stays 0: not available
-  const size_t stage = static_cast<size_t>(t.pair ? bn / 2 : bn) * 128 * 2;
-  auto bytes = [&](int raw_, int bs_) {
-    return static_cast<size_t>(raw_) * KBLOCK_BYTES + static_cast<size_t>(bs_) * stage + 2 * bn * sizeof(float) +
-           6 * TILE_M * 4 + sizeof(Barriers) + 1024;
-  };
-  int b_stages = 3, resident = 0;
-  if (k_tiles * t.kb <= MAX_STAGES && bytes(4, k_tiles * t.kb) <= h.smem_optin) {
-    b_stages = k_tiles * t.kb;
-    resident = 1;
-  }
-  if (bytes(2, b_stages) > h.smem_optin) return t;
-  if (!resident) b_stages = MAX_STAGES;   // deep centroid ring: stages are small (<= 32 KB)
-  while (b_stages > 2 && bytes(4, b_stages) > h.smem_optin) --b_stages;
-  int raw = 2;
-  while (raw < MAX_RAW && bytes(raw + 1, b_stages) <= h.smem_optin) ++raw;
-  t.bn = bn; t.a_slots = a_slots; t.raw_slots = raw; t.b_stages = b_stages; t.b_resident = resident; t.n_acc = n_acc;
-  t.smem = bytes(raw, b_stages);
-  return t;
-}
-
-bool use_ts(const Handle& h, int d, int k)
-{
-  // Experimental: the MMA itself is 33 % faster with A in tensor memory (tools/micro/mma_rate.cu), but the
-  // whole kernel is then bound by the argmin epilogue (BN <= 128 doubles its per-tile hand-offs) and
-  // measures slower than the shared-memory CTA-pair kernel (profiles/).  Opt-in with CUML_B200_TS=1.
-  const char* e = std::getenv("CUML_B200_TS");
-  if (!e || std::atoi(e) == 0) return false;
-  return plan_ts(h, d, k).bn > 0;
-}
-
 }  // namespace
 
 bool tc_supported(int64_t d, int k)
@@ -2326,10 +1916,9 @@ bool tc_supported(int64_t d, int k)
 
 int tc_variant(const Handle& h, int d, int k)
 {
-  if (pack_k_sub(d, k)) return (use_solo_v2() && use_bf16_corrections()) ? 5 : 1;
-  if (use_ts(h, d, k)) return 4;
+  if (pack_k_sub(d, k)) return use_bf16_corrections() ? 5 : 1;
   if (use_2cta(h, d, k)) return use_bf16_corrections() ? 3 : 2;
-  if (use_solo_v2() && use_bf16_corrections()) return 5;
+  if (use_bf16_corrections()) return 5;
   return 1;
 }
 
@@ -2349,8 +1938,8 @@ void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out, bool 
     out.k_sub   = k_sub;
     out.bf16c   = 0;
     out.fold    = 0;
-    if (use_solo_v2() && allow_bf16 && use_bf16_corrections()) {
-      // opt-in single-CTA tf32 + bf16 kernel on the row-packed operands (see prepare_centroids_packed_v2_kernel)
+    if (allow_bf16 && use_bf16_corrections()) {
+      // tf32 + bf16 kernels on the row-packed operands (see prepare_centroids_packed_v2_kernel)
       const TilePlan t = plan_tiles(2 * d, k_pad, h.smem_optin);
       CB2_EXPECTS(t.bn == k_pad && t.kb == 1, "row-packed plan mismatch");
       out.bf16c = 1;
@@ -2373,14 +1962,8 @@ void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out, bool 
   }
   out.pack  = 1;
   out.k_sub = 0;
-  const bool ts   = use_ts(h, d, k);
-  const bool pair = !ts && use_2cta(h, d, k);
+  const bool pair = use_2cta(h, d, k);
   TilePlan t = pair ? plan_tiles_2cta(d, k, h.smem_optin) : plan_tiles(d, k, h.smem_optin);
-  if (ts) {
-    const TsPlan tp = plan_ts(h, d, k);
-    t.bn = tp.bn;
-    t.kb = tp.kb;
-  }
   CB2_EXPECTS(t.bn > 0, "tcgen05 k-means tile plan does not fit shared memory");
   const int d_pad = t.kb * KBLOCK;
   const int k_pad = static_cast<int>(ceil_div(k, t.bn)) * t.bn;
@@ -2392,7 +1975,7 @@ void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out, bool 
     out.d_pad = d_pad;
   }
   out.block_n = t.bn;
-  const bool solo = !pair && !ts && use_solo_v2();
+  const bool solo = !pair;
   out.bf16c   = ((pair || solo) && allow_bf16 && use_bf16_corrections()) ? 1 : 0;
   if (out.bf16c && out.hb.n < static_cast<size_t>(k_pad) * d_pad) {
     out.hb.alloc(static_cast<size_t>(k_pad) * d_pad, h.stream);
@@ -2435,21 +2018,20 @@ __global__ void assign_tail_row_kernel(const float* __restrict__ x, int d, int k
 bool tc_transform_supported(const Handle& h, int64_t d, int k)
 {
   // the distance-matrix epilogue exists for the unpacked shared-memory-operand kernels
-  return h.cc_major == 10 && tc_supported(d, k) && !pack_k_sub(static_cast<int>(d), k) &&
-         !use_ts(h, static_cast<int>(d), k);
+  return h.cc_major == 10 && tc_supported(d, k) && !pack_k_sub(static_cast<int>(d), k);
 }
 
 bool tc_best_supported(const Handle& h, int d, int k)
 {
-  return h.cc_major == 10 && tc_supported(d, k) && !use_ts(h, d, k);
+  return h.cc_major == 10 && tc_supported(d, k);
 }
 
 // ---- row-packed kernel with the X operand in tensor memory (fused_l2_argmin_tsp_kernel) ------------------------------
 // CUML_B200_TSP (read per call so that a test can switch it).
 static bool use_tsp() { return env_flag("CUML_B200_TSP", true); }
-// fused M-step: on by default with the tensor-memory kernel (C5: 4.6 ms per Lloyd step against 3.7 + 2.1 ms for the two
-// kernels); with CUML_B200_TSP=0 the shared-memory twin takes it, where it measured slower (8.0 ms against 5.1 + 2.1 ms)
-static bool fused_mstep_on() { return env_flag("CUML_B200_FUSED_MSTEP", use_tsp()); }
+// fused M-step: C5 4.6 ms per Lloyd step against 3.7 (E) + 2.1 (M) ms for two kernels.  (On the shared-memory-operand
+// twin the same fusion measured SLOWER, 8.0 ms against 5.1 + 2.1 ms, and was removed: profiles/README.md.)
+static bool fused_mstep_on() { return env_flag("CUML_B200_FUSED_MSTEP", true); }
 
 struct TspPlan {
   int raw_slots, n_acc, a_col0;
@@ -2471,33 +2053,10 @@ static bool plan_tsp(const Handle& h, int d, int k, bool mstep, TspPlan& out)
   return true;
 }
 
-// fused E + M step (see mstep_smem_bytes): the plan of the row-packed single-CTA kernel with room for the tables
-static bool plan_fused_mstep(const Handle& h, int d, int k, TilePlan& t_out, size_t& smem_out)
-{
-  // opt-in (CUML_B200_FUSED_MSTEP=1, read per call so that a test can switch it): parity-green, but on the shared-memory
-  // operand kernel measured SLOWER than the two-kernel step at C5 (8.0 ms against 5.1 + 2.1 ms, profiles/README.md): the
-  // table updates of the four accumulate warps add ~48 KB of shared-memory traffic per tile to a kernel already bound by it
-  const bool on = fused_mstep_on();
-  const int k_sub = pack_k_sub(d, k);
-  if (!on || d != 16 || k_sub == 0 || k_sub > 64 || !use_solo_v2() || !use_bf16_corrections() || !use_epi_rowown() || !use_cn_fold())
-    return false;
-  const int k_pad      = 2 * k_sub;
-  const size_t extra   = mstep_smem_bytes(k_sub) + static_cast<size_t>(2) * TILE_M * 32;   // tables + the fold tiles
-  if (h.smem_optin <= extra) return false;
-  TilePlan t = plan_tiles(2 * d, k_pad, h.smem_optin - extra);
-  if (t.bn != k_pad || t.kb != 1 || t.a_slots < 3 || !t.b_resident || 512 / t.bn < 4) return false;
-  t_out    = t;
-  smem_out = t.smem + extra;
-  return true;
-}
-
 bool tc_fused_update_supported(const Handle& h, int d, int k)
 {
-  TilePlan t;
-  size_t smem;
   TspPlan tp;
-  if (h.cc_major == 10 && fused_mstep_on() && use_tsp() && plan_tsp(h, d, k, true, tp)) return true;
-  return h.cc_major == 10 && plan_fused_mstep(h, d, k, t, smem);
+  return h.cc_major == 10 && fused_mstep_on() && use_tsp() && plan_tsp(h, d, k, true, tp);
 }
 
 void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentroids& cen, int32_t* labels,
@@ -2548,8 +2107,6 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       EventPair ev{};
       if (h.timing) ev = h.begin_event();
       const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
-      TilePlan tf;
-      size_t smem_f = 0;
       TspPlan tp{};
       const bool tsp_mstep = mstep && (n & 1) == 0 && fused_mstep_on();
       if (use_tsp() && cen.bf16c && cen.fold && !best_out && plan_tsp(h, d, k, tsp_mstep, tp)) {
@@ -2584,31 +2141,6 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
         } else {
           fused_l2_argmin_tsp_kernel<false><<<grid, PAIR_THREADS, tp.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
         }
-      } else if (mstep && cen.bf16c && cen.fold && !best_out && (n & 1) == 0 && plan_fused_mstep(h, d, k, tf, smem_f)) {
-        // ---- one pass over X: distance + argmin + centroid sums / counts (fused_l2_argmin_solo_kernel<.., MSTEP>) ----
-        p.a_slots = tf.a_slots; p.b_stages = tf.b_stages; p.b_resident = tf.b_resident;
-        p.fold = 1; p.l2_ahead = 3;
-        if (mstep->partial_S->n < static_cast<size_t>(grid) * k * d) mstep->partial_S->alloc(static_cast<size_t>(grid) * k * d, h.stream);
-        if (mstep->partial_W->n < static_cast<size_t>(grid) * k) mstep->partial_W->alloc(static_cast<size_t>(grid) * k, h.stream);
-        p.dbg_dots  = mstep->partial_S->get();   // idle fields carry the M-step outputs (see mstep_smem_bytes)
-        p.cnh       = mstep->partial_W->get();
-        p.raw_slots = k;
-        CUtensorMap tm_hb = make_map_2d(cen.hb.get(), KBLOCK, cen.k_pad, static_cast<uint64_t>(KBLOCK) * 2, KBLOCK, tf.bn,
-                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                        CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-        CUtensorMap tm_lb = make_map_2d(cen.lb.get(), KBLOCK, cen.k_pad, static_cast<uint64_t>(KBLOCK) * 2, KBLOCK, tf.bn,
-                                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                        CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-        CUtensorMap tm_cn = make_map_2d(cen.cnp.get(), 8, cen.k_pad, 8 * sizeof(float), 8, tf.bn, CU_TENSOR_MAP_SWIZZLE_32B,
-                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-        static PerDeviceOnce ms_attr;
-        ms_attr.run(h.device, [&] {
-          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, 0, true, true, true>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
-        });
-        fused_l2_argmin_solo_kernel<true, 0, true, true, true><<<grid, PAIR_THREADS, smem_f, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb,
-                                                                                                        tm_cn, p);
-        mstep->row_blocks = static_cast<int>(grid);
       } else if (cen.bf16c && !best_out) {
         // opt-in single-CTA tf32 + bf16 kernel (CUML_B200_SOLO_V2=1) on the row-packed operands.  (It has no best-value
         // epilogue; the 3xTF32 kernel below reads the same buffers: hi rounded to nearest is still tf32-exact and
@@ -2633,19 +2165,12 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
           CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_solo_kernel<true, 0, false, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
         });
-        if (use_epi_rowown() && t.bn <= TILE_M)   // one centroid tile, >= 4 accumulator stages
+        if (t.bn <= TILE_M)   // one centroid tile, >= 4 accumulator stages: row-owner epilogue
           fused_l2_argmin_solo_kernel<true, 0, false, true><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
         else
           fused_l2_argmin_solo_kernel<true, 0, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
       } else if (best_out) fused_l2_argmin_kernel<3><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
-      else if (use_epi_rowown() && t.bn <= TILE_M) {   // opt-in row-owner epilogue on the 3xTF32 kernel
-        static PerDeviceOnce ro_attr;
-        ro_attr.run(h.device, [&] {
-          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        static_cast<int>(h.smem_optin)));
-        });
-        fused_l2_argmin_kernel<0, true><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
-      } else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+      else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);   // 3xTF32 (CUML_B200_BF16C=0)
       CB2_CHECK_LAUNCH();
       if (h.timing) h.end_event(ev, true);
       if (want_clk) {
@@ -2661,50 +2186,6 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       assign_tail_row_kernel<<<1, 32, 0, h.stream>>>(X + (n - 1) * d, d, k, cen.hi.get(), cen.lo.get(), labels + (n - 1));
       CB2_CHECK_LAUNCH();
     }
-    return;
-  }
-  if (use_ts(h, d, k)) {
-    CB2_EXPECTS(!best_out, "the A-in-TMEM variant has no best-value epilogue");
-    const TsPlan tp = plan_ts(h, d, k);
-    CB2_EXPECTS(tp.bn == cen.block_n, "centroid operand buffers were prepared for a different tile plan");
-    FusedParams p{};
-    p.n = n; p.m_tiles = ceil_div(n, TILE_M); p.k_tiles = cen.k_pad / tp.bn; p.d = d; p.kb = tp.kb; p.bn = tp.bn;
-    p.a_slots = tp.a_slots; p.raw_slots = tp.raw_slots; p.b_stages = tp.b_stages; p.b_resident = tp.b_resident;
-    p.n_acc = tp.n_acc; p.a_col0 = tp.n_acc * tp.bn; p.tmem_cols = 512; p.pack = 1; p.k_sub = 0;
-    p.cnh = cen.cnh.get(); p.labels = labels; p.dbg_dots = dbg_dots;
-    CUtensorMap tm_x = make_map_2d(X, static_cast<uint64_t>(d), static_cast<uint64_t>(n),
-                                   static_cast<uint64_t>(d) * sizeof(float), KBLOCK, TILE_M,
-                                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
-    const uint32_t rows_box = tp.pair ? tp.bn / 2 : tp.bn;
-    CUtensorMap tm_hi = make_map_2d(cen.hi.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * sizeof(float),
-                                    KBLOCK, rows_box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-    CUtensorMap tm_lo = make_map_2d(cen.lo.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * sizeof(float),
-                                    KBLOCK, rows_box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
-    static PerDeviceOnce ts_attr;
-    ts_attr.run(h.device, [&] {
-      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_ts_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(h.smem_optin)));
-      CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_ts_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(h.smem_optin)));
-    });
-    EventPair ev{};
-    if (h.timing) ev = h.begin_event();
-    if (tp.pair) {
-      const int64_t pair_tiles = (p.m_tiles + 1) / 2;
-      const unsigned grid = 2u * static_cast<unsigned>(std::min<int64_t>(pair_tiles, h.sm_count / 2));
-      cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = tp.smem; cfg.stream = h.stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
-      CB2_CUDA(cudaLaunchKernelEx(&cfg, fused_l2_argmin_ts_kernel<true>, tm_x, tm_hi, tm_lo, p));
-    } else {
-      const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
-      fused_l2_argmin_ts_kernel<false><<<grid, NUM_THREADS, tp.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
-    }
-    CB2_CHECK_LAUNCH();
-    if (h.timing) h.end_event(ev, true);
     return;
   }
   const bool pair = use_2cta(h, d, k);
@@ -2738,10 +2219,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     p.raw_slots = dist->sqrt ? 1 : 0;
   }
   {
-    const char* e = std::getenv("CUML_B200_DBG_SKIP");
-    p.dbg_skip    = e ? std::atoi(e) : 0;
-    const char* a = std::getenv("CUML_B200_L2_AHEAD");
-    p.l2_ahead    = a ? std::atoi(a) : 3;
+    p.l2_ahead = 3;   // row tiles prefetched into L2 ahead of the ring (0 / 6 / 12 measured the same)
   }
   DevBuf<long long> clk;
   const bool want_clk = std::getenv("CUML_B200_DBG_CLK") != nullptr;
@@ -2764,13 +2242,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   attr_set.run(h.device, [&] {
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
-    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(h.smem_optin)));
-    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(h.smem_optin)));
-    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
@@ -2780,14 +2252,9 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
                                   static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
-    CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(h.smem_optin)));
     CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   static_cast<int>(h.smem_optin)));
   });
-  // transform only: lane-pair store pattern of the distance-matrix epilogue (DIST = 2 instantiations), opt-in
-  static const bool dist_pair_store =
-    env_flag("CUML_B200_DIST_PAIRST", true);
   EventPair ev{};
   if (h.timing) ev = h.begin_event();
   const long long grid_dbg = pair ? h.sm_count / 2 : h.sm_count;
@@ -2808,31 +2275,27 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       CUtensorMap tm_lb = make_map_2d(cen.lb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
                                       b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-      static const bool conv_trunc = env_flag("CUML_B200_CONV_TRUNC", true);
       if (best_out) {
         fused_l2_argmin_2cta_kernel<true, 3><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
-      } else if (want_clk && !conv_trunc) {   // role-level cycle counters: a separate instantiation, printed below
+      } else if (want_clk) {   // role-level cycle counters: a separate instantiation, printed below
         static PerDeviceOnce clk_attr;
         clk_attr.run(h.device, [&] {
-          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true, 0, false, true>,
+          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_2cta_kernel<true, 0, true, true>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(h.smem_optin)));
         });
-        fused_l2_argmin_2cta_kernel<true, 0, false, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
-      } else if (conv_trunc)
+        fused_l2_argmin_2cta_kernel<true, 0, true, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+      } else {   // the converter leaves the raw tile alone: the tensor core truncates it to tf32 (TRUNC)
         fused_l2_argmin_2cta_kernel<true, 0, true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
-      else
-        fused_l2_argmin_2cta_kernel<true><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+      }
     } else if (best_out) {
       fused_l2_argmin_2cta_kernel<false, 3><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
-    } else if (dist && dist_pair_store) {
+    } else if (dist) {   // distance matrix (transform): 3xTF32, lane-pair stores (32-byte sectors)
       fused_l2_argmin_2cta_kernel<false, 2><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
-    } else if (dist) {
-      fused_l2_argmin_2cta_kernel<false, 1><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     } else {
       fused_l2_argmin_2cta_kernel<false><<<grid, PAIR_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, tm_lo, tm_cn, p);
     }
-  } else if (use_solo_v2() && !best_out) {
-    // opt-in single-CTA twin of the pair kernel (see fused_l2_argmin_solo_kernel)
+  } else if (!best_out) {
+    // single-CTA twin of the pair kernel (see fused_l2_argmin_solo_kernel)
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
     p.fold = (cen.fold && !dbg_dots && solo_fold_fits(t, k, h.smem_optin)) ? 1 : 0;
     const size_t smem = t.smem + (p.fold ? static_cast<size_t>(1 + p.k_tiles) * TILE_M * 32 : 0);
@@ -2858,7 +2321,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       CUtensorMap tm_lb = make_map_2d(cen.lb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
                                       b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-      if (use_epi_rowown() && p.k_tiles == 1 && t.bn <= TILE_M && !dbg_dots)
+      if (p.k_tiles == 1 && t.bn <= TILE_M && !dbg_dots)   // row-owner epilogue
         fused_l2_argmin_solo_kernel<true, 0, false, true><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
       else
         fused_l2_argmin_solo_kernel<true, 0, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
@@ -2869,17 +2332,8 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     }
   } else {
     const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
-    if (best_out) fused_l2_argmin_kernel<3><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
-    else if (dist && dist_pair_store) fused_l2_argmin_kernel<2><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
-    else if (dist) fused_l2_argmin_kernel<1><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
-    else if (use_epi_rowown() && p.k_tiles == 1 && t.bn <= TILE_M && !dbg_dots) {   // opt-in row-owner epilogue
-      static PerDeviceOnce ro_attr;
-      ro_attr.run(h.device, [&] {
-        CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      static_cast<int>(h.smem_optin)));
-      });
-      fused_l2_argmin_kernel<0, true><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
-    } else fused_l2_argmin_kernel<0><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
+    // winning-value epilogue (seeding: min-distance update) of the shapes the single-CTA kernels take
+    fused_l2_argmin_kernel<3><<<grid, NUM_THREADS, t.smem, h.stream>>>(tm_x, tm_hi, tm_lo, p);
   }
   CB2_CHECK_LAUNCH();
   if (h.timing) h.end_event(ev, true);

@@ -112,41 +112,6 @@ def test_baseline_config_shapes_step_and_predict(env, name, n, d, k, init_kind):
     assert abs(inertia.value - ref_in) / ref_in <= 1e-5
 
 
-@pytest.mark.parametrize("n,k", [(100000, 64), (40002, 33), (5000, 8), (131072, 64), (258, 5)])
-@pytest.mark.parametrize("init_kind", ["parity", "throughput"])
-def test_fused_e_m_step_short_rows(env, n, k, init_kind, monkeypatch):
-    # n_features = 16, k <= 64, unweighted, even n: ONE kernel does distance + argmin + centroid sums / counts
-    # (fused_l2_argmin_solo_kernel<.., MSTEP>); it is taken when the caller does not ask for the per-step inertia
-    # (sums_out == NULL), as the Lloyd loop of fit does.  Three consecutive steps against the oracle.
-    # Opt-in since it measured slower than the two-kernel step (CUML_B200_FUSED_MSTEP is read per call).
-    monkeypatch.setenv("CUML_B200_FUSED_MSTEP", "1")
-    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
-    from oracle import blobs, lloyd
-    d = 16
-    X, centres, _ = blobs.make_blobs(n, d, k)
-    C_o = (blobs.parity_init(centres) if init_kind == "parity" else blobs.throughput_init(X, k)).astype(np.float32)
-    Xd = torch.from_numpy(X).cuda()
-    Cd = torch.from_numpy(C_o.copy()).cuda()
-    labels = torch.zeros(n, dtype=torch.int32, device="cuda")
-    shift = torch.zeros(1, dtype=torch.float64, device="cuda")
-    for _ in range(3):
-        C_in = Cd.cpu().numpy().copy()
-        torch.cuda.synchronize()
-        _lib.check(lib.cuml_b200_kmeans_lloyd_step_f32(h.ptr, Xd.data_ptr(), n, d, None, k, Cd.data_ptr(), labels.data_ptr(),
-                                                       None, shift.data_ptr(), 0))
-        h.sync()
-        lab = labels.cpu().numpy()
-        agree, bad = lloyd.label_disagreements_ok(X, C_in, lab, FP32_GAP_TOL)
-        assert agree >= 0.9999 and bad == 0, (agree, bad)
-        S, W, C_ref = lloyd.m_step(X, lab.astype(np.int64), k, C_old=C_in)
-        got = Cd.cpu().numpy()
-        assert np.abs(got - C_ref).max() / np.abs(C_ref).max() < 1e-6
-        # squared shift: relative when the centroids move, absolute (fp32 resolution of the coordinates) at the fixed point
-        shift_o = float(((C_ref - C_in.astype(np.float64)) ** 2).sum())
-        floor = float((C_ref ** 2).sum()) * (2.0 ** -23) ** 2 * 4
-        assert abs(float(shift.item()) - shift_o) <= 1e-4 * shift_o + floor
-
-
 # ---- row-packed kernel with the X operand in tensor memory (fused_l2_argmin_tsp_kernel, CUML_B200_TSP) -------------
 TSP_SHAPES = [(100000, 16, 64), (40002, 16, 33), (5001, 16, 8), (131072, 16, 64), (258, 16, 5), (2000, 8, 5),
               (129, 4, 2), (30000, 12, 40), (70000, 16, 17)]
@@ -154,9 +119,11 @@ TSP_SHAPES = [(100000, 16, 64), (40002, 16, 33), (5001, 16, 8), (131072, 16, 64)
 
 @pytest.mark.parametrize("n,d,k", TSP_SHAPES)
 @pytest.mark.parametrize("init_kind", ["parity", "throughput"])
-def test_tsp_kernel_step_matches_oracle(env, n, d, k, init_kind, monkeypatch):
+@pytest.mark.parametrize("tsp", ["1", "0"])
+def test_tsp_kernel_step_matches_oracle(env, n, d, k, init_kind, tsp, monkeypatch):
+    # tsp = "0": the same shapes on the shared-memory-operand twin (the fallback when CUML_B200_TSP=0)
     from oracle import blobs
-    monkeypatch.setenv("CUML_B200_TSP", "1")
+    monkeypatch.setenv("CUML_B200_TSP", tsp)
     monkeypatch.setenv("CUML_B200_FUSED_MSTEP", "0")
     X, centres, _ = blobs.make_blobs(n, d, k)
     init = (blobs.parity_init(centres) if init_kind == "parity" else blobs.throughput_init(X, k)).astype(np.float32)
@@ -198,8 +165,8 @@ def test_tsp_fused_e_m_step(env, n, k, init_kind, monkeypatch):
 
 @pytest.mark.parametrize("fused", ["0", "1"])
 def test_fused_e_m_fit_matches_oracle_d16(fused, monkeypatch):
-    # end to end through the estimator at the C5 shape (d = 16, k = 64): the Lloyd loop on the two-kernel step (default)
-    # and on the opt-in fused E + M kernel
+    # end to end through the estimator at the C5 shape (d = 16, k = 64): the Lloyd loop on the fused E + M kernel
+    # (default) and on the two-kernel step
     monkeypatch.setenv("CUML_B200_FUSED_MSTEP", fused)
     from cuml_b200.cluster import KMeans
     from oracle import blobs, lloyd
