@@ -32,7 +32,8 @@ def _nvcc():
 
 
 def lib_path():
-    return os.path.join(LIBDIR, LIBNAME)
+    # CUML_B200_LIB: load another build of the library (A/B measurements of compile-time variants)
+    return os.environ.get("CUML_B200_LIB") or os.path.join(LIBDIR, LIBNAME)
 
 
 def _deps():

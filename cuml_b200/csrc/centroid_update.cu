@@ -409,10 +409,37 @@ template <typename T>
 __global__ void weighted_hist_kernel(const int32_t* __restrict__ labels, const T* __restrict__ w, int64_t n, int k,
                                      double* __restrict__ out)
 {
-  // small-k seeding helper (candidate weights); low contention because labels are spread
+  // fallback for tables that do not fit shared memory: global fp64 atomics
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     atomicAdd(out + labels[i], w ? static_cast<double>(w[i]) : 1.0);
+}
+
+// candidate weights of k-means|| (rows per candidate, or their weight sums): a per-block table in shared memory --
+// integer counts when unweighted (native shared-memory atomics, exact), fp64 otherwise -- flushed with one global
+// atomic per non-empty bin.  (The global-atomic kernel above took 9.8 ms for 200M labels over ~640 bins.)
+template <typename T, bool HAS_W>
+__global__ void weighted_hist_smem_kernel(const int32_t* __restrict__ labels, const T* __restrict__ w, int64_t n, int k,
+                                          double* __restrict__ out)
+{
+  extern __shared__ unsigned char hist_raw[];
+  double* hd         = reinterpret_cast<double*>(hist_raw);
+  unsigned int* hc   = reinterpret_cast<unsigned int*>(hist_raw);
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    if (HAS_W) hd[j] = 0.0;
+    else hc[j] = 0u;
+  }
+  __syncthreads();
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+    if (HAS_W) atomicAdd(hd + labels[i], static_cast<double>(w[i]));
+    else atomicAdd(hc + labels[i], 1u);
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const double v = HAS_W ? hd[j] : static_cast<double>(hc[j]);
+    if (v != 0.0) atomicAdd(out + j, v);
+  }
 }
 
 }  // namespace
@@ -580,7 +607,13 @@ void weighted_histogram(Handle& h, const int32_t* labels, const T* w, int64_t n,
 {
   if (n == 0) return;
   int blocks = static_cast<int>(std::min<int64_t>(h.sm_count * 8, ceil_div(n, 256)));
-  weighted_hist_kernel<T><<<blocks, 256, 0, h.stream>>>(labels, w, n, k, out);
+  const size_t bytes = static_cast<size_t>(k) * (w ? sizeof(double) : sizeof(unsigned int));
+  if (bytes <= 40 * 1024) {   // (a block sees n / blocks rows: its integer counts stay far below 2^32)
+    if (w) weighted_hist_smem_kernel<T, true><<<blocks, 256, bytes, h.stream>>>(labels, w, n, k, out);
+    else weighted_hist_smem_kernel<T, false><<<blocks, 256, bytes, h.stream>>>(labels, w, n, k, out);
+  } else {
+    weighted_hist_kernel<T><<<blocks, 256, 0, h.stream>>>(labels, w, n, k, out);
+  }
   CB2_CHECK_LAUNCH();
 }
 
