@@ -51,6 +51,11 @@ void check_params(const cuml_b200_kmeans_params_t& p)
   CB2_EXPECTS(p.n_init >= 1, "n_init must be >= 1");
   CB2_EXPECTS(p.oversampling_factor >= 0.0, "oversampling_factor must be >= 0");
   CB2_EXPECTS(p.device_buffer_samples >= 0, "device_buffer_samples must be >= 0");
+  // raft::random::GeneratorType: GenPhilox = 0, GenPC = 1.  The seeded inits draw from a Philox4x32-10 keyed by the
+  // global row index (what makes a sharded fit draw what the single-GPU fit draws); a PCG request changes results in
+  // the reference, so it is refused here rather than silently served by Philox.
+  CB2_EXPECTS(p.init == CUML_B200_INIT_Array || p.rng_type == 0,
+              "rng_state.type: only the Philox generator (GenPhilox) is implemented for the seeded inits");
 }
 
 // verbosity <= debug (rapids_logger::level_enum numbering: trace 0, debug 1, info 2 ...): one line per Lloyd iteration

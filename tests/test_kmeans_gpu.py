@@ -529,6 +529,26 @@ def test_seeded_inits_recover_blobs(init):
     assert np.array_equal(km.cluster_centers_, km2.cluster_centers_)  # same seed -> same model
 
 
+def test_non_philox_generator_is_refused(env):
+    # kmeans_params.hpp:22 rng_state{0, GenPhilox}: a PCG request (type 1) changes the reference's draws; here it is
+    # refused for the seeded inits instead of being served by Philox, and accepted with init=Array (nothing is drawn)
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    from oracle import blobs
+    X, centres, _ = blobs.make_blobs(2000, 8, 4)
+    Xd = torch.from_numpy(X).cuda()
+    Cd = torch.from_numpy(blobs.parity_init(centres)).cuda()
+    inertia, it = C.c_float(), C.c_int32()
+    for init, want in ((_lib.INIT_KMEANS_PLUS_PLUS, 1), (_lib.INIT_ARRAY, 0)):
+        p = _lib.default_params()
+        p.n_clusters, p.init, p.max_iter, p.rng_type = 4, init, 2, 1
+        torch.cuda.synchronize()
+        st = lib.cuml_b200_kmeans_fit_f32_i32(h.ptr, C.byref(p), Xd.data_ptr(), 2000, 8, None, Cd.data_ptr(),
+                                              C.byref(inertia), C.byref(it))
+        assert st == want
+        if want:
+            assert b"Philox" in lib.cuml_b200_last_error()
+
+
 def test_error_messages_match_reference():
     # reference python/cuml/tests/test_kmeans.py:425-473
     from cuml_b200.cluster import KMeans
