@@ -607,6 +607,7 @@ def run_ours(args):
         # kernel with bf16 correction terms issues 1 tf32 + 2 bf16 MMAs: time per product = 1/(bf16/2) + 2/bf16, so
         # peak(2nkd) = bf16/4 (the denominator is larger, the fraction therefore lower, than under the 3xTF32 rule).
         variant = int(lib.cuml_b200_kmeans_estep_variant(h.ptr, d, k))
+        fused_upd = (not predict_only) and bool(int(lib.cuml_b200_kmeans_fused_update(h.ptr, d, k))) and n_local % 2 == 0
         mma_cost = 4.0 if variant in (3, 5) else 6.0
         tf_peak = peaks["bf16_tflops_sustained"] / mma_cost
         # which roofline binds the fused kernel: time at the tensor peak vs time at the HBM peak
@@ -642,12 +643,12 @@ def run_ours(args):
                          f"({'1 tf32 + 2 bf16 MMAs' if variant in (3, 5) else '3 tf32 MMAs'} per algorithmic product, "
                          f"tf32 = bf16/2); hbm peak = hbm_gbs (copy)",
             "update_kernel": ("none: centroid sums / counts come out of the fused kernel (one pass over X); time below = reduce_partials"
-                              if int(lib.cuml_b200_kmeans_fused_update(h.ptr, d, k)) else
+                              if fused_upd else
                               "accumulate (TMA ring; label-class ownership or lane = column tables) + reduce_partials"),
             "update_kernel_ms": update_ms,
-            "update_kernel_hbm_gbs": 4.0 * n_local * (d + 1) / (update_ms * 1e-3) / 1e9 if update_ms > 0 else None,
+            "update_kernel_hbm_gbs": 4.0 * n_local * (d + 1) / (update_ms * 1e-3) / 1e9 if (update_ms > 0 and not fused_upd) else None,
             "update_kernel_frac_of_hbm_peak": (4.0 * n_local * (d + 1) / (update_ms * 1e-3) / 1e9 / peaks["hbm_gbs"])
-                                              if update_ms > 0 else None,
+                                              if (update_ms > 0 and not fused_upd) else None,
             "hbm_peak_gbs": peaks["hbm_gbs"], "tensor_peak_tflops": tf_peak})
         metric, unit = metric_unit(args.workload)
         line = {
