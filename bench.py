@@ -607,7 +607,7 @@ def run_ours(args):
         # kernel with bf16 correction terms issues 1 tf32 + 2 bf16 MMAs: time per product = 1/(bf16/2) + 2/bf16, so
         # peak(2nkd) = bf16/4 (the denominator is larger, the fraction therefore lower, than under the 3xTF32 rule).
         variant = int(lib.cuml_b200_kmeans_estep_variant(h.ptr, d, k))
-        fused_upd = (not predict_only) and bool(int(lib.cuml_b200_kmeans_fused_update(h.ptr, d, k))) and n_local % 2 == 0
+        fused_upd = (not predict_only) and bool(int(lib.cuml_b200_kmeans_fused_update(h.ptr, d, k))) and n_local >= 2
         mma_cost = 4.0 if variant in (3, 5) else 6.0
         tf_peak = peaks["bf16_tflops_sustained"] / mma_cost
         # which roofline binds the fused kernel: time at the tensor peak vs time at the HBM peak

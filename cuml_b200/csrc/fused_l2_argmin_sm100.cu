@@ -2015,6 +2015,15 @@ __global__ void assign_tail_row_kernel(const float* __restrict__ x, int d, int k
   if (threadIdx.x == 0) *label = bidx;
 }
 
+// fused M-step with an odd number of rows: the last row (labelled by assign_tail_row_kernel) is added to CTA 0's partials
+__global__ void mstep_tail_row_kernel(const float* __restrict__ x, int d, const int32_t* __restrict__ label,
+                                      float* __restrict__ S0, float* __restrict__ W0)
+{
+  const int j = *label;
+  for (int c = threadIdx.x; c < d; c += 32) S0[static_cast<int64_t>(j) * d + c] += x[c];
+  if (threadIdx.x == 0) W0[j] += 1.0f;
+}
+
 bool tc_transform_supported(const Handle& h, int64_t d, int k)
 {
   // the distance-matrix epilogue exists for the unpacked shared-memory-operand kernels
@@ -2108,7 +2117,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       if (h.timing) ev = h.begin_event();
       const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.m_tiles, h.sm_count));
       TspPlan tp{};
-      const bool tsp_mstep = mstep && (n & 1) == 0 && fused_mstep_on();
+      const bool tsp_mstep = mstep && fused_mstep_on();   // (an odd last row is added to CTA 0's partials below)
       if (use_tsp() && cen.bf16c && cen.fold && !best_out && plan_tsp(h, d, k, tsp_mstep, tp)) {
         // ---- X operand in tensor memory (fused_l2_argmin_tsp_kernel), optionally with the fused M-step ----
         p.raw_slots = tp.raw_slots; p.a_slots = 2; p.n_acc = tp.n_acc; p.a_col0 = tp.a_col0; p.tmem_cols = 512;
@@ -2185,6 +2194,11 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
     if (n & 1) {   // (labels only: a caller that wants the winning value of an odd last row computes it itself)
       assign_tail_row_kernel<<<1, 32, 0, h.stream>>>(X + (n - 1) * d, d, k, cen.hi.get(), cen.lo.get(), labels + (n - 1));
       CB2_CHECK_LAUNCH();
+      if (mstep && mstep->row_blocks > 0) {   // fused M-step: the odd row joins CTA 0's partial sums / counts
+        mstep_tail_row_kernel<<<1, 32, 0, h.stream>>>(X + (n - 1) * d, d, labels + (n - 1), mstep->partial_S->get(),
+                                                      mstep->partial_W->get());
+        CB2_CHECK_LAUNCH();
+      }
     }
     return;
   }

@@ -173,7 +173,7 @@ class LloydSolver {
   }
 
   // E-step and M-step in one pass over X where the fused kernel applies (fp32, n_features = 16, k <= 64, no weights,
-  // even partition sizes): labels + packed sums / weights.  false = not applicable, nothing was launched.
+  // at least two rows per partition): labels + packed sums / weights.  false = not applicable, nothing was launched.
   bool assign_accumulate_fused(const T* C)
   {
     if constexpr (!std::is_same<T, float>::value) {
@@ -181,7 +181,7 @@ class LloydSolver {
     } else {
       if (!use_tc_ || parts_.empty() || !tc_fused_update_supported(h_, d_, k_)) return false;
       for (auto& p : parts_)
-        if (p.w != nullptr || (p.n & 1) != 0 || p.n == 0) return false;
+        if (p.w != nullptr || p.n < 2) return false;
       prepare(C);
       for (size_t i = 0; i < parts_.size(); ++i) {
         TcMstepOut ms;

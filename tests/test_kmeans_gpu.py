@@ -131,7 +131,7 @@ def test_tsp_kernel_step_matches_oracle(env, n, d, k, init_kind, tsp, monkeypatc
     _check_step_against_oracle(X, init, k, lab, packed, C_new, shift2)
 
 
-@pytest.mark.parametrize("n,k", [(100000, 64), (40002, 33), (5000, 8), (131072, 64), (258, 5)])
+@pytest.mark.parametrize("n,k", [(100000, 64), (40002, 33), (5000, 8), (131072, 64), (258, 5), (40001, 64), (257, 3), (3, 2)])
 @pytest.mark.parametrize("init_kind", ["parity", "throughput"])
 def test_tsp_fused_e_m_step(env, n, k, init_kind, monkeypatch):
     # the same kernel with the fused M-step (one pass over X per Lloyd step), three consecutive steps against the oracle
@@ -691,6 +691,61 @@ def test_full_size_c3_properties(env):
         agree = (dist.argmin(1).int() == labels[idx]).double().mean().item()
         assert agree >= 0.9999, agree
         del again, xs, dist
+
+
+def test_full_size_c5_fused_step_properties(env):
+    # BASELINE config C5 at its FULL size (n = 200M, d = 16, k = 64; 12.8 GB of X) on the one-pass E + M kernel
+    # (fused_l2_argmin_tsp_kernel<MSTEP>, taken when the caller does not ask for the per-step sums): the new centroids
+    # are the per-cluster means of the labels the same launch produced (sums vs a torch index_add_ in fp64, every row
+    # counted once: sum_j W_j c_j = column sums of X), the labels equal those of the stand-alone E-step kernel, and a
+    # sample of rows carries the exact fp64 argmin.
+    torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
+    n, d, k = 200_000_000, 16, 64
+    free, _ = torch.cuda.mem_get_info()
+    if free < 30 * 2**30:
+        pytest.skip("needs 30 GB of free device memory")
+    assert lib.cuml_b200_kmeans_fused_update(h.ptr, d, k) == 1
+    g = torch.Generator(device="cuda").manual_seed(77)
+    cent = torch.rand((k, d), device="cuda", generator=g) * 20 - 10
+    X = torch.empty((n, d), dtype=torch.float32, device="cuda")
+    colsum = torch.zeros(d, dtype=torch.float64, device="cuda")
+    chunk = 1 << 23
+    for s0 in range(0, n, chunk):
+        e0 = min(n, s0 + chunk)
+        lab = torch.randint(0, k, (e0 - s0,), device="cuda", generator=g)
+        X[s0:e0] = cent[lab]
+        X[s0:e0] += torch.randn((e0 - s0, d), device="cuda", generator=g)
+        colsum += X[s0:e0].double().sum(0)
+        del lab
+    Cd = X[torch.randint(0, n, (k,), device="cuda", generator=g)].clone()
+    labels = torch.zeros(n, dtype=torch.int32, device="cuda")
+    for it in range(2):
+        C_before = Cd.clone()
+        torch.cuda.synchronize()
+        _lib.check(lib.cuml_b200_kmeans_lloyd_step_f32(h.ptr, X.data_ptr(), n, d, None, k, Cd.data_ptr(),
+                                                       labels.data_ptr(), None, None, 0))
+        h.sync()
+        W = torch.bincount(labels.long(), minlength=k).double()
+        assert W.sum().item() == n
+        S_ref = torch.zeros((k, d), dtype=torch.float64, device="cuda")
+        for s0 in range(0, n, chunk):
+            e0 = min(n, s0 + chunk)
+            S_ref.index_add_(0, labels[s0:e0].long(), X[s0:e0].double())
+        C_ref = torch.where(W[:, None] > 0, S_ref / W.clamp(min=1)[:, None], C_before.double())
+        assert ((Cd.double() - C_ref).abs().max() / C_ref.abs().max()).item() < 1e-6
+        assert (((W[:, None] * Cd.double()).sum(0) - colsum).abs().max() / colsum.abs().max()).item() < 1e-5
+        again = torch.zeros(n, dtype=torch.int32, device="cuda")
+        torch.cuda.synchronize()
+        _lib.check(lib.cuml_b200_kmeans_assign_f32(h.ptr, X.data_ptr(), n, d, k, C_before.data_ptr(),
+                                                   again.data_ptr(), 0))
+        h.sync()
+        assert torch.equal(again, labels)                                   # fused and stand-alone E-step agree
+        idx = torch.cat([torch.randint(0, n, (100_000,), device="cuda", generator=g),
+                         torch.arange(n - 1000, n, device="cuda")])
+        xs, c64 = X[idx].double(), C_before.double()
+        dist = (xs * xs).sum(1, keepdim=True) - 2 * xs @ c64.T + (c64 * c64).sum(1)[None, :]
+        assert (dist.argmin(1).int() == labels[idx]).double().mean().item() >= 0.9999
+        del again, xs, dist, S_ref
 
 
 def test_cpp_surface_example_kat(tmp_path):
