@@ -39,9 +39,11 @@ WORKLOADS = {
 # roofline.traffic = dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant (fused) kernel at the
 # full single-GPU workload, taken from the committed `ncu --set full` captures (bytes cannot be counted inside a timed
 # run); roofline.traffic_source names the file.  Absent capture => null.
-TRAFFIC_NCU = {"C3": (25.602643e9 + 0.401213e9, "profiles/r01_ncu_full_c3.txt"),
+TRAFFIC_NCU = {"C3": (25.602092e9 + 0.401808e9, "profiles/r02_ncu_full_c3.txt"),
                "C2": (5.121371e9 + 0.042751e9, "profiles/r01_ncu_full_c2.txt"),
-               "C5": (12.800976e9 + 0.748216e9, "profiles/r02_ncu_full_c5_before.txt")}
+               # C4 streams the X K-blocks once per centroid tile (16 tiles): 820 GB reach the SMs, L2 serves 78 % of it
+               "C4": (368.469337e9 + 0.216847e9, "profiles/r02_ncu_full_c4.txt"),
+               "C5": (12.800274e9 + 0.746665e9, "profiles/r02_ncu_full_c5.txt")}
 METRIC = "kmeans_lloyd_iters_per_sec"
 UNIT = "Lloyd iter/s"
 
