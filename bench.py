@@ -398,7 +398,10 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
-    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else "single rank: not bound"
+    # pinned host buffers should come from the GPU's own NUMA node at every N (a single-rank run that landed on the far
+    # node measured 31 instead of 55 GB/s of H2D: e2e 16 instead of 24.5 iter/s); the CPU baseline gets every core back
+    full_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(torch, local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n, d, k, desc = WORKLOADS[args.workload]
@@ -674,6 +677,10 @@ def run_ours(args):
         if parity is not None:
             line["parity_fit"] = parity
         if world == 1 and not args.no_cpu:
+            try:
+                os.sched_setaffinity(0, full_affinity)   # the CPU baseline runs on every core again
+            except OSError:
+                pass
             if predict_only:
                 rate, cores, sample, _ = cpu_reference_predict_rate(n, d, k, budget_s=args.cpu_budget or 20.0)
             else:
