@@ -1455,9 +1455,10 @@ fused_l2_argmin_tsp_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
   const uint32_t fold_u32 = base + fold_off;
   Barriers* bars          = reinterpret_cast<Barriers*>(gbase + fold_off + 2u * FOLD_TILE);
   float* ms_tab           = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ((sizeof(Barriers) + 127) & ~size_t(127)));
-  const int ms_rows       = p.k_sub + 1;   // private table rows per accumulate warp: k_sub clusters + one dummy row
+  const int ms_k          = p.pack > 1 ? p.k_sub : p.bn;   // accumulator columns per data row = table rows
+  const int ms_rows       = ms_k + 1;      // private table rows per accumulate warp: the clusters + one dummy row
   int* ms_counts          = reinterpret_cast<int*>(ms_tab + static_cast<size_t>(TSP_ACC_WARPS) * ms_rows * 32);
-  uint32_t* ms_labels     = reinterpret_cast<uint32_t*>(ms_counts + 2 * p.k_sub);
+  uint32_t* ms_labels     = reinterpret_cast<uint32_t*>(ms_counts + 2 * ms_k);
 
   const int warp = threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
@@ -1486,7 +1487,7 @@ fused_l2_argmin_tsp_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
     ptx::fence_proxy_async_smem();
   }
   if (MSTEP) {
-    for (int i = threadIdx.x; i < TSP_ACC_WARPS * ms_rows * 32 + 2 * p.k_sub; i += blockDim.x) ms_tab[i] = 0.0f;   // tables + counts
+    for (int i = threadIdx.x; i < TSP_ACC_WARPS * ms_rows * 32 + 2 * ms_k; i += blockDim.x) ms_tab[i] = 0.0f;   // tables + counts
   }
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tm_x);
@@ -1627,12 +1628,13 @@ fused_l2_argmin_tsp_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
   } else if (MSTEP && warp >= 20) {
     // ===================== fused M-step: accumulate warps 20..27 (16 operand rows of every tile each) ===============
     const int aw         = warp - 20;
-    // lane = (data row of the packed pair, column): lane l only ever touches bank l of its warp's private table
+    // lane = (data row of the packed pair, column) -- or simply the column of an unpacked row: lane l only ever touches
+    // bank l of its warp's private table
     uint8_t* tab         = reinterpret_cast<uint8_t*>(ms_tab + static_cast<size_t>(aw) * ms_rows * 32 + lane);
-    const uint32_t sel   = (lane >> 4) ? 0x4432u : 0x4410u;                        // byte_perm selector: this half's 16 bits
+    const uint32_t sel   = (p.pack > 1 && (lane >> 4)) ? 0x4432u : 0x4410u;        // byte_perm selector: this half's 16 bits
     const uint32_t xch   = static_cast<uint32_t>(lane >> 2);                       // logical 16-byte chunk of the lane's float
     const uint32_t xin   = static_cast<uint32_t>(lane & 3) * 4u;
-    const uint32_t dummy = static_cast<uint32_t>(p.k_sub) * 128u;                  // byte offset of the row nobody reads
+    const uint32_t dummy = static_cast<uint32_t>(ms_k) * 128u;                     // byte offset of the row nobody reads
     Ring rr;
     for (int64_t t = cta; t < tiles; t += n_ctas) {
       const uint32_t rs = rr.slot, rp = rr.phase;
@@ -1677,16 +1679,17 @@ fused_l2_argmin_tsp_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
   if (MSTEP) {
     // fold the private tables in a fixed order (accumulate warp 0..7, packed group 0 then 1) into this CTA's partials
     const int k_true = p.a_stream;
-    float* out_S     = p.dbg_dots + static_cast<size_t>(blockIdx.x) * k_true * 16;
+    const int d_true = p.pack > 1 ? p.d / 2 : p.d;
+    float* out_S     = p.dbg_dots + static_cast<size_t>(blockIdx.x) * k_true * d_true;
     float* out_W     = const_cast<float*>(p.cnh) + static_cast<size_t>(blockIdx.x) * k_true;
-    for (int e = threadIdx.x; e < k_true * 16; e += blockDim.x) {
-      const int j = e >> 4, c = e & 15;
+    for (int e = threadIdx.x; e < k_true * d_true; e += blockDim.x) {
+      const int j = e / d_true, c = e - j * d_true;
       float acc = 0.0f;
 #pragma unroll
       for (int w = 0; w < TSP_ACC_WARPS; ++w) {
         const float* tw = ms_tab + (static_cast<size_t>(w) * ms_rows + j) * 32;
         acc += tw[c];
-        acc += tw[16 + c];
+        if (p.pack > 1) acc += tw[16 + c];
       }
       out_S[e] = acc;
     }
@@ -2048,12 +2051,23 @@ struct TspPlan {
 };
 static bool plan_tsp(const Handle& h, int d, int k, bool mstep, TspPlan& out)
 {
+  if (h.cc_major != 10 || !use_bf16_corrections() || !use_cn_fold()) return false;
   const int k_sub = pack_k_sub(d, k);
-  if (h.cc_major != 10 || k_sub == 0 || k_sub > 64 || !use_bf16_corrections() || !use_cn_fold()) return false;
-  if (mstep && d != 16) return false;
-  const int bn       = 2 * k_sub;
+  int bn, ms_k;
+  if (k_sub) {   // two data rows per operand row (n_features <= 16), block-diagonal centroids
+    if (k_sub > 64 || (mstep && d != 16)) return false;
+    bn   = 2 * k_sub;
+    ms_k = k_sub;
+  } else {       // one data row per operand row: 17..32 features in one K-block, one centroid tile of <= 128 columns
+    if (d > KBLOCK || d % 4 != 0 || k > 128) return false;
+    const TilePlan t = plan_tiles(d, k, h.smem_optin);
+    if (t.bn == 0 || t.bn > 128 || t.kb != 1 || k > t.bn || !solo_fold_fits(t, k, h.smem_optin)) return false;
+    bn   = t.bn;
+    ms_k = bn;
+    if (mstep && bn > 64) return false;   // eight private tables of bn + 1 rows
+  }
   const size_t fixed = static_cast<size_t>(bn) * 256 + 2 * static_cast<size_t>(TILE_M) * 32 +
-                       ((sizeof(Barriers) + 127) & ~size_t(127)) + (mstep ? tsp_mstep_smem_bytes(k_sub) : 0) + 1024;
+                       ((sizeof(Barriers) + 127) & ~size_t(127)) + (mstep ? tsp_mstep_smem_bytes(ms_k) : 0) + 1024;
   if (h.smem_optin < fixed + 3 * static_cast<size_t>(KBLOCK_BYTES)) return false;
   out.raw_slots = static_cast<int>(std::min<size_t>(mstep ? MAX_A_SLOTS : MAX_RAW, (h.smem_optin - fixed) / KBLOCK_BYTES));
   out.n_acc     = std::min(mstep ? 3 : 4, (512 - 128) / bn);   // fused M-step: warps 20..23 accumulate, 3 epilogue groups
@@ -2335,7 +2349,34 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
       CUtensorMap tm_lb = make_map_2d(cen.lb.get(), cen.d_pad, cen.k_pad, static_cast<uint64_t>(cen.d_pad) * 2, KBLOCK,
                                       b_box_rows, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
-      if (p.k_tiles == 1 && t.bn <= TILE_M && !dbg_dots)   // row-owner epilogue
+      TspPlan tp{};
+      const bool tsp_mstep = mstep && fused_mstep_on();
+      if (use_tsp() && p.fold && !dbg_dots && p.k_tiles == 1 && plan_tsp(h, d, k, tsp_mstep, tp)) {
+        // ---- 17..32 features, k <= 128: X operand in tensor memory (fused_l2_argmin_tsp_kernel, one data row per
+        // operand row), optionally with the fused M-step ----
+        p.raw_slots = tp.raw_slots; p.a_slots = 2; p.n_acc = tp.n_acc; p.a_col0 = tp.a_col0; p.tmem_cols = 512;
+        p.b_resident = 1; p.b_stages = 1;
+        if (tsp_mstep) {
+          if (mstep->partial_S->n < static_cast<size_t>(grid) * k * d) mstep->partial_S->alloc(static_cast<size_t>(grid) * k * d, h.stream);
+          if (mstep->partial_W->n < static_cast<size_t>(grid) * k) mstep->partial_W->alloc(static_cast<size_t>(grid) * k, h.stream);
+          p.dbg_dots = mstep->partial_S->get();   // idle fields carry the M-step outputs (see the kernel's header)
+          p.cnh      = mstep->partial_W->get();
+          p.a_stream = k;
+        }
+        static PerDeviceOnce tspu_attr;
+        tspu_attr.run(h.device, [&] {
+          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_tsp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(h.smem_optin)));
+          CB2_CUDA(cudaFuncSetAttribute(fused_l2_argmin_tsp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        static_cast<int>(h.smem_optin)));
+        });
+        if (tsp_mstep) {
+          fused_l2_argmin_tsp_kernel<true><<<grid, PAIR_THREADS, tp.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+          mstep->row_blocks = static_cast<int>(grid);
+        } else {
+          fused_l2_argmin_tsp_kernel<false><<<grid, PAIR_THREADS, tp.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
+        }
+      } else if (p.k_tiles == 1 && t.bn <= TILE_M && !dbg_dots)   // row-owner epilogue
         fused_l2_argmin_solo_kernel<true, 0, false, true><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
       else
         fused_l2_argmin_solo_kernel<true, 0, false><<<grid, PAIR_THREADS, smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);

@@ -114,7 +114,9 @@ def test_baseline_config_shapes_step_and_predict(env, name, n, d, k, init_kind):
 
 # ---- row-packed kernel with the X operand in tensor memory (fused_l2_argmin_tsp_kernel, CUML_B200_TSP) -------------
 TSP_SHAPES = [(100000, 16, 64), (40002, 16, 33), (5001, 16, 8), (131072, 16, 64), (258, 16, 5), (2000, 8, 5),
-              (129, 4, 2), (30000, 12, 40), (70000, 16, 17)]
+              (129, 4, 2), (30000, 12, 40), (70000, 16, 17),
+              # one data row per operand row: 17..32 features, k <= 128 (C1's shape among them)
+              (60000, 32, 16), (5000, 24, 40), (3001, 20, 3), (40000, 32, 100), (131072, 28, 64), (300, 32, 128)]
 
 
 @pytest.mark.parametrize("n,d,k", TSP_SHAPES)
@@ -131,15 +133,18 @@ def test_tsp_kernel_step_matches_oracle(env, n, d, k, init_kind, tsp, monkeypatc
     _check_step_against_oracle(X, init, k, lab, packed, C_new, shift2)
 
 
-@pytest.mark.parametrize("n,k", [(100000, 64), (40002, 33), (5000, 8), (131072, 64), (258, 5), (40001, 64), (257, 3), (3, 2)])
+@pytest.mark.parametrize("n,d,k", [(100000, 16, 64), (40002, 16, 33), (5000, 16, 8), (131072, 16, 64), (258, 16, 5),
+                                   (40001, 16, 64), (257, 16, 3), (3, 16, 2),
+                                   # unpacked rows (17..32 features, k <= 64): C1's shape, ragged tails, d % 32 != 0
+                                   (60000, 32, 16), (20001, 32, 64), (5000, 24, 40), (999, 20, 3), (131072, 32, 33)])
 @pytest.mark.parametrize("init_kind", ["parity", "throughput"])
-def test_tsp_fused_e_m_step(env, n, k, init_kind, monkeypatch):
+def test_tsp_fused_e_m_step(env, n, d, k, init_kind, monkeypatch):
     # the same kernel with the fused M-step (one pass over X per Lloyd step), three consecutive steps against the oracle
     monkeypatch.setenv("CUML_B200_TSP", "1")
     torch, _lib, lib, h = env["torch"], env["_lib"], env["lib"], env["h"]
     from oracle import blobs, lloyd
     monkeypatch.setenv("CUML_B200_FUSED_MSTEP", "1")
-    d = 16
+    assert lib.cuml_b200_kmeans_fused_update(h.ptr, d, k) == 1
     X, centres, _ = blobs.make_blobs(n, d, k)
     C_o = (blobs.parity_init(centres) if init_kind == "parity" else blobs.throughput_init(X, k)).astype(np.float32)
     Xd = torch.from_numpy(X).cuda()
@@ -154,7 +159,9 @@ def test_tsp_fused_e_m_step(env, n, k, init_kind, monkeypatch):
         h.sync()
         lab = labels.cpu().numpy()
         agree, bad = lloyd.label_disagreements_ok(X, C_in, lab, FP32_GAP_TOL)
-        assert agree >= 0.9999 and bad == 0, (agree, bad)
+        # (below 10 000 rows a single excusable near-tie already exceeds 0.01 %: the throughput init puts centroids
+        # inside the same blob, whose rows then sit close to the boundary)
+        assert (agree >= 0.9999 or round((1.0 - agree) * n) <= 1) and bad == 0, (agree, bad)
         S, W, C_ref = lloyd.m_step(X, lab.astype(np.int64), k, C_old=C_in)
         got = Cd.cpu().numpy()
         assert np.abs(got - C_ref).max() / np.abs(C_ref).max() < 1e-6
