@@ -1631,7 +1631,10 @@ fused_l2_argmin_tsp_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
     // lane = (data row of the packed pair, column) -- or simply the column of an unpacked row: lane l only ever touches
     // bank l of its warp's private table
     uint8_t* tab         = reinterpret_cast<uint8_t*>(ms_tab + static_cast<size_t>(aw) * ms_rows * 32 + lane);
-    const uint32_t sel   = (p.pack > 1 && (lane >> 4)) ? 0x4432u : 0x4410u;        // byte_perm selector: this half's 16 bits
+    // packed rows: the operand row is [data row 2r (d floats) | data row 2r+1 (d floats) | zero fill]; lanes past 2 d add
+    // the zero fill into columns nobody reads
+    const int d_row      = p.pack > 1 ? p.d / 2 : p.d;
+    const uint32_t sel   = (p.pack > 1 && lane >= d_row && lane < 2 * d_row) ? 0x4432u : 0x4410u;   // this half's 16 bits
     const uint32_t xch   = static_cast<uint32_t>(lane >> 2);                       // logical 16-byte chunk of the lane's float
     const uint32_t xin   = static_cast<uint32_t>(lane & 3) * 4u;
     const uint32_t dummy = static_cast<uint32_t>(ms_k) * 128u;                     // byte offset of the row nobody reads
@@ -1689,7 +1692,7 @@ fused_l2_argmin_tsp_kernel(const __grid_constant__ CUtensorMap tm_x, const __gri
       for (int w = 0; w < TSP_ACC_WARPS; ++w) {
         const float* tw = ms_tab + (static_cast<size_t>(w) * ms_rows + j) * 32;
         acc += tw[c];
-        if (p.pack > 1) acc += tw[16 + c];
+        if (p.pack > 1) acc += tw[d_true + c];
       }
       out_S[e] = acc;
     }
@@ -1797,6 +1800,9 @@ int pack_k_sub(int d, int k)
   const char* e = std::getenv("CUML_B200_PACK");
   if (e && std::atoi(e) == 0) return 0;
   if (d > 16 || d % 4 != 0 || k > 128) return 0;
+  // 65..128 clusters: the packed operand would need a 256-column accumulator tile (no row-owner epilogue, no tensor-memory
+  // kernel); one data row per operand row on the tensor-memory kernel measures 3.2 against 4.8 ms (100M x 16, k = 100)
+  if (k > 64 && env_flag("CUML_B200_TSP", true)) return 0;
   return k <= 32 ? 32 : (k <= 64 ? 64 : 128);
 }
 
@@ -2055,7 +2061,9 @@ static bool plan_tsp(const Handle& h, int d, int k, bool mstep, TspPlan& out)
   const int k_sub = pack_k_sub(d, k);
   int bn, ms_k;
   if (k_sub) {   // two data rows per operand row (n_features <= 16), block-diagonal centroids
-    if (k_sub > 64 || (mstep && d != 16)) return false;
+    // fused M-step: its cost is per operand row, so it pays for rows of 8+ features (200M rows: 16 features 4.6 against
+    // 7.0 ms, 8 features 4.8 against 4.8, 4 features 4.4 against 3.5 -- there the stand-alone M-step takes 0.65 ms)
+    if (k_sub > 64 || (mstep && d < 8)) return false;
     bn   = 2 * k_sub;
     ms_k = k_sub;
   } else {       // one data row per operand row: 17..32 features in one K-block, one centroid tile of <= 128 columns

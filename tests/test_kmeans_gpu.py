@@ -116,7 +116,9 @@ def test_baseline_config_shapes_step_and_predict(env, name, n, d, k, init_kind):
 TSP_SHAPES = [(100000, 16, 64), (40002, 16, 33), (5001, 16, 8), (131072, 16, 64), (258, 16, 5), (2000, 8, 5),
               (129, 4, 2), (30000, 12, 40), (70000, 16, 17),
               # one data row per operand row: 17..32 features, k <= 128 (C1's shape among them)
-              (60000, 32, 16), (5000, 24, 40), (3001, 20, 3), (40000, 32, 100), (131072, 28, 64), (300, 32, 128)]
+              (60000, 32, 16), (5000, 24, 40), (3001, 20, 3), (40000, 32, 100), (131072, 28, 64), (300, 32, 128),
+              # short rows with 65..128 clusters: unpacked as well (the packed operand would need a 256-column tile)
+              (50000, 16, 100), (30000, 8, 128)]
 
 
 @pytest.mark.parametrize("n,d,k", TSP_SHAPES)
@@ -136,7 +138,9 @@ def test_tsp_kernel_step_matches_oracle(env, n, d, k, init_kind, tsp, monkeypatc
 @pytest.mark.parametrize("n,d,k", [(100000, 16, 64), (40002, 16, 33), (5000, 16, 8), (131072, 16, 64), (258, 16, 5),
                                    (40001, 16, 64), (257, 16, 3), (3, 16, 2),
                                    # unpacked rows (17..32 features, k <= 64): C1's shape, ragged tails, d % 32 != 0
-                                   (60000, 32, 16), (20001, 32, 64), (5000, 24, 40), (999, 20, 3), (131072, 32, 33)])
+                                   (60000, 32, 16), (20001, 32, 64), (5000, 24, 40), (999, 20, 3), (131072, 32, 33),
+                                   # packed rows shorter than 16 features
+                                   (60000, 8, 64), (20001, 12, 40)])
 @pytest.mark.parametrize("init_kind", ["parity", "throughput"])
 def test_tsp_fused_e_m_step(env, n, d, k, init_kind, monkeypatch):
     # the same kernel with the fused M-step (one pass over X per Lloyd step), three consecutive steps against the oracle
