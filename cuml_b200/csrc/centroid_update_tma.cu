@@ -986,7 +986,7 @@ void tma_update_accumulate(Handle& h, const float* X, int64_t n, int d, const in
     return;
   }
   if (const int lc_warps = lanecol_warps(h, d, k); lc_warps > 0) {
-    // opt-in lane = column kernel for short rows (see accumulate_lanecol_kernel)
+    // lane = column kernel for short rows (see accumulate_lanecol_kernel)
     const int rows_batch = LC_U * (32 / d);
     const int64_t batches = ceil_div(n, rows_batch);
     int64_t rb = std::min<int64_t>(h.sm_count, ceil_div(batches, lc_warps));

@@ -5,18 +5,20 @@
 //
 // The x.c contraction runs on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in TMEM) in split
 // precision, hi = x rounded / truncated to tf32, lo = x - hi (exact in fp32):
-//   3xTF32          x.c ~= x_lo.c_hi + x_hi.c_lo + x_hi.c_hi, all kind::tf32          (single-CTA kernel)
 //   tf32 + 2 bf16   x_hi.c_hi as kind::tf32, the two correction terms as kind::f16 with bf16 operands (half
 //                   the MMA instructions per term); -1/2||c||^2 enters the accumulator through one extra
-//                   K = 8 MMA of a ones tile with three tf32-exact pieces               (CTA-pair kernel)
+//                   K = 8 MMA of a ones tile with three tf32-exact pieces               (default everywhere)
+//   3xTF32          x.c ~= x_lo.c_hi + x_hi.c_lo + x_hi.c_hi, all kind::tf32     (CUML_B200_BF16C=0, transform)
 // Both give fp32-grade labels (tests/test_kmeans_gpu.py::test_tensor_core_dot_accuracy, label-gap tests).
 //
 // Persistent warp-specialised kernels, one CTA per SM:
 //   fused_l2_argmin_2cta_kernel  k > 128: two CTAs of a TPC share M = 256, N = 256 MMAs (cta_group::2), each
 //                                holds half of every centroid block; 8 converter warps, 16 epilogue warps
-//   fused_l2_argmin_kernel       k <= 128 and the row-packed small-d case
-//   fused_l2_argmin_tsp_kernel   n_features <= 16 (two data rows per operand row), k <= 64: X operand in tensor memory,
-//                                optionally with the M-step fused in (one pass over X per Lloyd step)
+//   fused_l2_argmin_solo_kernel  k <= 128: the same roles in one CTA, row-owner epilogue for one centroid tile
+//   fused_l2_argmin_tsp_kernel   n_features <= 32 with few clusters: X operand in tensor memory (converter writes TMEM
+//                                columns, A-from-TMEM MMAs), optionally with the M-step fused in (one pass over X per
+//                                Lloyd step)
+//   fused_l2_argmin_kernel       round 1's 3xTF32 kernel: winning-value epilogue of the seeding rounds, 3xTF32 row-packed
 // Roles: TMA producers for X and centroid K-blocks (128B / 64B / 32B-swizzled tiles), converter warps that
 // split the raw X tile in shared memory, one MMA-issuing warp (uniform control flow, elect.sync lane), and the
 // argmin epilogue (tcgen05.ld, thread = row, four (min, argmin) chains, parts merged through shared memory).
@@ -221,7 +223,7 @@ __device__ __forceinline__ void epilogue_role(const FusedParams& p, Barriers* ba
           }
         }
         if (DIST == 2) {
-          // opt-in store pattern (CUML_B200_DIST_PAIRST=1 selects the DIST = 2 instantiations; not yet measured): lanes 2i and 2i+1 swap half of every
+          // store pattern of the CTA-pair kernel (1.2 -> 1.7 TB/s of output at the C4 shape): lanes 2i and 2i+1 swap half of every
           // 8-column group, so each store instruction writes 32 contiguous bytes (a whole sector) of ONE row per
           // lane pair instead of 16 bytes in two different rows.  Same values, same addresses, other lanes.
           const int64_t row   = first_row + t * row_stride + rit;
@@ -717,7 +719,7 @@ fused_l2_argmin_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_co
 // rounding lo and hi to bf16 perturbs each correction by <= 2^-9 relative: ~2^-20 |x||c| per product -- the size of
 // the lo.lo term every 3xTF32 scheme drops.  Operand slot layout per 32-feature K-block:
 //   [0, 16 KB) hi tf32, 128B swizzle | [16 KB, 24 KB) hi bf16, 64B swizzle | [24 KB, 32 KB) lo bf16, 64B swizzle
-// TRUNC (opt-in experiment, CUML_B200_CONV_TRUNC=1): hi = x truncated to tf32, which is what the tensor core reads
+// TRUNC (the shipped E-step instantiation; C3 12.3 -> 11.9 ms): hi = x truncated to tf32, which is what the tensor core reads
 // from the raw fp32 tile anyway, so the converter neither rounds nor rewrites the tile (fewer instructions on the
 // issue-bound d = 64 path) at the price of |lo| <= 2^-11 |x| instead of 2^-12.
 template <bool BF16C, int DIST = 0, bool TRUNC = false, bool CLK = false>
@@ -1077,9 +1079,9 @@ fused_l2_argmin_2cta_kernel(const __grid_constant__ CUtensorMap tm_x, const __gr
   if (warp == 1) ptx::tmem_dealloc_2cta(tmem_base, p.tmem_cols);
 }
 
-// Single-CTA twin of the CTA-pair kernel (opt-in, CUML_B200_SOLO_V2=1; NOT yet validated on hardware): the same
-// roles, bf16 correction terms and folded half norms for k <= 128, with cta_group::1 instructions and local
-// barriers.  Generated from the pair kernel's source; once measured it is meant to replace fused_l2_argmin_kernel.
+// Single-CTA twin of the CTA-pair kernel: the same roles, bf16 correction terms and folded half norms for k <= 128,
+// with cta_group::1 instructions and local barriers, plus the row-owner epilogue (ROWOWN) for one centroid tile.  It
+// replaced fused_l2_argmin_kernel as the E-step of these shapes in round 2 (profiles/r02_ab_table.txt).
 template <bool BF16C, int DIST = 0, bool TRUNC = false, bool ROWOWN = false>
 __global__ void __launch_bounds__(PAIR_THREADS, 1)
 fused_l2_argmin_solo_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_hi,
@@ -1760,10 +1762,10 @@ __global__ void prepare_centroids_packed_kernel(const float* __restrict__ C, int
   if (lane == 0) cnh[jj] = (j < k) ? static_cast<float>(0.5 * s) : __int_as_float(0x7f800000);
 }
 
-// The same block-diagonal operands for the opt-in single-CTA tf32 + bf16 kernel (CUML_B200_SOLO_V2=1): hi rounded to
+// The same block-diagonal operands for the tf32 + bf16 kernels (single-CTA twin, tensor-memory kernel): hi rounded to
 // the nearest tf32, bf16 copies of hi / lo for the two correction terms and the tf32-exact pieces of -1/2||c||^2 the
 // fold MMA adds to every accumulator column (row jj of the pieces tile = accumulator column jj).  A separate kernel,
-// so the default row-packed path keeps its measured binary.
+// so the 3xTF32 row-packed path (CUML_B200_BF16C=0) keeps its measured binary.
 __global__ void prepare_centroids_packed_v2_kernel(const float* __restrict__ C, int k, int d, int k_sub,
                                                    float* __restrict__ hi, float* __restrict__ lo,
                                                    float* __restrict__ cnh, __nv_bfloat16* __restrict__ hb,
@@ -2173,7 +2175,7 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
           fused_l2_argmin_tsp_kernel<false><<<grid, PAIR_THREADS, tp.smem, h.stream>>>(tm_x, tm_hi, tm_hb, tm_lb, tm_cn, p);
         }
       } else if (cen.bf16c && !best_out) {
-        // opt-in single-CTA tf32 + bf16 kernel (CUML_B200_SOLO_V2=1) on the row-packed operands.  (It has no best-value
+        // single-CTA tf32 + bf16 kernel on the row-packed operands (CUML_B200_TSP=0, or 65..128 clusters).  (It has no best-value
         // epilogue; the 3xTF32 kernel below reads the same buffers: hi rounded to nearest is still tf32-exact and
         // lo = c - hi is exact.)
         p.fold = (cen.fold && solo_fold_fits(t, cen.k_pad, h.smem_optin)) ? 1 : 0;

@@ -31,7 +31,7 @@ struct TcCentroids {           // per-iteration operand buffers (hi/lo split + h
   int k_sub = 0;  // centroid rows per packed group (k padded to 32/64/128) when pack == 2
 };
 void tc_prepare(Handle& h, const float* C, int k, int d, TcCentroids& out, bool allow_bf16 = true);
-int tc_variant(const Handle& h, int d, int k);   // 1 one-CTA 3xTF32, 2 pair 3xTF32, 3 pair tf32+bf16, 4 A-in-TMEM, 5 one-CTA tf32+bf16 (opt-in)
+int tc_variant(const Handle& h, int d, int k);   // 1 one-CTA 3xTF32, 2 pair 3xTF32, 3 pair tf32+bf16, 5 one-CTA tf32+bf16 (shared-memory or tensor-memory X operand)
 // distance-matrix mode of the same kernels (ML::kmeans::transform): out[i, j] = ||x_i - c_j||^2 (or its sqrt)
 struct TcDistOut {
   float* out         = nullptr;   // [n, k] row-major
