@@ -2101,6 +2101,9 @@ void tc_assign(Handle& h, const float* X, int64_t n, int d, int k, const TcCentr
   CB2_EXPECTS(!dist || cen.pack == 1, "distance-matrix mode does not support row packing");
   CB2_EXPECTS(h.cc_major == 10, "the tcgen05 k-means engine needs an sm_100-class GPU (B200)");
   CB2_EXPECTS(reinterpret_cast<uintptr_t>(X) % 16 == 0, "X must be 16-byte aligned for TMA");
+  // TMA tile coordinates are 32-bit: more rows than that would be mis-addressed silently
+  CB2_EXPECTS(n < (int64_t(1) << 31), "the tcgen05 k-means engine takes at most 2^31 - 1 rows per array; pass the rows as several "
+                                      "partitions (ML::kmeans::fit partition list / chunked predict)");
   if (cen.pack == 2) {
     // two rows per operand row: X viewed as [n/2, 2d]
     const int64_t n2 = n / 2;
